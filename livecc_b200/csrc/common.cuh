@@ -1,0 +1,215 @@
+// Common device helpers for the LiveCC B200 (sm_100a) kernels: PTX wrappers for
+// mbarrier / TMA / tcgen05 / TMEM, bf16 rounding helpers and warp reductions.
+// Everything here is hand-written for sm_100a; there is no fallback path.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace lcc {
+
+typedef __nv_bfloat16 bf16;
+
+// ----------------------------------------------------------------------------
+// bf16 rounding helpers. The reference (HF eager graph, mq2vl.py) materialises a
+// bf16 tensor after every torch op; fused epilogues reproduce those rounding
+// points with rbf(): fp32 -> bf16 (RNE) -> fp32.
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ float rbf(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+__device__ __forceinline__ float bf2f(bf16 x) { return __bfloat162float(x); }
+__device__ __forceinline__ bf16 f2bf(float x) { return __float2bfloat16_rn(x); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
+    __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
+    return __bfloat1622float2(v);
+}
+
+// ----------------------------------------------------------------------------
+// Warp / block reductions
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Block-wide sum; `red` must hold >= 32 floats of shared memory. All threads get the result.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nwarps = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();  // protect `red` reuse
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    float t = (lane < nwarps) ? red[lane] : 0.f;
+    t = warp_sum(t);
+    return t;
+}
+
+// ----------------------------------------------------------------------------
+// Streaming 16-byte loads (weights / KV are read once per step: bypass L1)
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ uint4 ld_stream16(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+// ----------------------------------------------------------------------------
+// Shared-memory address, mbarrier, TMA
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "LAB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra LAB_WAIT;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+__device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* tm) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
+
+// 2-D tiled TMA load global -> shared, completion counted on `bar` (bytes).
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar,
+                                            int c_inner, int c_outer) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer)
+        : "memory");
+}
+
+// ----------------------------------------------------------------------------
+// tcgen05 / TMEM
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_holder, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(smem_holder)),
+                 "r"(ncols)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+// tcgen05.commit: arrive on `bar` once all previously issued MMAs of this thread finished.
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                     smem_u32(bar))
+                 : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], bf16 inputs, fp32 accumulate.
+__device__ __forceinline__ void umma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                             uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// Shared-memory matrix descriptor, K-major operand staged by TMA with SWIZZLE_128B:
+// rows are 128 B (64 bf16) apart, 8-row groups 1024 B apart (SBO), LBO unused (=1),
+// descriptor version 1 (Blackwell), layout type 2 (SWIZZLE_128B).
+// Bit layout follows cute/arch/mma_sm100_desc.hpp (SmemDescriptor).
+__device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);        // start address  [0,14)
+    d |= (uint64_t)1 << 16;                               // LBO (ignored)  [16,30)
+    d |= (uint64_t)(1024 >> 4) << 32;                     // SBO = 1024 B   [32,46)
+    d |= (uint64_t)1 << 46;                               // version = 1    [46,48)
+    d |= (uint64_t)2 << 61;                               // SWIZZLE_128B   [61,64)
+    return d;
+}
+
+// Instruction descriptor for kind::f16, A/B = bf16 K-major, D = fp32 (InstrDescriptor bits).
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int umma_m, int umma_n) {
+    return (1u << 4)      // c_format = F32
+           | (1u << 7)    // a_format = BF16
+           | (1u << 10)   // b_format = BF16
+           | ((uint32_t)(umma_n >> 3) << 17) | ((uint32_t)(umma_m >> 4) << 24);
+}
+
+// TMEM -> registers: 32 lanes x 32 columns of 32-bit; thread i of the warp gets lane (base+i).
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+          "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+          "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]),
+          "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]),
+          "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
+}  // namespace lcc

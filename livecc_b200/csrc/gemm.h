@@ -1,0 +1,34 @@
+// Internal interface of the tcgen05 GEMM core (see gemm_tcgen05.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace lcc {
+
+// Fused epilogues; values are part of the C ABI (include/livecc_b200.h, LCC_EPI_*).
+enum GemmEpilogue {
+    EPI_NONE = 0,            // C = bf16(acc)
+    EPI_BIAS = 1,            // C = bf16(acc + bias)
+    EPI_BIAS_QUICKGELU = 2,  // C = quick_gelu(bf16(acc + bias))          (ViT fc1, mq2vl.py:333-337)
+    EPI_BIAS_GELU = 3,       // C = gelu_erf(bf16(acc + bias))            (merger, mq2vl.py:317-326)
+    EPI_RESIDUAL = 4,        // C = bf16(bf16(acc) + residual)            (o_proj/down_proj, mq2vl.py:645-660)
+    EPI_BIAS_RESIDUAL = 5,   // C = bf16(bf16(acc + bias) + residual)     (ViT proj/fc2, mq2vl.py:479-487)
+    EPI_SWIGLU = 6,          // C[:, j] = bf16(silu(bf16 gate_j) * bf16 up_j), gate/up rows interleaved by 16
+};
+
+struct GemmArgs {
+    const void* A;  // [M, K] bf16, row stride lda
+    const void* B;  // [N, K] bf16, row stride ldb   (nn.Linear weight layout)
+    void* C;        // [M, N] bf16 (EPI_SWIGLU: [M, N/2]), row stride ldc
+    int M, N, K;
+    int lda, ldb, ldc;
+    const void* bias;      // [N] bf16 or null
+    const void* residual;  // [M, N] bf16, row stride ldr, or null
+    int ldr;
+    int epi;
+    int block_n;  // 0 = heuristic, else 64 / 128 / 256
+};
+
+int gemm_bf16_tn(const GemmArgs& a, int num_sms, cudaStream_t stream);
+
+}  // namespace lcc

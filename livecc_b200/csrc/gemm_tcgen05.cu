@@ -1,0 +1,346 @@
+// Persistent, warp-specialised tcgen05 GEMM for sm_100a:
+//     C[M,N] (bf16) = epilogue( A[M,K] (bf16, K-major) x B[N,K]^T (bf16, K-major, nn.Linear layout) )
+//
+// Used for every M >= 16 contraction of the LiveCC hot path: ViT patch-embed / qkv / proj /
+// fc1 / fc2 / merger (mq2vl.py:304-337,385-458) and the decoder prefill projections
+// (mq2vl.py:491-504,539-594, lm_head :1437).
+//
+// Structure (one CTA per SM, 256 threads):
+//   warp 0      : TMA producer  (cp.async.bulk.tensor, SWIZZLE_128B tiles, mbarrier complete_tx)
+//   warp 1      : MMA issuer    (one elected lane issues tcgen05.mma, fp32 accumulators in TMEM)
+//   warp 2      : TMEM allocator
+//   warps 4..7  : epilogue      (tcgen05.ld 32x32b -> registers -> fused epilogue -> bf16 stores)
+// Pipelines: smem ring (full/empty mbarriers, STAGES deep) between TMA and MMA; a 2-deep TMEM
+// accumulator ring (tmem_full/tmem_empty) between MMA and epilogue so the epilogue of tile i
+// overlaps the main loop of tile i+1.
+//
+// The fused epilogues reproduce the reference's bf16 rounding points (one torch op = one rounding).
+#include "common.cuh"
+#include "gemm.h"
+
+namespace lcc {
+
+static constexpr int BLOCK_M = 128;
+static constexpr int BLOCK_K = 64;   // 64 bf16 = 128 B = one SWIZZLE_128B row
+static constexpr int UMMA_K = 16;
+
+template <int BLOCK_N>
+struct GemmCfg {
+    static constexpr int STAGES = (BLOCK_N == 256) ? 4 : ((BLOCK_N == 128) ? 6 : 8);
+    static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+    static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : 2 * BLOCK_N;  // power of two >= 32
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ float quick_gelu_bf16(float x) {
+    // ACT2FN["quick_gelu"]: input * sigmoid(1.702 * input), every op rounded to bf16
+    // (SP/transformers/activations.py:117-123).
+    float t1 = rbf(1.702f * x);
+    float t2 = rbf(1.0f / (1.0f + expf(-t1)));
+    return rbf(x * t2);
+}
+__device__ __forceinline__ float gelu_erf_bf16(float x) {
+    return rbf(0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)));
+}
+__device__ __forceinline__ float silu_bf16(float x) { return rbf(x / (1.0f + expf(-x))); }
+
+template <int BLOCK_N, int EPI>
+__global__ void __launch_bounds__(256, 1)
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                    const __grid_constant__ CUtensorMap tmap_b, bf16* C, int M, int N,
+                    int K, int ldc, const bf16* __restrict__ bias,
+                    const bf16* residual /* may alias C */, int ldr) {
+    using Cfg = GemmCfg<BLOCK_N>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    // SWIZZLE_128B tiles need 1024-byte alignment.
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                               ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full = empty_bar + STAGES;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
+    const int n_tiles = (N + BLOCK_N - 1) / BLOCK_N;
+    const int num_tiles = m_tiles * n_tiles;
+    const int num_k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tensormap(&tmap_a);
+        prefetch_tensormap(&tmap_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full[i], 1);
+            mbar_init(&tmem_empty[i], 4);  // one arrive per epilogue warp
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_holder, Cfg::TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m_blk = tile % m_tiles, n_blk = tile / m_tiles;
+                for (int kb = 0; kb < num_k_blocks; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+                    uint8_t* sb = sa + Cfg::A_BYTES;
+                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                    tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
+                    tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N);
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+            for (int kb = 0; kb < num_k_blocks; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                    const uint32_t sb = sa + Cfg::A_BYTES;
+                    const uint64_t da = make_sw128_kmajor_desc(sa);
+                    const uint64_t db = make_sw128_kmajor_desc(sb);
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        // advance start address by k*32 bytes (>>4 => +2k) inside the swizzle atom
+                        umma_bf16_ss(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
+                                     (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);  // frees the smem slot when the MMAs retire
+                    if (kb == num_k_blocks - 1) umma_commit(&tmem_full[acc]);
+                }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    } else if (warp >= 4) {
+        // ===================== Epilogue =====================
+        const int q = warp - 4;  // TMEM lane quarter this warp may access
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m_blk = tile % m_tiles, n_blk = tile / m_tiles;
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const int row = m_blk * BLOCK_M + q * 32 + lane;
+            const bool row_ok = row < M;
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N / 32; ++c) {
+                uint32_t v[32];
+                const uint32_t taddr =
+                    tmem_base + (uint32_t)(acc * BLOCK_N + c * 32) + ((uint32_t)(q * 32) << 16);
+                tmem_ld_32x32b_x32(taddr, v);
+                tmem_ld_wait();
+                const int col0 = n_blk * BLOCK_N + c * 32;
+                if (EPI == EPI_SWIGLU) {
+                    // Weight rows are interleaved in 32-row groups: 16 gate rows then the 16
+                    // matching up rows. out[j] = bf16(silu_bf16(bf16 gate) * bf16 up)  (mq2vl.py:503)
+                    if (row_ok && col0 < N) {
+                        const int ocol0 = (col0 >> 5) << 4;
+                        uint32_t o[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            float g0 = rbf(__uint_as_float(v[2 * j])), g1 = rbf(__uint_as_float(v[2 * j + 1]));
+                            float u0 = rbf(__uint_as_float(v[16 + 2 * j])), u1 = rbf(__uint_as_float(v[16 + 2 * j + 1]));
+                            o[j] = pack_bf16x2(silu_bf16(g0) * u0, silu_bf16(g1) * u1);
+                        }
+                        uint4* dst = reinterpret_cast<uint4*>(C + (size_t)row * ldc + ocol0);
+                        dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+                        dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+                    }
+                } else {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {  // 4 groups of 8 columns (16 B of bf16 each)
+                        const int col = col0 + g * 8;
+                        if (row_ok && col < N) {
+                            float x[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v[g * 8 + j]);
+                            if (EPI == EPI_BIAS || EPI == EPI_BIAS_QUICKGELU || EPI == EPI_BIAS_GELU ||
+                                EPI == EPI_BIAS_RESIDUAL) {
+                                const uint4 bb = *reinterpret_cast<const uint4*>(bias + col);
+                                const uint32_t bw[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    float2 f = unpack_bf16x2(bw[j]);
+                                    x[2 * j] += f.x;
+                                    x[2 * j + 1] += f.y;
+                                }
+                            }
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) x[j] = rbf(x[j]);
+                            if (EPI == EPI_BIAS_QUICKGELU) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) x[j] = quick_gelu_bf16(x[j]);
+                            } else if (EPI == EPI_BIAS_GELU) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) x[j] = gelu_erf_bf16(x[j]);
+                            } else if (EPI == EPI_RESIDUAL || EPI == EPI_BIAS_RESIDUAL) {
+                                const uint4 rr =
+                                    *reinterpret_cast<const uint4*>(residual + (size_t)row * ldr + col);
+                                const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    float2 f = unpack_bf16x2(rw[j]);
+                                    x[2 * j] += f.x;
+                                    x[2 * j + 1] += f.y;
+                                }
+                            }
+                            uint4 o;
+                            o.x = pack_bf16x2(x[0], x[1]);
+                            o.y = pack_bf16x2(x[2], x[3]);
+                            o.z = pack_bf16x2(x[4], x[5]);
+                            o.w = pack_bf16x2(x[6], x[7]);
+                            *reinterpret_cast<uint4*>(C + (size_t)row * ldc + col) = o;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+// ----------------------------------------------------------------------------
+// Host side
+// ----------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) !=
+                cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            return nullptr;
+        fn = reinterpret_cast<PFN_encodeTiled>(p);
+    }
+    return fn;
+}
+
+// 2-D bf16 row-major [rows, cols] with row stride ld (elements); box = [box_rows, 64 cols], SW128.
+int make_tmap_bf16_2d(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t cols, int64_t ld,
+                      int box_rows) {
+    PFN_encodeTiled fn = get_encode_fn();
+    if (!fn) return -1;
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride,
+                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : -2;
+}
+
+template <int BLOCK_N, int EPI>
+static int launch_cfg(const GemmArgs& a, int num_sms, cudaStream_t stream) {
+    using Cfg = GemmCfg<BLOCK_N>;
+    CUtensorMap ta, tb;
+    if (make_tmap_bf16_2d(&ta, a.A, a.M, a.K, a.lda, BLOCK_M)) return -10;
+    if (make_tmap_bf16_2d(&tb, a.B, a.N, a.K, a.ldb, BLOCK_N)) return -11;
+    auto kern = gemm_bf16_tn_kernel<BLOCK_N, EPI>;
+    static bool attr_set = false;  // per template instantiation
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 Cfg::SMEM_BYTES) != cudaSuccess)
+            return -12;
+        attr_set = true;
+    }
+    const int m_tiles = (a.M + BLOCK_M - 1) / BLOCK_M, n_tiles = (a.N + BLOCK_N - 1) / BLOCK_N;
+    const int tiles = m_tiles * n_tiles;
+    const int grid = tiles < num_sms ? tiles : num_sms;
+    kern<<<grid, 256, Cfg::SMEM_BYTES, stream>>>(ta, tb, (bf16*)a.C, a.M, a.N, a.K, a.ldc,
+                                                 (const bf16*)a.bias, (const bf16*)a.residual,
+                                                 a.ldr);
+    return cudaGetLastError() == cudaSuccess ? 0 : -13;
+}
+
+template <int BLOCK_N>
+static int launch_epi(const GemmArgs& a, int num_sms, cudaStream_t stream) {
+    switch (a.epi) {
+        case EPI_NONE: return launch_cfg<BLOCK_N, EPI_NONE>(a, num_sms, stream);
+        case EPI_BIAS: return launch_cfg<BLOCK_N, EPI_BIAS>(a, num_sms, stream);
+        case EPI_BIAS_QUICKGELU: return launch_cfg<BLOCK_N, EPI_BIAS_QUICKGELU>(a, num_sms, stream);
+        case EPI_BIAS_GELU: return launch_cfg<BLOCK_N, EPI_BIAS_GELU>(a, num_sms, stream);
+        case EPI_RESIDUAL: return launch_cfg<BLOCK_N, EPI_RESIDUAL>(a, num_sms, stream);
+        case EPI_BIAS_RESIDUAL: return launch_cfg<BLOCK_N, EPI_BIAS_RESIDUAL>(a, num_sms, stream);
+        case EPI_SWIGLU: return launch_cfg<BLOCK_N, EPI_SWIGLU>(a, num_sms, stream);
+    }
+    return -14;
+}
+
+int gemm_bf16_tn(const GemmArgs& a, int num_sms, cudaStream_t stream) {
+    if (a.M <= 0 || a.N <= 0 || a.K <= 0) return -1;
+    if ((a.K % 8) || (a.lda % 8) || (a.ldb % 8) || (a.N % 8) || (a.ldc % 8)) return -2;
+    if (a.epi == EPI_SWIGLU && (a.N % 32)) return -3;
+    if ((a.epi == EPI_RESIDUAL || a.epi == EPI_BIAS_RESIDUAL) && (!a.residual || (a.ldr % 8))) return -4;
+    if ((a.epi == EPI_BIAS || a.epi == EPI_BIAS_QUICKGELU || a.epi == EPI_BIAS_GELU ||
+         a.epi == EPI_BIAS_RESIDUAL) && !a.bias) return -5;
+    // Tile-shape heuristic: widest N tile that still yields >= one wave of CTAs.
+    int block_n = a.block_n;
+    if (block_n == 0) {
+        const int m_tiles = (a.M + BLOCK_M - 1) / BLOCK_M;
+        if (m_tiles * ((a.N + 255) / 256) >= num_sms) block_n = 256;
+        else if (m_tiles * ((a.N + 127) / 128) >= num_sms || a.N < 64 * 2) block_n = 128;
+        else block_n = 64;
+        if (a.N <= 64) block_n = 64;
+    }
+    switch (block_n) {
+        case 256: return launch_epi<256>(a, num_sms, stream);
+        case 128: return launch_epi<128>(a, num_sms, stream);
+        case 64: return launch_epi<64>(a, num_sms, stream);
+    }
+    return -6;
+}
+
+}  // namespace lcc
