@@ -1,33 +1,41 @@
 /*
- * livecc_b200.h — C ABI of liblivecc_sm100a.so, the B200-native (sm_100a) kernels behind LiveCC's
- * per-chunk encode -> prefill -> decode hot path.
+ * livecc_b200.h — C ABI of liblivecc_sm100a.so, the B200-native (sm_100a) kernels and model runtime
+ * behind LiveCC's per-chunk encode -> prefill -> decode hot path.
  *
- * The reference (showlab/livecc) has no native/FFI boundary of its own: the path sits behind
- * Python surfaces (REF/demo/infer.py:43-50,165-174 -> transformers Qwen2VLForConditionalGeneration).
- * This header is therefore the boundary *we* define one level below that surface;
+ * The reference (showlab/livecc) has no native/FFI boundary of its own: the path sits behind Python
+ * surfaces (REF/demo/infer.py:43-50,165-174 -> transformers Qwen2VLForConditionalGeneration). This
+ * header is therefore the boundary *we* define one level below that surface;
  * each entry point cites the reference interface (file:line) whose arithmetic it replaces.
- * `mq2vl.py` = transformers/models/qwen2_vl/modeling_qwen2_vl.py (transformers 5.5.0).
+ *   mq2vl.py     = transformers/models/qwen2_vl/modeling_qwen2_vl.py   (transformers 5.5.0)
+ *   gen/utils.py = transformers/generation/utils.py
+ *   REF/         = showlab/livecc
  *
  * Conventions
- *   - All data pointers are DEVICE pointers owned by the caller (PyTorch storage in our host code).
+ *   - All data pointers are DEVICE pointers owned by the caller (PyTorch storage in our host code);
+ *     the library never allocates device memory.
  *   - Every call is asynchronous on `stream`; nothing synchronises the device.
  *   - Return value: 0 on success, negative on error; lcc_last_error(ctx) returns a message.
  *   - A ctx is bound to one device and one host thread at a time; no hidden globals.
  *   - bf16 everywhere unless the name says otherwise; "bf16 rounding points" follow the reference's
  *     eager graph (one torch op = one rounding).
+ *   - The paged KV cache uses pages of LCC_PAGE_SIZE tokens; a layer's K (or V) pool is
+ *     [num_pages, kv_heads, LCC_PAGE_SIZE, 128] bf16.
  */
 #ifndef LIVECC_B200_H
 #define LIVECC_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
 extern "C" {
 #endif
 
-#define LCC_ABI_VERSION 1
+#define LCC_ABI_VERSION 2
+#define LCC_PAGE_SIZE 64
 
 typedef struct lcc_ctx lcc_ctx;
+typedef struct lcc_model lcc_model;
 typedef void* lcc_stream_t; /* cudaStream_t */
 
 /* GEMM epilogues (lcc_gemm_bf16) */
@@ -39,25 +47,189 @@ typedef void* lcc_stream_t; /* cudaStream_t */
 #define LCC_EPI_BIAS_RESIDUAL 5   /* ViT proj / fc2 + residual: mq2vl.py:479-487 */
 #define LCC_EPI_SWIGLU 6          /* gate|up (16-row interleaved) -> silu(gate)*up: mq2vl.py:502-504 */
 
+/* Device-side per-stream scalars (int32[LCC_SC_COUNT]); they replace the host-side loop state of
+ * GenerationMixin._sample (gen/utils.py:2743-2805) so that a generate() call needs no host sync. */
+#define LCC_SC_KV_LEN 0       /* tokens in the KV cache */
+#define LCC_SC_ROPE_POS 1     /* position id of the next token to forward = kv_len + rope_delta (mq2vl.py:1212-1222) */
+#define LCC_SC_FINISHED 2     /* non-zero once EOS was produced or max_new_tokens reached */
+#define LCC_SC_N_GENERATED 3  /* tokens generated in this generate() call */
+#define LCC_SC_SEQ_LEN 4      /* ids in the sequence buffer (history + generated) */
+#define LCC_SC_LAST_TOKEN 5
+#define LCC_SC_VIDEO_TOKENS 6 /* number of video placeholder ids seen by the last lcc_prefill (mq2vl.py:1169-1175 check) */
+#define LCC_SC_COUNT 8
+
 int lcc_abi_version(void);
 
-/* Context. lcc_create returns NULL unless `device` is an sm_100 GPU (there is no fallback path). */
+/* ---- context ---------------------------------------------------------------------------- */
+/* lcc_create returns NULL unless `device` is an sm_100 GPU (there is no fallback path). */
 lcc_ctx* lcc_create(int device);
 void lcc_destroy(lcc_ctx* ctx);
 const char* lcc_last_error(lcc_ctx* ctx);
 int lcc_num_sms(lcc_ctx* ctx);
 
-/*
- * C[M,N] = epilogue(A[M,K] x B[N,K]^T), bf16 in, fp32 accumulate (tcgen05/TMEM), bf16 out.
+/* ---- op level (each is unit-tested against the oracle) ---------------------------------- */
+
+/* C[M,N] = epilogue(A[M,K] x B[N,K]^T), bf16 in, fp32 accumulate (tcgen05/TMEM), bf16 out.
  * Replaces every nn.Linear / Conv3d-as-GEMM call with M >= 16 on the path:
  * mq2vl.py:304-310 (patch embed), :385,:401-403,:456 (ViT qkv/proj), :329-337 (ViT MLP),
- * :317-326 (merger), :539-541,:559-565,:593 (decoder q/k/v/o), :502-504 (MLP), :1437-1438 (lm_head).
- * K, N and all leading dimensions must be multiples of 8 elements.
- * block_n: 0 = heuristic, else 64/128/256.
- */
+ * :317-326 (merger), :539-541,:559-565,:593 (decoder q/k/v/o), :502-504 (MLP).
+ * K, N and all leading dimensions must be multiples of 8 elements. block_n: 0 = heuristic, else 64/128/256. */
 int lcc_gemm_bf16(lcc_ctx* ctx, const void* A, int lda, const void* B, int ldb, void* C, int ldc,
                   int M, int N, int K, const void* bias, const void* residual, int ldr, int epilogue,
                   int block_n, lcc_stream_t stream);
+
+/* hidden_states.to(bf16) of the f32 patch rows (mq2vl.py:309). */
+int lcc_cast_f32_bf16(lcc_ctx* ctx, const float* in, void* out, int64_t n, lcc_stream_t stream);
+
+/* nn.LayerNorm(dim, eps) over rows (ViT norm1/norm2/ln_q, mq2vl.py:464-465,317). */
+int lcc_layernorm(lcc_ctx* ctx, const void* x, int ldx, const void* w, const void* b, void* y, int ldy,
+                  int rows, int dim, float eps, lcc_stream_t stream);
+
+/* Qwen2VLRMSNorm over rows (mq2vl.py:126-131). */
+int lcc_rmsnorm(lcc_ctx* ctx, const void* x, int ldx, const void* w, void* y, int ldy, int rows, int dim,
+                float eps, lcc_stream_t stream);
+
+/* ViT 2-D rotary: table for a (t,h,w) grid in merge-window patch order (rot_pos_emb, mq2vl.py:725-752;
+ * inv_freq[head_dim/4] fp32 from VisionRotaryEmbedding :271-284), then in-place application to the
+ * q and k thirds of qkv [N, 3*heads*head_dim] (apply_rotary_pos_emb_vision, :257-268). */
+int lcc_vit_rope_table(lcc_ctx* ctx, float* cos_t, float* sin_t, int t, int h, int w, int merge,
+                       int head_dim, const float* inv_freq, lcc_stream_t stream);
+int lcc_vit_rope_apply(lcc_ctx* ctx, void* qkv, int ld, const float* cos_t, const float* sin_t, int N,
+                       int heads, int head_dim, lcc_stream_t stream);
+
+/* VisionAttention core (mq2vl.py:392-454): non-causal attention inside each cu_seqlens segment,
+ * q/k/v read from qkv [N, 3*heads*80] (already rotated), out [N, heads*80]. cu_seqlens: device int32[nseg+1]. */
+int lcc_vit_attention(lcc_ctx* ctx, const void* qkv, int ld, void* out, int o_ld, const int32_t* cu_seqlens,
+                      int nseg, int max_seg_len, int heads, int head_dim, lcc_stream_t stream);
+
+/* embed_tokens gather + masked_scatter of the video features (mq2vl.py:1255-1272).
+ * ids: device int64[S]; rank_ws: device int32[S+1] scratch (last entry receives the video-token count). */
+int lcc_embed_gather(lcc_ctx* ctx, const int64_t* ids, const void* table, const void* video_embeds,
+                     int64_t video_token_id, void* out, int32_t* rank_ws, int S, int H, int64_t vocab,
+                     lcc_stream_t stream);
+
+/* M-RoPE (mq2vl.py:188-201,212-254) on the q and k parts of qkv [S, (Hq+2Hkv)*128] (q rotated in
+ * place) and append of rotated k / v to the paged cache at positions kv_start..kv_start+S-1
+ * (DynamicLayer.update, cache_utils.py:102-121). pos3: device int32[3,S]; inv_freq: device f32[64]. */
+int lcc_mrope_kv_write(lcc_ctx* ctx, void* qkv, int ld, const int32_t* pos3, int S, const float* inv_freq,
+                       int sec_t, int sec_h, int Hq, int Hkv, void* k_cache, void* v_cache,
+                       const int32_t* page_table, int kv_start, lcc_stream_t stream);
+
+/* Causal GQA attention of S new tokens over past+S cached tokens (Qwen2VLAttention core,
+ * mq2vl.py:572-594; eager_attention_forward :353-375). q: rotated rows of qkv; out [S, Hq*128]. */
+int lcc_attn_prefill(lcc_ctx* ctx, const void* q, int q_ld, const void* k_cache, const void* v_cache,
+                     const int32_t* page_table, int Hq, int Hkv, int S, int past, void* out, int o_ld,
+                     lcc_stream_t stream);
+
+/* One-token attention: RoPE of q, RoPE + append of the new k/v at slot scalars[LCC_SC_KV_LEN],
+ * split-KV attention over the paged cache and merge. qkv: raw projections(+bias) of the new token.
+ * part_o: f32[nsplit,Hq,128], part_ml: f32[nsplit,Hq,2] scratch; out: bf16[Hq*128]. */
+int lcc_attn_decode(lcc_ctx* ctx, void* qkv, void* k_cache, void* v_cache, const int32_t* page_table,
+                    const int32_t* scalars, const float* inv_freq, int Hq, int Hkv, int nsplit, float* part_o,
+                    float* part_ml, void* out, lcc_stream_t stream);
+
+/* Decode-step projections (M = 1), each fused with its neighbours in the layer
+ * (Qwen2VLDecoderLayer.forward, mq2vl.py:613-662). `scalars` may be NULL (no early-exit flag). */
+int lcc_gemv_norm_bias(lcc_ctx* ctx, const void* W, int ldw, const void* x, const void* norm_w, float eps,
+                       const void* bias, void* out, int N, int K, const int32_t* scalars, lcc_stream_t stream);
+int lcc_gemv_residual(lcc_ctx* ctx, const void* W, int ldw, const void* x, void* h_inout, int N, int K,
+                      const int32_t* scalars, lcc_stream_t stream);
+int lcc_gemv_norm_swiglu(lcc_ctx* ctx, const void* W_gate_up, int ldw, const void* x, const void* norm_w,
+                         float eps, void* act, int N2, int K, const int32_t* scalars, lcc_stream_t stream);
+/* final norm + lm_head on one token -> fp32 logits (mq2vl.py:905,1437-1438; gen/utils.py:2762). */
+int lcc_gemv_norm_logits(lcc_ctx* ctx, const void* W, int ldw, const void* x, const void* norm_w, float eps,
+                         float* logits, float* logits_copy, int N, int K, const int32_t* scalars,
+                         lcc_stream_t stream);
+
+/* Logits processing + greedy token selection + stream bookkeeping (gen/utils.py:2762-2805;
+ * logits_process.py:407-410; REF/demo/infer.py:10-23). */
+typedef struct {
+    float repetition_penalty; /* 1.0 = off */
+    int32_t thr_token;        /* ThresholdLogitsProcessor token id, < 0 = off */
+    float thr_base, thr_step;
+    int32_t eos_token_id;
+    int32_t max_new_tokens;
+} lcc_sampling;
+
+int lcc_sample_greedy(lcc_ctx* ctx, const float* logits_raw, float* logits_proc, int V, int64_t* seq,
+                      int32_t* scalars, const lcc_sampling* sp, int advance_kv, const void* embed, void* h,
+                      int H, lcc_stream_t stream);
+
+/* ---- model level (native runtime: one call launches a whole phase) ---------------------- */
+typedef struct {
+    /* vision (Qwen2VLVisionConfig) */
+    int32_t vit_depth, vit_dim, vit_heads, vit_mlp, patch_dim, merge, vit_out;
+    /* text (Qwen2VLTextConfig) */
+    int32_t hidden, inter, layers, q_heads, kv_heads, vocab;
+    float rms_eps, rope_theta;
+    int32_t mrope_t, mrope_h; /* mrope_section[0], [1] */
+    int64_t video_token_id;
+} lcc_model_config;
+
+typedef struct {
+    const void *norm1_w, *norm1_b, *norm2_w, *norm2_b;
+    const void *qkv_w, *qkv_b, *proj_w, *proj_b, *fc1_w, *fc1_b, *fc2_w, *fc2_b;
+} lcc_vit_block_weights;
+
+typedef struct {
+    const void *ln1_w, *qkv_w, *qkv_b, *o_w, *ln2_w, *gate_up_w /* 16-row interleaved */, *down_w;
+} lcc_layer_weights;
+
+typedef struct {
+    const void* patch_w; /* [vit_dim, patch_dim] */
+    const lcc_vit_block_weights* vit_blocks;
+    const void *merger_ln_w, *merger_ln_b, *merger_fc1_w, *merger_fc1_b, *merger_fc2_w, *merger_fc2_b;
+    const void* embed; /* [vocab, hidden] */
+    const lcc_layer_weights* layers;
+    const void* final_norm_w;
+    const void* lm_head; /* [vocab, hidden] */
+    /* fp32 rotary tables computed by the host exactly as the reference does:
+     * text_inv_freq[64]  = 1/theta^(2i/128)            (mq2vl.py:175-183)
+     * vit_inv_freq[hd/4] = 1/10000^(2i/(hd/2))         (mq2vl.py:274-279) */
+    const float* text_inv_freq;
+    const float* vit_inv_freq;
+} lcc_model_weights;
+
+/* One video stream's device state (all caller-owned). */
+typedef struct {
+    void* k_pool;               /* [layers][num_pages][kv_heads][LCC_PAGE_SIZE][128] bf16 */
+    void* v_pool;
+    int64_t layer_stride;       /* elements between consecutive layers of a pool */
+    const int32_t* page_table;  /* device int32: logical page -> physical page */
+    int32_t* scalars;           /* device int32[LCC_SC_COUNT] */
+    int64_t* seq;               /* device int64[cap]: input ids then generated ids */
+} lcc_stream_state;
+
+lcc_model* lcc_model_create(lcc_ctx* ctx, const lcc_model_config* cfg, const lcc_model_weights* w);
+void lcc_model_destroy(lcc_model* m);
+
+/* Scratch bytes needed by the calls below for at most `max_patches` ViT rows / `max_tokens` prefill rows,
+ * and binding of a caller-owned scratch buffer of that size to the model. */
+size_t lcc_workspace_bytes(const lcc_model* m, int max_patches, int max_tokens);
+int lcc_model_bind_workspace(lcc_model* m, void* ws, size_t ws_bytes, int max_patches, int max_tokens);
+
+/* Qwen2VisionTransformerPretrainedModel.forward (mq2vl.py:757-795) for one video of grid (t,h,w):
+ * pixel_values f32 [t*h*w, patch_dim] -> out bf16 [t*h*w/merge^2, vit_out]. */
+int lcc_vit_forward(lcc_model* m, const float* pixel_values, int t, int h, int w, void* out,
+                    lcc_stream_t stream);
+
+/* Prefill of S new tokens (Qwen2VLModel.forward + lm_head on the last token, mq2vl.py:1230-1300,
+ * 828-910, 1437) followed by the first token selection. ids: device int64[S] (the new tokens);
+ * pos3: device int32[3,S]; video_embeds: bf16 [n_video_tokens, hidden] or NULL; past = tokens already
+ * cached. Host must have set scalars {KV_LEN = past+S, ROPE_POS, FINISHED=0, N_GENERATED=0, SEQ_LEN}. */
+int lcc_prefill(lcc_model* m, const lcc_stream_state* st, const int64_t* ids, const int32_t* pos3, int S,
+                int past, const void* video_embeds, const lcc_sampling* sp, lcc_stream_t stream);
+
+/* n_steps x (one-token forward + token selection) (the loop body of _sample, gen/utils.py:2743-2805).
+ * No-ops once scalars[LCC_SC_FINISHED] is set. Capturable in a CUDA graph. nsplit: KV splits (1..64). */
+int lcc_decode_steps(lcc_model* m, const lcc_stream_state* st, int n_steps, int nsplit, const lcc_sampling* sp,
+                     lcc_stream_t stream);
+
+/* Debug/parity hooks: byte offsets of buffers inside the bound workspace. */
+#define LCC_WS_PREFILL_HIDDEN 0 /* bf16 [S, hidden] residual stream of the last prefill */
+#define LCC_WS_LOGITS 1         /* f32 [vocab] raw logits of the last token selection */
+#define LCC_WS_DECODE_HIDDEN 2  /* bf16 [hidden] embedding row / residual stream of the decode step */
+size_t lcc_ws_offset(const lcc_model* m, int which);
 
 #ifdef __cplusplus
 }

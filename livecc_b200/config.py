@@ -63,7 +63,21 @@ class LiveCCConfig:
     bos_token_id: int = 151643
     eos_token_id: int = 151645
     pad_token_id: int = 151643
+    im_start_token_id: int = 151644
+    newline_token_id: int = 198
     name: str = "livecc-7b"
+
+    def special_token_ids(self) -> dict:
+        """Token string -> id for the special tokens the chat template emits."""
+        return {
+            "<|endoftext|>": self.bos_token_id,
+            "<|im_start|>": self.im_start_token_id,
+            "<|im_end|>": self.eos_token_id,
+            "<|vision_start|>": self.vision_start_token_id,
+            "<|vision_end|>": self.vision_end_token_id,
+            "<|image_pad|>": self.image_token_id,
+            "<|video_pad|>": self.video_token_id,
+        }
 
     # -- factories --------------------------------------------------------------------------
     @staticmethod
@@ -80,7 +94,20 @@ class LiveCCConfig:
                                    num_attention_heads=14, num_key_value_heads=2),
             vision_config=VisionConfig(depth=vit_depth, embed_dim=320, hidden_size=1792, num_heads=4),
             name=f"livecc-small-l{layers}v{vit_depth}",
-        )
+        ).with_vocab(16384)
+
+    def with_vocab(self, vocab_size: int) -> "LiveCCConfig":
+        """Shrinks the vocabulary (CPU-oracle speed) and relocates the special ids to its top."""
+        self.text_config.vocab_size = vocab_size
+        top = vocab_size - 32
+        self.bos_token_id = self.pad_token_id = top + 0
+        self.im_start_token_id = top + 1
+        self.eos_token_id = top + 2
+        self.vision_start_token_id = top + 9
+        self.vision_end_token_id = top + 10
+        self.image_token_id = top + 12
+        self.video_token_id = top + 13
+        return self
 
     def validate(self) -> None:
         t, v = self.text_config, self.vision_config

@@ -1,0 +1,560 @@
+// Attention kernels of the LiveCC path (round-1 implementation: mma.sync.m16n8k16 bf16 flash-style
+// kernels with cp.async-staged K/V tiles; the tcgen05 version is the next step).
+//
+//  * flash_fwd_kernel<D, CAUSAL, PAGED>: multi-row attention.
+//      - ViT (D=80, non-causal, K/V read from the fused qkv buffer, one cu_seqlens segment per
+//        blockIdx.z):  VisionAttention, mq2vl.py:392-454.
+//      - decoder prefill (D=128, causal over past+new, K/V read from the paged cache, the G query
+//        heads of a KV group packed into the row dimension so a K/V tile is loaded once per group):
+//        Qwen2VLAttention, mq2vl.py:572-594 + eager_attention_forward :353-375.
+//  * attn_decode_kernel: one new token, split-KV over the paged cache; the 7 query heads of a KV
+//    group form one 16-row MMA tile; fuses the 1-D RoPE of q, the RoPE + append of the new k/v.
+//  * attn_combine_kernel: merges the split-KV partials.
+// Softmax statistics are fp32; P is rounded to bf16 before P·V (as the reference does, :370).
+#include "common.cuh"
+#include "ops.h"
+
+namespace lcc {
+
+// ---------------------------------------------------------------------------------------------
+// small PTX helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool pred) {
+    const uint32_t s = smem_u32(smem);
+    const int sz = pred ? 16 : 0;  // src-size 0 => zero fill
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void ldmatrix_x4(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3,
+                                            const void* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                 : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3,
+                                                  const void* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                 : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+        "{%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// One warp: S[16 x 16*NT16] = Q_frag (16 x D) * K_tile^T.  K_tile rows (tokens) start at `ks`
+// (row stride LDS elements); NT16 groups of 16 tokens.
+template <int D, int LDS, int NT16>
+__device__ __forceinline__ void warp_qk(const uint32_t (&qf)[D / 16][4], const bf16* ks, int lane,
+                                        float (&s)[NT16 * 2][4]) {
+#pragma unroll
+    for (int n = 0; n < NT16 * 2; ++n)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s[n][j] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < D / 16; ++kk) {
+#pragma unroll
+        for (int nt = 0; nt < NT16; ++nt) {
+            // x4: matrices (tok 0-7,k 0-7) (tok 0-7,k 8-15) (tok 8-15,k 0-7) (tok 8-15,k 8-15)
+            const int mat = lane >> 3, r = lane & 7;
+            const bf16* p = ks + (size_t)(nt * 16 + (mat >> 1) * 8 + r) * LDS + kk * 16 + (mat & 1) * 8;
+            uint32_t b0, b1, b2, b3;
+            ldmatrix_x4(b0, b1, b2, b3, p);
+            mma_bf16_16816(s[nt * 2], qf[kk], b0, b1);
+            mma_bf16_16816(s[nt * 2 + 1], qf[kk], b2, b3);
+        }
+    }
+}
+
+// One warp: O[16 x D] += P (16 x 16*NT16, bf16 A fragments) * V_tile (tokens x D).
+template <int D, int LDS, int NT16>
+__device__ __forceinline__ void warp_pv(const uint32_t (&pf)[NT16][4], const bf16* vs, int lane,
+                                        float (&o)[D / 8][4]) {
+#pragma unroll
+    for (int kt = 0; kt < NT16; ++kt) {
+#pragma unroll
+        for (int dn = 0; dn < D / 16; ++dn) {
+            // trans x4: matrices (tok 0-7,d 0-7) (tok 8-15,d 0-7) (tok 0-7,d 8-15) (tok 8-15,d 8-15)
+            const int mat = lane >> 3, r = lane & 7;
+            const bf16* p = vs + (size_t)(kt * 16 + (mat & 1) * 8 + r) * LDS + dn * 16 + (mat >> 1) * 8;
+            uint32_t b0, b1, b2, b3;
+            ldmatrix_x4_trans(b0, b1, b2, b3, p);
+            mma_bf16_16816(o[dn * 2], pf[kt], b0, b1);
+            mma_bf16_16816(o[dn * 2 + 1], pf[kt], b2, b3);
+        }
+    }
+}
+
+// Online softmax update for one warp tile. s: raw scores (fp32) of 16 rows x 16*NT16 columns,
+// already masked with -inf. Each thread owns rows (lane/4) and (lane/4 + 8). Converts P to bf16
+// A-fragments and rescales O.
+template <int D, int NT16>
+__device__ __forceinline__ void softmax_step(float (&s)[NT16 * 2][4], float scale_log2, float (&m)[2],
+                                             float (&l)[2], float (&o)[D / 8][4], uint32_t (&pf)[NT16][4]) {
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int n = 0; n < NT16 * 2; ++n) {
+        mx[0] = fmaxf(mx[0], fmaxf(s[n][0], s[n][1]));
+        mx[1] = fmaxf(mx[1], fmaxf(s[n][2], s[n][3]));
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+    }
+    float mnew[2], corr[2], msub[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        mnew[r] = fmaxf(m[r], mx[r]);
+        msub[r] = (mnew[r] == -INFINITY) ? 0.f : mnew[r] * scale_log2;
+        corr[r] = (m[r] == -INFINITY) ? 0.f : exp2f(m[r] * scale_log2 - msub[r]);
+        m[r] = mnew[r];
+    }
+    float rs[2] = {0.f, 0.f};
+#pragma unroll
+    for (int n = 0; n < NT16 * 2; ++n) {
+        s[n][0] = exp2f(s[n][0] * scale_log2 - msub[0]);
+        s[n][1] = exp2f(s[n][1] * scale_log2 - msub[0]);
+        s[n][2] = exp2f(s[n][2] * scale_log2 - msub[1]);
+        s[n][3] = exp2f(s[n][3] * scale_log2 - msub[1]);
+        rs[0] += s[n][0] + s[n][1];
+        rs[1] += s[n][2] + s[n][3];
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) l[r] = l[r] * corr[r] + rs[r];  // per-thread partial row sums
+#pragma unroll
+    for (int d = 0; d < D / 8; ++d) {
+        o[d][0] *= corr[0]; o[d][1] *= corr[0];
+        o[d][2] *= corr[1]; o[d][3] *= corr[1];
+    }
+#pragma unroll
+    for (int kt = 0; kt < NT16; ++kt) {
+        pf[kt][0] = pack_bf16x2(s[kt * 2][0], s[kt * 2][1]);
+        pf[kt][1] = pack_bf16x2(s[kt * 2][2], s[kt * 2][3]);
+        pf[kt][2] = pack_bf16x2(s[kt * 2 + 1][0], s[kt * 2 + 1][1]);
+        pf[kt][3] = pack_bf16x2(s[kt * 2 + 1][2], s[kt * 2 + 1][3]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Multi-row flash attention. CTA = 4 warps = 64 packed rows; KV tiles of 64 tokens.
+// Packed row r of KV group g maps to (query position r / G, query head g*G + r % G).
+// ---------------------------------------------------------------------------------------------
+struct FlashParams {
+    const bf16* q;      // [S, *] row stride q_ld; head h at column h*D
+    int q_ld;
+    const bf16* k;      // contiguous mode: row stride kv_ld, head g at column g*D
+    const bf16* v;
+    int kv_ld;
+    const bf16* kc;     // paged mode: [pages, Hkv, P=64, D]
+    const bf16* vc;
+    const int* page_table;
+    int Hkv;
+    bf16* out;          // [S, *] row stride o_ld; head h at column h*D
+    int o_ld;
+    const int* cu_seqlens;  // contiguous mode: segment boundaries (blockIdx.z); null => one segment [0,S)
+    int S;              // number of query positions (paged mode / single segment)
+    int past;           // paged+causal: number of cached tokens before the S new ones
+    int G;              // query heads per KV head
+    float scale_log2;   // softmax scale * log2(e)
+};
+
+template <int D, bool CAUSAL, bool PAGED>
+__global__ void __launch_bounds__(128) flash_fwd_kernel(const FlashParams p) {
+    constexpr int LDS = D + 8;
+    constexpr int BM = 64, BN = 64;
+    extern __shared__ __align__(16) uint8_t smem_attn[];
+    bf16* sq = reinterpret_cast<bf16*>(smem_attn);           // [64][LDS]
+    bf16* sk = sq + BM * LDS;                                 // [2][64][LDS]
+    bf16* sv = sk + 2 * BN * LDS;                             // [2][64][LDS]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.y;  // KV head / group
+    int seg_start = 0, seg_len = p.S;
+    if (!PAGED && p.cu_seqlens) {
+        seg_start = p.cu_seqlens[blockIdx.z];
+        seg_len = p.cu_seqlens[blockIdx.z + 1] - seg_start;
+    }
+    const int rows_total = seg_len * p.G;
+    const int row0 = blockIdx.x * BM;
+    if (row0 >= rows_total) return;
+
+    // ---- stage Q tile (zero-filled beyond rows_total) ----
+    for (int i = threadIdx.x; i < BM * (D / 8); i += 128) {
+        const int r = i / (D / 8), c = i % (D / 8);
+        const int rr = row0 + r;
+        const bool ok = rr < rows_total;
+        const int pos = ok ? rr / p.G : 0, hq = g * p.G + (ok ? rr % p.G : 0);
+        cp_async16(sq + r * LDS + c * 8, p.q + (size_t)(seg_start + pos) * p.q_ld + (size_t)hq * D + c * 8, ok);
+    }
+    cp_async_commit();
+
+    // KV range for this CTA
+    int kv_len = PAGED ? (p.past + p.S) : seg_len;
+    if (CAUSAL) {
+        const int last_row = min(row0 + BM, rows_total) - 1;
+        kv_len = min(kv_len, p.past + last_row / p.G + 1);
+    }
+    const int n_tiles = (kv_len + BN - 1) / BN;
+
+    auto load_kv = [&](int tile, int buf) {
+        bf16* dk = sk + buf * BN * LDS;
+        bf16* dv = sv + buf * BN * LDS;
+        const int t0 = tile * BN;
+        const bf16 *gk, *gv;
+        size_t stride;
+        if (PAGED) {
+            const int page = p.page_table[tile];
+            gk = p.kc + ((size_t)page * p.Hkv + g) * BN * D;
+            gv = p.vc + ((size_t)page * p.Hkv + g) * BN * D;
+            stride = D;
+        } else {
+            gk = p.k + (size_t)(seg_start + t0) * p.kv_ld + (size_t)g * D;
+            gv = p.v + (size_t)(seg_start + t0) * p.kv_ld + (size_t)g * D;
+            stride = p.kv_ld;
+        }
+        for (int i = threadIdx.x; i < BN * (D / 8); i += 128) {
+            const int r = i / (D / 8), c = i % (D / 8);
+            const bool ok = (t0 + r) < kv_len;
+            cp_async16(dk + r * LDS + c * 8, gk + (size_t)r * stride + c * 8, ok);
+            cp_async16(dv + r * LDS + c * 8, gv + (size_t)r * stride + c * 8, ok);
+        }
+    };
+
+    if (n_tiles > 0) load_kv(0, 0);
+    cp_async_commit();
+
+    cp_async_wait<1>();  // Q landed
+    __syncthreads();
+    uint32_t qf[D / 16][4];
+#pragma unroll
+    for (int kk = 0; kk < D / 16; ++kk) {
+        const int mat = lane >> 3, r = lane & 7;
+        const bf16* ptr = sq + (size_t)(warp * 16 + (mat & 1) * 8 + r) * LDS + kk * 16 + (mat >> 1) * 8;
+        ldmatrix_x4(qf[kk][0], qf[kk][1], qf[kk][2], qf[kk][3], ptr);
+    }
+
+    float o[D / 8][4];
+#pragma unroll
+    for (int d = 0; d < D / 8; ++d)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[d][j] = 0.f;
+    float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
+
+    // causal limit (inclusive key index) of this thread's two rows
+    int lim[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int rr = row0 + warp * 16 + (lane >> 2) + r * 8;
+        lim[r] = CAUSAL ? (p.past + rr / p.G) : (kv_len - 1);
+    }
+
+    for (int t = 0; t < n_tiles; ++t) {
+        if (t + 1 < n_tiles) load_kv(t + 1, (t + 1) & 1);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        const bf16* ks = sk + (t & 1) * BN * LDS;
+        const bf16* vs = sv + (t & 1) * BN * LDS;
+        float s[8][4];
+        warp_qk<D, LDS, 4>(qf, ks, lane, s);
+        // mask: key index beyond the causal limit or beyond kv_len
+        const int kbase = t * BN + 2 * (lane & 3);
+        const bool need_mask = CAUSAL ? true : ((t + 1) * BN > kv_len);
+        if (need_mask) {
+#pragma unroll
+            for (int n = 0; n < 8; ++n) {
+                const int kidx = kbase + n * 8;
+                if (kidx > lim[0] || kidx >= kv_len) s[n][0] = -INFINITY;
+                if (kidx + 1 > lim[0] || kidx + 1 >= kv_len) s[n][1] = -INFINITY;
+                if (kidx > lim[1] || kidx >= kv_len) s[n][2] = -INFINITY;
+                if (kidx + 1 > lim[1] || kidx + 1 >= kv_len) s[n][3] = -INFINITY;
+            }
+        }
+        uint32_t pf[4][4];
+        softmax_step<D, 4>(s, p.scale_log2, m, l, o, pf);
+        warp_pv<D, LDS, 4>(pf, vs, lane, o);
+        __syncthreads();  // all warps done with this buffer before it is refilled
+    }
+
+    // finalize: full row sums across the quad, normalise, store bf16
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        l[r] += __shfl_xor_sync(0xffffffffu, l[r], 1);
+        l[r] += __shfl_xor_sync(0xffffffffu, l[r], 2);
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int rr = row0 + warp * 16 + (lane >> 2) + r * 8;
+        if (rr >= rows_total) continue;
+        const float inv = l[r] > 0.f ? 1.f / l[r] : 0.f;
+        const int pos = rr / p.G, hq = g * p.G + rr % p.G;
+        bf16* dst = p.out + (size_t)(seg_start + pos) * p.o_ld + (size_t)hq * D + 2 * (lane & 3);
+#pragma unroll
+        for (int d = 0; d < D / 8; ++d) {
+            *reinterpret_cast<uint32_t*>(dst + d * 8) = pack_bf16x2(o[d][2 * r] * inv, o[d][2 * r + 1] * inv);
+        }
+    }
+}
+
+template <int D, bool CAUSAL, bool PAGED>
+static int launch_flash(const FlashParams& p, dim3 grid, cudaStream_t s) {
+    constexpr int LDS = D + 8;
+    constexpr int smem = (64 + 4 * 64) * LDS * 2;
+    auto kern = flash_fwd_kernel<D, CAUSAL, PAGED>;
+    static bool set = false;
+    if (!set) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -1;
+        set = true;
+    }
+    kern<<<grid, 128, smem, s>>>(p);
+    return 0;
+}
+
+// ViT: qkv [N, 3*heads*80]; segments from cu_seqlens (device int32, nseg+1 entries); max_seg_len bounds the grid.
+int vit_attention(const bf16* qkv, int ld, bf16* out, int o_ld, const int* cu_seqlens, int nseg,
+                  int max_seg_len, int heads, int head_dim, cudaStream_t s) {
+    if (head_dim != 80) return -1;
+    if (nseg <= 0 || max_seg_len <= 0) return 0;
+    FlashParams p{};
+    p.q = qkv; p.q_ld = ld;
+    p.k = qkv + (size_t)heads * head_dim; p.v = qkv + (size_t)2 * heads * head_dim; p.kv_ld = ld;
+    p.out = out; p.o_ld = o_ld; p.cu_seqlens = cu_seqlens; p.S = max_seg_len; p.past = 0; p.G = 1;
+    p.Hkv = heads;
+    p.scale_log2 = 1.4426950408889634f / sqrtf((float)head_dim);
+    dim3 grid((max_seg_len + 63) / 64, heads, nseg);
+    return launch_flash<80, false, false>(p, grid, s);
+}
+
+// Decoder prefill: q rows of the fused qkv buffer (already rotated), K/V in the paged cache
+// (already containing the S new tokens at positions past..past+S-1).
+int attn_prefill_paged(const bf16* q, int q_ld, const bf16* kc, const bf16* vc, const int* page_table,
+                       int page_size, int Hq, int Hkv, int S, int past, bf16* out, int o_ld, cudaStream_t s) {
+    if (page_size != 64) return -1;
+    if (S <= 0) return 0;
+    FlashParams p{};
+    p.q = q; p.q_ld = q_ld; p.kc = kc; p.vc = vc; p.page_table = page_table; p.Hkv = Hkv;
+    p.out = out; p.o_ld = o_ld; p.cu_seqlens = nullptr; p.S = S; p.past = past; p.G = Hq / Hkv;
+    p.scale_log2 = 1.4426950408889634f / sqrtf(128.f);
+    dim3 grid((S * p.G + 63) / 64, Hkv, 1);
+    return launch_flash<128, true, true>(p, grid, s);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Decode attention (one token). grid = (Hkv, nsplit); CTA = 4 warps; each warp owns 16 of the 64
+// tokens of a page-tile; rows of the MMA tile = the G (<=16) query heads of the KV group.
+// Device-side scalars (graph-replay friendly): kv_len = tokens already in the cache; the new token
+// is appended at slot kv_len by the CTA whose range contains it.
+// ---------------------------------------------------------------------------------------------
+struct DecodeAttnParams {
+    bf16* qkv;          // [ (Hq + 2Hkv) * 128 ] raw projections (+bias) of the new token
+    bf16* kc;           // layer K cache [pages, Hkv, 64, 128]
+    bf16* vc;
+    const int* page_table;
+    const int* kv_len;      // device scalar
+    const int* rope_pos;    // device scalar: position id of the new token (kv_len + rope_delta)
+    const int* finished;    // device flag: non-zero => no-op
+    const float* inv_freq;  // [64]
+    int Hq, Hkv, nsplit;
+    float* part_o;      // [nsplit, Hq, 128]
+    float* part_ml;     // [nsplit, Hq, 2]  (m in log2 domain already scaled, l)
+    float scale_log2;
+};
+
+__device__ __forceinline__ void rope1d_row(const bf16* src, bf16* dst, int lane_dim /*0..63*/, float pos,
+                                           const float* inv_freq) {
+    // one (j, j+64) pair; torch bf16 semantics (each product and the sum rounded to bf16)
+    const float ang = __fmul_rn(pos, inv_freq[lane_dim]);
+    const float c = rbf(cosf(ang)), s = rbf(sinf(ang));
+    const float x1 = bf2f(src[lane_dim]), x2 = bf2f(src[lane_dim + 64]);
+    dst[lane_dim] = f2bf(rbf(rbf(x1 * c) + rbf(-x2 * s)));
+    dst[lane_dim + 64] = f2bf(rbf(rbf(x2 * c) + rbf(x1 * s)));
+}
+
+__global__ void __launch_bounds__(128) attn_decode_kernel(const DecodeAttnParams p) {
+    constexpr int D = 128, LDS = D + 8, BN = 64;
+    if (p.finished && *p.finished) return;
+    extern __shared__ __align__(16) uint8_t smem_attn[];
+    bf16* sq = reinterpret_cast<bf16*>(smem_attn);  // [16][LDS]
+    bf16* sk = sq + 16 * LDS;                        // [2][64][LDS]
+    bf16* sv = sk + 2 * BN * LDS;                    // [2][64][LDS]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.x, split = blockIdx.y;
+    const int G = p.Hq / p.Hkv;
+    const int kv_old = *p.kv_len;
+    const int T = kv_old + 1;
+    const float pos = (float)(*p.rope_pos);
+
+    const int n_tiles_total = (T + BN - 1) / BN;
+    const int tiles_per_split = (n_tiles_total + p.nsplit - 1) / p.nsplit;
+    const int tile_begin = split * tiles_per_split;
+    const int tile_end = min(n_tiles_total, tile_begin + tiles_per_split);
+
+    float* po = p.part_o + ((size_t)split * p.Hq + (size_t)g * G) * D;
+    float* pml = p.part_ml + ((size_t)split * p.Hq + (size_t)g * G) * 2;
+    if (tile_begin >= tile_end) {  // empty split: neutral partial
+        if (threadIdx.x < G) { pml[threadIdx.x * 2] = -INFINITY; pml[threadIdx.x * 2 + 1] = 0.f; }
+        return;
+    }
+
+    // ---- q: rotate the G heads of this group into smem (rows >= G zero) ----
+    for (int i = threadIdx.x; i < 16 * 64; i += 128) {
+        const int r = i >> 6, j = i & 63;
+        if (r < G) rope1d_row(p.qkv + (size_t)(g * G + r) * D, sq + r * LDS, j, pos, p.inv_freq);
+        else { sq[r * LDS + j] = f2bf(0.f); sq[r * LDS + j + 64] = f2bf(0.f); }
+    }
+    // ---- append the new token's k (rotated) and v to the cache (the CTA owning the last tile) ----
+    if (tile_end == n_tiles_total) {
+        const int page = p.page_table[kv_old / BN], slot = kv_old % BN;
+        bf16* dk = p.kc + (((size_t)page * p.Hkv + g) * BN + slot) * D;
+        bf16* dv = p.vc + (((size_t)page * p.Hkv + g) * BN + slot) * D;
+        const bf16* ksrc = p.qkv + (size_t)(p.Hq + g) * D;
+        const bf16* vsrc = p.qkv + (size_t)(p.Hq + p.Hkv + g) * D;
+        if (threadIdx.x < 64) rope1d_row(ksrc, dk, threadIdx.x, pos, p.inv_freq);
+        else if (threadIdx.x < 80) {
+            const int c = threadIdx.x - 64;
+            *reinterpret_cast<uint4*>(dv + c * 8) = *reinterpret_cast<const uint4*>(vsrc + c * 8);
+        }
+        __threadfence();
+    }
+    __syncthreads();
+
+    auto load_kv = [&](int tile, int buf) {
+        bf16* dk = sk + buf * BN * LDS;
+        bf16* dv = sv + buf * BN * LDS;
+        const int page = p.page_table[tile];
+        const bf16* gk = p.kc + ((size_t)page * p.Hkv + g) * BN * D;
+        const bf16* gv = p.vc + ((size_t)page * p.Hkv + g) * BN * D;
+        const int t0 = tile * BN;
+        for (int i = threadIdx.x; i < BN * (D / 8); i += 128) {
+            const int r = i >> 4, c = i & 15;
+            const bool ok = (t0 + r) < T;
+            cp_async16(dk + r * LDS + c * 8, gk + (size_t)r * D + c * 8, ok);
+            cp_async16(dv + r * LDS + c * 8, gv + (size_t)r * D + c * 8, ok);
+        }
+    };
+    load_kv(tile_begin, 0);
+    cp_async_commit();
+
+    uint32_t qf[D / 16][4];
+#pragma unroll
+    for (int kk = 0; kk < D / 16; ++kk) {
+        const int mat = lane >> 3, r = lane & 7;
+        const bf16* ptr = sq + (size_t)((mat & 1) * 8 + r) * LDS + kk * 16 + (mat >> 1) * 8;
+        ldmatrix_x4(qf[kk][0], qf[kk][1], qf[kk][2], qf[kk][3], ptr);
+    }
+    float o[D / 8][4];
+#pragma unroll
+    for (int d = 0; d < D / 8; ++d)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[d][j] = 0.f;
+    float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
+
+    for (int t = tile_begin; t < tile_end; ++t) {
+        const int buf = (t - tile_begin) & 1;
+        if (t + 1 < tile_end) load_kv(t + 1, buf ^ 1);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        const bf16* ks = sk + buf * BN * LDS + warp * 16 * LDS;
+        const bf16* vs = sv + buf * BN * LDS + warp * 16 * LDS;
+        float s[2][4];
+        warp_qk<D, LDS, 1>(qf, ks, lane, s);
+        const int kbase = t * BN + warp * 16 + 2 * (lane & 3);
+        if ((t + 1) * BN > T) {
+#pragma unroll
+            for (int n = 0; n < 2; ++n) {
+                const int kidx = kbase + n * 8;
+                if (kidx >= T) { s[n][0] = -INFINITY; s[n][2] = -INFINITY; }
+                if (kidx + 1 >= T) { s[n][1] = -INFINITY; s[n][3] = -INFINITY; }
+            }
+        }
+        uint32_t pf[1][4];
+        softmax_step<D, 1>(s, p.scale_log2, m, l, o, pf);
+        warp_pv<D, LDS, 1>(pf, vs, lane, o);
+        __syncthreads();
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        l[r] += __shfl_xor_sync(0xffffffffu, l[r], 1);
+        l[r] += __shfl_xor_sync(0xffffffffu, l[r], 2);
+    }
+
+    // ---- merge the 4 warps (each saw a disjoint token subset) through shared memory ----
+    float* so = reinterpret_cast<float*>(sk);  // [4][8][128] fp32 = 16 KB   (only rows < 8 are kept: G <= 8)
+    float* sml = so + 4 * 8 * D;               // [4][8][2]
+    __syncthreads();
+    if ((lane >> 2) < 8) {
+        const int r = lane >> 2;  // row (thread's first row); second row r+8 is padding when G <= 8
+        float* dst = so + ((size_t)warp * 8 + r) * D + 2 * (lane & 3);
+#pragma unroll
+        for (int d = 0; d < D / 8; ++d) { dst[d * 8] = o[d][0]; dst[d * 8 + 1] = o[d][1]; }
+        if ((lane & 3) == 0) { sml[(warp * 8 + r) * 2] = m[0]; sml[(warp * 8 + r) * 2 + 1] = l[0]; }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < G * D; i += 128) {
+        const int r = i / D, d = i % D;
+        float M = -INFINITY;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) M = fmaxf(M, sml[(w * 8 + r) * 2]);
+        float acc = 0.f, L = 0.f;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const float mw = sml[(w * 8 + r) * 2];
+            const float f = (mw == -INFINITY) ? 0.f : exp2f((mw - M) * p.scale_log2);
+            acc += f * so[((size_t)w * 8 + r) * D + d];
+            L += f * sml[(w * 8 + r) * 2 + 1];
+        }
+        po[(size_t)r * D + d] = acc;
+        if (d == 0) { pml[r * 2] = M; pml[r * 2 + 1] = L; }
+    }
+}
+
+__global__ void __launch_bounds__(128) attn_combine_kernel(const float* __restrict__ part_o,
+                                                           const float* __restrict__ part_ml, int nsplit,
+                                                           int Hq, float scale_log2, bf16* __restrict__ out,
+                                                           const int* finished) {
+    if (finished && *finished) return;
+    const int h = blockIdx.x, d = threadIdx.x;
+    float M = -INFINITY;
+    for (int s = 0; s < nsplit; ++s) M = fmaxf(M, part_ml[((size_t)s * Hq + h) * 2]);
+    float acc = 0.f, L = 0.f;
+    for (int s = 0; s < nsplit; ++s) {
+        const float ms = part_ml[((size_t)s * Hq + h) * 2];
+        if (ms == -INFINITY) continue;
+        const float f = exp2f((ms - M) * scale_log2);
+        acc += f * part_o[((size_t)s * Hq + h) * 128 + d];
+        L += f * part_ml[((size_t)s * Hq + h) * 2 + 1];
+    }
+    out[(size_t)h * 128 + d] = f2bf(L > 0.f ? acc / L : 0.f);
+}
+
+int attn_decode(bf16* qkv, bf16* kc, bf16* vc, const int* page_table, int page_size, const int* kv_len,
+                const int* rope_pos, const int* finished, const float* inv_freq, int Hq, int Hkv, int nsplit,
+                float* part_o, float* part_ml, bf16* out, cudaStream_t s) {
+    if (page_size != 64 || Hq % Hkv || Hq / Hkv > 8) return -1;
+    constexpr int smem = (16 + 4 * 64) * 136 * 2;
+    static bool set = false;
+    if (!set) {
+        if (cudaFuncSetAttribute(attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+            return -2;
+        set = true;
+    }
+    DecodeAttnParams p{};
+    p.qkv = qkv; p.kc = kc; p.vc = vc; p.page_table = page_table; p.kv_len = kv_len; p.rope_pos = rope_pos;
+    p.finished = finished; p.inv_freq = inv_freq; p.Hq = Hq; p.Hkv = Hkv; p.nsplit = nsplit;
+    p.part_o = part_o; p.part_ml = part_ml;
+    p.scale_log2 = 1.4426950408889634f / sqrtf(128.f);
+    attn_decode_kernel<<<dim3(Hkv, nsplit), 128, smem, s>>>(p);
+    attn_combine_kernel<<<Hq, 128, 0, s>>>(part_o, part_ml, nsplit, Hq, p.scale_log2, out, finished);
+    return 0;
+}
+
+}  // namespace lcc

@@ -3,6 +3,9 @@
 #include "../../include/livecc_b200.h"
 #include "cabi_common.h"
 #include "gemm.h"
+#include "ops.h"
+
+using lcc::bf16;
 
 extern "C" {
 
@@ -41,6 +44,123 @@ int lcc_gemm_bf16(lcc_ctx* ctx, const void* A, int lda, const void* B, int ldb, 
     int r = lcc::gemm_bf16_tn(a, ctx->num_sms, (cudaStream_t)stream);
     if (r) LCC_FAIL(ctx, r, "lcc_gemm_bf16 failed (code %d; M=%d N=%d K=%d epi=%d)", r, M, N, K, epilogue);
     return 0;
+}
+
+
+#define OP_RET(ctx, expr, name)                                              \
+    do {                                                                     \
+        if (!(ctx)) return -1;                                               \
+        int rc__ = (expr);                                                   \
+        if (rc__) LCC_FAIL(ctx, rc__, name " failed (code %d)", rc__);       \
+        LCC_CHECK_LAUNCH(ctx, name);                                         \
+        return 0;                                                            \
+    } while (0)
+
+int lcc_cast_f32_bf16(lcc_ctx* ctx, const float* in, void* out, int64_t n, lcc_stream_t stream) {
+    OP_RET(ctx, lcc::cast_f32_bf16(in, (bf16*)out, n, ctx->num_sms, (cudaStream_t)stream), "lcc_cast_f32_bf16");
+}
+
+int lcc_layernorm(lcc_ctx* ctx, const void* x, int ldx, const void* w, const void* b, void* y, int ldy,
+                  int rows, int dim, float eps, lcc_stream_t stream) {
+    OP_RET(ctx, lcc::layernorm((const bf16*)x, ldx, (const bf16*)w, (const bf16*)b, (bf16*)y, ldy, rows, dim, eps,
+                               (cudaStream_t)stream), "lcc_layernorm");
+}
+
+int lcc_rmsnorm(lcc_ctx* ctx, const void* x, int ldx, const void* w, void* y, int ldy, int rows, int dim,
+                float eps, lcc_stream_t stream) {
+    OP_RET(ctx, lcc::rmsnorm((const bf16*)x, ldx, (const bf16*)w, (bf16*)y, ldy, rows, dim, eps, (cudaStream_t)stream),
+           "lcc_rmsnorm");
+}
+
+int lcc_vit_rope_table(lcc_ctx* ctx, float* cos_t, float* sin_t, int t, int h, int w, int merge,
+                       int head_dim, const float* inv_freq, lcc_stream_t stream) {
+    OP_RET(ctx, lcc::vit_rope_table(cos_t, sin_t, t, h, w, merge, head_dim, inv_freq, (cudaStream_t)stream),
+           "lcc_vit_rope_table");
+}
+
+int lcc_vit_rope_apply(lcc_ctx* ctx, void* qkv, int ld, const float* cos_t, const float* sin_t, int N,
+                       int heads, int head_dim, lcc_stream_t stream) {
+    OP_RET(ctx, lcc::vit_rope_apply((bf16*)qkv, ld, cos_t, sin_t, N, heads, head_dim, (cudaStream_t)stream),
+           "lcc_vit_rope_apply");
+}
+
+int lcc_vit_attention(lcc_ctx* ctx, const void* qkv, int ld, void* out, int o_ld, const int32_t* cu_seqlens,
+                      int nseg, int max_seg_len, int heads, int head_dim, lcc_stream_t stream) {
+    OP_RET(ctx, lcc::vit_attention((const bf16*)qkv, ld, (bf16*)out, o_ld, cu_seqlens, nseg, max_seg_len, heads,
+                                   head_dim, (cudaStream_t)stream), "lcc_vit_attention");
+}
+
+int lcc_embed_gather(lcc_ctx* ctx, const int64_t* ids, const void* table, const void* video_embeds,
+                     int64_t video_token_id, void* out, int32_t* rank_ws, int S, int H, int64_t vocab,
+                     lcc_stream_t stream) {
+    OP_RET(ctx, lcc::embed_gather(ids, (const bf16*)table, (const bf16*)video_embeds, video_token_id, (bf16*)out,
+                                  rank_ws, rank_ws + S, S, H, vocab, (cudaStream_t)stream), "lcc_embed_gather");
+}
+
+int lcc_mrope_kv_write(lcc_ctx* ctx, void* qkv, int ld, const int32_t* pos3, int S, const float* inv_freq,
+                       int sec_t, int sec_h, int Hq, int Hkv, void* k_cache, void* v_cache,
+                       const int32_t* page_table, int kv_start, lcc_stream_t stream) {
+    OP_RET(ctx, lcc::mrope_kv_write((bf16*)qkv, ld, pos3, S, inv_freq, sec_t, sec_h, Hq, Hkv, (bf16*)k_cache,
+                                    (bf16*)v_cache, page_table, LCC_PAGE_SIZE, kv_start, (cudaStream_t)stream),
+           "lcc_mrope_kv_write");
+}
+
+int lcc_attn_prefill(lcc_ctx* ctx, const void* q, int q_ld, const void* k_cache, const void* v_cache,
+                     const int32_t* page_table, int Hq, int Hkv, int S, int past, void* out, int o_ld,
+                     lcc_stream_t stream) {
+    OP_RET(ctx, lcc::attn_prefill_paged((const bf16*)q, q_ld, (const bf16*)k_cache, (const bf16*)v_cache, page_table,
+                                        LCC_PAGE_SIZE, Hq, Hkv, S, past, (bf16*)out, o_ld, (cudaStream_t)stream),
+           "lcc_attn_prefill");
+}
+
+int lcc_attn_decode(lcc_ctx* ctx, void* qkv, void* k_cache, void* v_cache, const int32_t* page_table,
+                    const int32_t* scalars, const float* inv_freq, int Hq, int Hkv, int nsplit, float* part_o,
+                    float* part_ml, void* out, lcc_stream_t stream) {
+    if (nsplit < 1 || nsplit > 64) LCC_FAIL(ctx, -2, "lcc_attn_decode: nsplit out of range");
+    OP_RET(ctx, lcc::attn_decode((bf16*)qkv, (bf16*)k_cache, (bf16*)v_cache, page_table, LCC_PAGE_SIZE,
+                                 scalars + LCC_SC_KV_LEN, scalars + LCC_SC_ROPE_POS, scalars + LCC_SC_FINISHED,
+                                 inv_freq, Hq, Hkv, nsplit, part_o, part_ml, (bf16*)out, (cudaStream_t)stream),
+           "lcc_attn_decode");
+}
+
+static inline const int* fin_ptr(const int32_t* scalars) { return scalars ? scalars + LCC_SC_FINISHED : nullptr; }
+
+int lcc_gemv_norm_bias(lcc_ctx* ctx, const void* W, int ldw, const void* x, const void* norm_w, float eps,
+                       const void* bias, void* out, int N, int K, const int32_t* scalars, lcc_stream_t stream) {
+    OP_RET(ctx, lcc::gemv_norm_bias((const bf16*)W, ldw, (const bf16*)x, (const bf16*)norm_w, eps, (const bf16*)bias,
+                                    (bf16*)out, N, K, fin_ptr(scalars), (cudaStream_t)stream), "lcc_gemv_norm_bias");
+}
+
+int lcc_gemv_residual(lcc_ctx* ctx, const void* W, int ldw, const void* x, void* h_inout, int N, int K,
+                      const int32_t* scalars, lcc_stream_t stream) {
+    OP_RET(ctx, lcc::gemv_residual((const bf16*)W, ldw, (const bf16*)x, (bf16*)h_inout, N, K, fin_ptr(scalars),
+                                   (cudaStream_t)stream), "lcc_gemv_residual");
+}
+
+int lcc_gemv_norm_swiglu(lcc_ctx* ctx, const void* W_gate_up, int ldw, const void* x, const void* norm_w,
+                         float eps, void* act, int N2, int K, const int32_t* scalars, lcc_stream_t stream) {
+    OP_RET(ctx, lcc::gemv_norm_swiglu((const bf16*)W_gate_up, ldw, (const bf16*)x, (const bf16*)norm_w, eps, (bf16*)act,
+                                      N2, K, fin_ptr(scalars), (cudaStream_t)stream), "lcc_gemv_norm_swiglu");
+}
+
+int lcc_gemv_norm_logits(lcc_ctx* ctx, const void* W, int ldw, const void* x, const void* norm_w, float eps,
+                         float* logits, float* logits_copy, int N, int K, const int32_t* scalars,
+                         lcc_stream_t stream) {
+    OP_RET(ctx, lcc::gemv_norm_logits((const bf16*)W, ldw, (const bf16*)x, (const bf16*)norm_w, eps, logits,
+                                      logits_copy, N, K, fin_ptr(scalars), (cudaStream_t)stream),
+           "lcc_gemv_norm_logits");
+}
+
+int lcc_sample_greedy(lcc_ctx* ctx, const float* logits_raw, float* logits_proc, int V, int64_t* seq,
+                      int32_t* scalars, const lcc_sampling* sp, int advance_kv, const void* embed, void* h,
+                      int H, lcc_stream_t stream) {
+    if (!sp) return -1;
+    lcc::SampleArgs a{};
+    a.logits_raw = logits_raw; a.logits_proc = logits_proc; a.V = V; a.seq = seq; a.scalars = scalars;
+    a.repetition_penalty = sp->repetition_penalty; a.thr_token = sp->thr_token; a.thr_base = sp->thr_base;
+    a.thr_step = sp->thr_step; a.eos_token_id = sp->eos_token_id; a.max_new_tokens = sp->max_new_tokens;
+    a.advance_kv = advance_kv; a.embed = (const bf16*)embed; a.h = (bf16*)h; a.H = H;
+    OP_RET(ctx, lcc::sample_greedy(a, (cudaStream_t)stream), "lcc_sample_greedy");
 }
 
 }  // extern "C"

@@ -1,0 +1,268 @@
+// Decode-step (M = 1) projections: weight-streaming GEMV kernels, HBM-bound by construction
+// (14.1 GB of bf16 weights per generated token at 7B). CUDA cores only — a 1-row
+// operand cannot feed a tensor-core tile — with 16-byte non-allocating loads, >= 8 independent loads
+// in flight per lane, the activation vector staged once per CTA in shared memory, and the
+// RMSNorm / bias / SwiGLU / residual work fused around the dot products.
+//
+//   gemv_rows_kernel  : K <= 8192.  Each warp owns ROWS consecutive weight rows (full K).
+//   gemv_splitk_kernel: large K (down_proj, K = 18944). A CTA owns ROWS rows; its 8 warps split K.
+#include "common.cuh"
+#include "ops.h"
+
+namespace lcc {
+
+enum { GV_BIAS = 0, GV_RESIDUAL = 1, GV_SWIGLU = 2, GV_LOGITS = 3 };
+
+__device__ __forceinline__ float dot8(const uint4& w, const uint4& x) {
+    const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+    const uint32_t xw[4] = {x.x, x.y, x.z, x.w};
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float2 a = unpack_bf16x2(ww[j]), b = unpack_bf16x2(xw[j]);
+        acc = fmaf(a.x, b.x, acc);
+        acc = fmaf(a.y, b.y, acc);
+    }
+    return acc;
+}
+
+// Stage x[K] (bf16) into shared memory; with NORM, apply Qwen2VLRMSNorm (mq2vl.py:126-131):
+// xs = w_norm * bf16(x * rsqrt(mean(x^2) + eps)).
+template <bool NORM>
+__device__ __forceinline__ void stage_x(bf16* xs, const bf16* __restrict__ x, const bf16* __restrict__ nw,
+                                        float eps, int K, float* red) {
+    float sq = 0.f;
+    for (int c = threadIdx.x * 8; c < K; c += blockDim.x * 8) {
+        const uint4 u = *reinterpret_cast<const uint4*>(x + c);
+        *reinterpret_cast<uint4*>(xs + c) = u;
+        if (NORM) {
+            const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { const float2 f = unpack_bf16x2(uw[j]); sq += f.x * f.x + f.y * f.y; }
+        }
+    }
+    if (NORM) {
+        const float tot = block_sum(sq, red);
+        const float rs = rsqrtf(tot / (float)K + eps);
+        for (int c = threadIdx.x * 8; c < K; c += blockDim.x * 8) {
+            const uint4 u = *reinterpret_cast<const uint4*>(xs + c);
+            const uint4 wv = *reinterpret_cast<const uint4*>(nw + c);
+            const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
+            const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+            uint32_t o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = unpack_bf16x2(uw[j]), g = unpack_bf16x2(ww[j]);
+                o[j] = pack_bf16x2(g.x * rbf(f.x * rs), g.y * rbf(f.y * rs));
+            }
+            *reinterpret_cast<uint4*>(xs + c) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+    }
+    __syncthreads();
+}
+
+struct GemvParams {
+    const bf16* W; int ldw;
+    const bf16* x;          // [K]
+    const bf16* norm_w;     // [K] or null
+    float eps;
+    int N, K;
+    const bf16* bias;       // GV_BIAS
+    bf16* out;              // GV_BIAS: [N]; GV_SWIGLU: [N/2]; GV_RESIDUAL: in/out residual stream [N]
+    float* out_f32;         // GV_LOGITS: raw logits [N]
+    float* out_f32_b;       // GV_LOGITS: second copy (processed-logits buffer)
+    const int* finished;
+};
+
+template <int ROWS, bool NORM, int EPI>
+__global__ void __launch_bounds__(256) gemv_rows_kernel(const GemvParams p) {
+    if (p.finished && *p.finished) return;
+    extern __shared__ __align__(16) uint8_t smem_gemv[];
+    bf16* xs = reinterpret_cast<bf16*>(smem_gemv);
+    __shared__ float red[32];
+    stage_x<NORM>(xs, p.x, p.norm_w, p.eps, p.K, red);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row0 = (blockIdx.x * 8 + warp) * ROWS;
+    if (row0 >= p.N) return;
+    // GV_SWIGLU: the warp's two rows are gate row and its matching up row (16 apart in a 32-row group)
+    int rows[ROWS];
+    if (EPI == GV_SWIGLU) {
+        const int j = row0 / 2;  // output index
+        rows[0] = (j >> 4) * 32 + (j & 15);
+        if (ROWS > 1) rows[ROWS - 1] = rows[0] + 16;
+    } else {
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) rows[r] = min(row0 + r, p.N - 1);
+    }
+    float acc[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) acc[r] = 0.f;
+    const int K = p.K;
+    constexpr int UNROLL = 4;
+    int c = lane * 8;
+    for (; c + (UNROLL - 1) * 256 < K; c += UNROLL * 256) {
+        uint4 w[ROWS][UNROLL];
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) w[r][u] = ld_stream16(p.W + (size_t)rows[r] * p.ldw + c + u * 256);
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const uint4 xv = *reinterpret_cast<const uint4*>(xs + c + u * 256);
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) acc[r] += dot8(w[r][u], xv);
+        }
+    }
+    for (; c < K; c += 256) {
+        const uint4 xv = *reinterpret_cast<const uint4*>(xs + c);
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) acc[r] += dot8(ld_stream16(p.W + (size_t)rows[r] * p.ldw + c), xv);
+    }
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) acc[r] = warp_sum(acc[r]);
+    if (lane != 0) return;
+    if (EPI == GV_SWIGLU) {
+        const float gt = rbf(acc[0]), up = rbf(acc[ROWS - 1]);
+        const float sl = rbf(gt / (1.0f + expf(-gt)));
+        p.out[row0 / 2] = f2bf(sl * up);
+    } else {
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+            const int n = row0 + r;
+            if (n >= p.N) break;
+            if (EPI == GV_BIAS) p.out[n] = f2bf(acc[r] + bf2f(p.bias[n]));
+            else if (EPI == GV_RESIDUAL) p.out[n] = f2bf(rbf(acc[r]) + bf2f(p.out[n]));
+            else if (EPI == GV_LOGITS) {
+                const float v = rbf(acc[r]);  // lm_head output is bf16, then .float() (gen/utils.py:2762)
+                p.out_f32[n] = v;
+                if (p.out_f32_b) p.out_f32_b[n] = v;
+            }
+        }
+    }
+}
+
+template <int ROWS>
+__global__ void __launch_bounds__(256) gemv_splitk_kernel(const GemvParams p) {
+    if (p.finished && *p.finished) return;
+    extern __shared__ __align__(16) uint8_t smem_gemv[];
+    bf16* xs = reinterpret_cast<bf16*>(smem_gemv);
+    __shared__ float red[32];
+    __shared__ float part[8][ROWS];
+    stage_x<false>(xs, p.x, nullptr, 0.f, p.K, red);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row0 = blockIdx.x * ROWS;
+    float acc[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) acc[r] = 0.f;
+    const int K = p.K;
+    constexpr int UNROLL = 2;
+    int c = (warp * 32 + lane) * 8;
+    for (; c + (UNROLL - 1) * 2048 < K; c += UNROLL * 2048) {
+        uint4 w[ROWS][UNROLL];
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u)
+                w[r][u] = ld_stream16(p.W + (size_t)min(row0 + r, p.N - 1) * p.ldw + c + u * 2048);
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const uint4 xv = *reinterpret_cast<const uint4*>(xs + c + u * 2048);
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) acc[r] += dot8(w[r][u], xv);
+        }
+    }
+    for (; c < K; c += 2048) {
+        const uint4 xv = *reinterpret_cast<const uint4*>(xs + c);
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r)
+            acc[r] += dot8(ld_stream16(p.W + (size_t)min(row0 + r, p.N - 1) * p.ldw + c), xv);
+    }
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+        acc[r] = warp_sum(acc[r]);
+        if (lane == 0) part[warp][r] = acc[r];
+    }
+    __syncthreads();
+    if (threadIdx.x < ROWS) {
+        const int n = row0 + threadIdx.x;
+        if (n < p.N) {
+            float t = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) t += part[w][threadIdx.x];
+            p.out[n] = f2bf(rbf(t) + bf2f(p.out[n]));  // down_proj + residual (mq2vl.py:660)
+        }
+    }
+}
+
+template <typename Kern>
+static int set_smem(Kern kern, int bytes) {
+    return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess ? 0 : -1;
+}
+
+static int check_common(const GemvParams& p) {
+    if (p.N <= 0 || p.K <= 0 || (p.K % 8) || (p.ldw % 8)) return -1;
+    if (p.K * 2 > 200 * 1024) return -2;
+    return 0;
+}
+
+// qkv = W_qkv * rmsnorm(h) + b          (mq2vl.py:631, 559-565)
+int gemv_norm_bias(const bf16* W, int ldw, const bf16* x, const bf16* norm_w, float eps, const bf16* bias,
+                   bf16* out, int N, int K, const int* finished, cudaStream_t s) {
+    GemvParams p{}; p.W = W; p.ldw = ldw; p.x = x; p.norm_w = norm_w; p.eps = eps; p.N = N; p.K = K;
+    p.bias = bias; p.out = out; p.finished = finished;
+    if (int r = check_common(p)) return r;
+    auto kern = gemv_rows_kernel<2, true, GV_BIAS>;
+    static bool set = false;
+    if (!set) { if (set_smem(kern, 200 * 1024)) return -3; set = true; }
+    kern<<<(N + 15) / 16, 256, K * 2, s>>>(p);
+    return 0;
+}
+
+// h += W_o * attn                          (mq2vl.py:593, 645)
+int gemv_residual(const bf16* W, int ldw, const bf16* x, bf16* h_inout, int N, int K, const int* finished,
+                  cudaStream_t s) {
+    GemvParams p{}; p.W = W; p.ldw = ldw; p.x = x; p.N = N; p.K = K; p.out = h_inout; p.finished = finished;
+    if (int r = check_common(p)) return r;
+    if (K > 8192) {
+        auto kern = gemv_splitk_kernel<4>;
+        static bool set = false;
+        if (!set) { if (set_smem(kern, 200 * 1024)) return -3; set = true; }
+        kern<<<(N + 3) / 4, 256, K * 2, s>>>(p);
+    } else {
+        auto kern = gemv_rows_kernel<2, false, GV_RESIDUAL>;
+        static bool set = false;
+        if (!set) { if (set_smem(kern, 200 * 1024)) return -3; set = true; }
+        kern<<<(N + 15) / 16, 256, K * 2, s>>>(p);
+    }
+    return 0;
+}
+
+// act = silu(Wg * rmsnorm(h)) * (Wu * rmsnorm(h)), gate/up rows interleaved by 16   (mq2vl.py:502-504, 657-659)
+int gemv_norm_swiglu(const bf16* W_gu, int ldw, const bf16* x, const bf16* norm_w, float eps, bf16* act,
+                     int N2 /* = 2*I */, int K, const int* finished, cudaStream_t s) {
+    GemvParams p{}; p.W = W_gu; p.ldw = ldw; p.x = x; p.norm_w = norm_w; p.eps = eps; p.N = N2; p.K = K;
+    p.out = act; p.finished = finished;
+    if (int r = check_common(p)) return r;
+    if (N2 % 32) return -4;
+    auto kern = gemv_rows_kernel<2, true, GV_SWIGLU>;
+    static bool set = false;
+    if (!set) { if (set_smem(kern, 200 * 1024)) return -3; set = true; }
+    kern<<<(N2 + 15) / 16, 256, K * 2, s>>>(p);
+    return 0;
+}
+
+// logits = float(bf16(W_lm * rmsnorm(h)))   (mq2vl.py:905, 1437-1438; gen/utils.py:2762)
+int gemv_norm_logits(const bf16* W, int ldw, const bf16* x, const bf16* norm_w, float eps, float* logits,
+                     float* logits_copy, int N, int K, const int* finished, cudaStream_t s) {
+    GemvParams p{}; p.W = W; p.ldw = ldw; p.x = x; p.norm_w = norm_w; p.eps = eps; p.N = N; p.K = K;
+    p.out_f32 = logits; p.out_f32_b = logits_copy; p.finished = finished;
+    if (int r = check_common(p)) return r;
+    auto kern = gemv_rows_kernel<4, true, GV_LOGITS>;
+    static bool set = false;
+    if (!set) { if (set_smem(kern, 200 * 1024)) return -3; set = true; }
+    kern<<<(N + 31) / 32, 256, K * 2, s>>>(p);
+    return 0;
+}
+
+}  // namespace lcc

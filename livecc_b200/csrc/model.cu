@@ -1,0 +1,293 @@
+// Native model runtime: one C call launches a whole phase of the LiveCC hot path on the given stream.
+//   lcc_vit_forward   — Qwen2VisionTransformerPretrainedModel.forward   (mq2vl.py:757-795)
+//   lcc_prefill       — Qwen2VLModel.forward over S new tokens + first token selection (mq2vl.py:1230-1300)
+//   lcc_decode_steps  — the loop body of GenerationMixin._sample         (gen/utils.py:2743-2805)
+// The host (Python) owns every buffer; this file only sequences kernel launches.
+#include <vector>
+
+#include "../../include/livecc_b200.h"
+#include "cabi_common.h"
+#include "gemm.h"
+#include "ops.h"
+
+using lcc::bf16;
+
+struct lcc_model {
+    lcc_ctx* ctx;
+    lcc_model_config cfg;
+    lcc_model_weights w;
+    std::vector<lcc_vit_block_weights> vit_blocks;
+    std::vector<lcc_layer_weights> layers;
+    // bound workspace (lcc_model_bind_workspace)
+    uint8_t* ws = nullptr;
+    size_t ws_bytes = 0;
+    int cap_patches = 0, cap_tokens = 0;
+};
+
+namespace {
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// Workspace carve-up (deterministic function of the model config and the two capacities).
+struct WsLayout;
+int get_layout(const lcc_model* m, int need_patches, int need_tokens, WsLayout* out);
+
+struct WsLayout {
+    size_t vx, vh, vn, vqkv, vattn, vmlp, vcos, vsin, vcu;  // ViT
+    size_t hid, normed, qkv, attn, act, rank;                // prefill
+    size_t h1, qkv1, attn1, act1, logits_raw, logits_proc, part_o, part_ml;  // decode
+    size_t total;
+};
+
+constexpr int kMaxSplit = 64;
+
+WsLayout make_layout(const lcc_model_config& c, int NP, int NT) {
+    WsLayout L{};
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes); return o; };
+    const size_t np = (size_t)(NP > 0 ? NP : 1), nt = (size_t)(NT > 0 ? NT : 1);
+    const size_t qkv_dim = (size_t)(c.q_heads + 2 * c.kv_heads) * 128;
+    L.vx = take(np * c.patch_dim * 2);
+    L.vh = take(np * c.vit_dim * 2);
+    L.vn = take(np * c.vit_dim * 2);
+    L.vqkv = take(np * 3 * c.vit_dim * 2);
+    L.vattn = take(np * c.vit_dim * 2);
+    L.vmlp = take(np * c.vit_mlp * 2);
+    L.vcos = take(np * (c.vit_dim / c.vit_heads / 2) * 4);
+    L.vsin = take(np * (c.vit_dim / c.vit_heads / 2) * 4);
+    L.vcu = take((np + 2) * 4);
+    L.hid = take(nt * c.hidden * 2);
+    L.normed = take(nt * c.hidden * 2);
+    L.qkv = take(nt * qkv_dim * 2);
+    L.attn = take(nt * c.q_heads * 128 * 2);
+    L.act = take(nt * c.inter * 2);
+    L.rank = take((nt + 2) * 4);
+    L.h1 = take((size_t)c.hidden * 2);
+    L.qkv1 = take(qkv_dim * 2);
+    L.attn1 = take((size_t)c.q_heads * 128 * 2);
+    L.act1 = take((size_t)c.inter * 2);
+    L.logits_raw = take((size_t)c.vocab * 4);
+    L.logits_proc = take((size_t)c.vocab * 4);
+    L.part_o = take((size_t)kMaxSplit * c.q_heads * 128 * 4);
+    L.part_ml = take((size_t)kMaxSplit * c.q_heads * 2 * 4);
+    L.total = off;
+    return L;
+}
+
+__global__ void fill_cu_seqlens_kernel(int* cu, int t, int hw) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= t) cu[i] = i * hw;
+}
+
+int gemm(lcc_model* m, const void* A, int lda, const void* B, int ldb, void* C, int ldc, int M, int N, int K,
+         const void* bias, const void* res, int ldr, int epi, cudaStream_t s) {
+    lcc::GemmArgs a;
+    a.A = A; a.B = B; a.C = C; a.M = M; a.N = N; a.K = K; a.lda = lda; a.ldb = ldb; a.ldc = ldc;
+    a.bias = bias; a.residual = res; a.ldr = ldr; a.epi = epi; a.block_n = 0;
+    return lcc::gemm_bf16_tn(a, m->ctx->num_sms, s);
+}
+
+#define STEP(expr, what)                                                                      \
+    do {                                                                                      \
+        int rc__ = (expr);                                                                    \
+        if (rc__) LCC_FAIL(m->ctx, rc__, "%s failed (code %d)", what, rc__);                  \
+    } while (0)
+
+lcc::SampleArgs make_sample(const lcc_model* m, const lcc_stream_state* st, const lcc_sampling* sp, uint8_t* ws,
+                            const WsLayout& L, int advance) {
+    lcc::SampleArgs a{};
+    a.logits_raw = reinterpret_cast<const float*>(ws + L.logits_raw);
+    a.logits_proc = reinterpret_cast<float*>(ws + L.logits_proc);
+    a.V = m->cfg.vocab;
+    a.seq = st->seq;
+    a.scalars = st->scalars;
+    a.repetition_penalty = sp->repetition_penalty;
+    a.thr_token = sp->thr_token;
+    a.thr_base = sp->thr_base;
+    a.thr_step = sp->thr_step;
+    a.eos_token_id = sp->eos_token_id;
+    a.max_new_tokens = sp->max_new_tokens;
+    a.advance_kv = advance;
+    a.embed = reinterpret_cast<const bf16*>(m->w.embed);
+    a.h = reinterpret_cast<bf16*>(ws + L.h1);
+    a.H = m->cfg.hidden;
+    return a;
+}
+
+}  // namespace
+
+extern "C" {
+
+lcc_model* lcc_model_create(lcc_ctx* ctx, const lcc_model_config* cfg, const lcc_model_weights* w) {
+    if (!ctx || !cfg || !w) return nullptr;
+    if (cfg->hidden != cfg->q_heads * 128 || cfg->vit_dim != cfg->vit_heads * 80 || cfg->q_heads % cfg->kv_heads ||
+        cfg->q_heads / cfg->kv_heads > 8 || cfg->inter % 16 || cfg->merge != 2) {
+        snprintf(ctx->err, sizeof(ctx->err), "unsupported model geometry (need head_dim 128 / ViT head_dim 80 / GQA group <= 8)");
+        return nullptr;
+    }
+    lcc_model* m = new lcc_model();
+    m->ctx = ctx;
+    m->cfg = *cfg;
+    m->w = *w;
+    m->vit_blocks.assign(w->vit_blocks, w->vit_blocks + cfg->vit_depth);
+    m->layers.assign(w->layers, w->layers + cfg->layers);
+    m->w.vit_blocks = m->vit_blocks.data();
+    m->w.layers = m->layers.data();
+    return m;
+}
+
+void lcc_model_destroy(lcc_model* m) { delete m; }
+
+size_t lcc_workspace_bytes(const lcc_model* m, int max_patches, int max_tokens) {
+    return m ? make_layout(m->cfg, max_patches, max_tokens).total : 0;
+}
+size_t lcc_ws_offset(const lcc_model* m, int which) {
+    if (!m) return 0;
+    const WsLayout L = make_layout(m->cfg, m->cap_patches, m->cap_tokens);
+    switch (which) {
+        case LCC_WS_PREFILL_HIDDEN: return L.hid;
+        case LCC_WS_LOGITS: return L.logits_raw;
+        case LCC_WS_DECODE_HIDDEN: return L.h1;
+    }
+    return 0;
+}
+
+int lcc_vit_forward(lcc_model* m, const float* pixel_values, int t, int h, int w, void* out,
+                    lcc_stream_t stream) {
+    if (!m) return -1;
+    const lcc_model_config& c = m->cfg;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int N = t * h * w;
+    if (N <= 0 || (h % c.merge) || (w % c.merge)) LCC_FAIL(m->ctx, -2, "lcc_vit_forward: bad grid %d,%d,%d", t, h, w);
+    WsLayout L;
+    if (get_layout(m, N, 0, &L)) LCC_FAIL(m->ctx, -3, "lcc_vit_forward: no workspace bound or too small for %d patches", N);
+    uint8_t* ws = m->ws;
+    bf16* vx = (bf16*)(ws + L.vx); bf16* vh = (bf16*)(ws + L.vh); bf16* vn = (bf16*)(ws + L.vn);
+    bf16* vqkv = (bf16*)(ws + L.vqkv); bf16* vattn = (bf16*)(ws + L.vattn); bf16* vmlp = (bf16*)(ws + L.vmlp);
+    float* vcos = (float*)(ws + L.vcos); float* vsin = (float*)(ws + L.vsin);
+    int* vcu = (int*)(ws + L.vcu);
+    const int dim = c.vit_dim, hd = dim / c.vit_heads;
+
+    STEP(lcc::cast_f32_bf16(pixel_values, vx, (int64_t)N * c.patch_dim, m->ctx->num_sms, s), "vit cast");
+    STEP(gemm(m, vx, c.patch_dim, m->w.patch_w, c.patch_dim, vh, dim, N, dim, c.patch_dim, nullptr, nullptr, 0,
+              lcc::EPI_NONE, s), "vit patch_embed");
+    STEP(lcc::vit_rope_table(vcos, vsin, t, h, w, c.merge, hd, m->w.vit_inv_freq, s), "vit rope table");
+    fill_cu_seqlens_kernel<<<(t + 256) / 256, 256, 0, s>>>(vcu, t, h * w);
+    for (int i = 0; i < c.vit_depth; ++i) {
+        const lcc_vit_block_weights& b = m->vit_blocks[i];
+        STEP(lcc::layernorm(vh, dim, (const bf16*)b.norm1_w, (const bf16*)b.norm1_b, vn, dim, N, dim, 1e-6f, s), "vit norm1");
+        STEP(gemm(m, vn, dim, b.qkv_w, dim, vqkv, 3 * dim, N, 3 * dim, dim, b.qkv_b, nullptr, 0, lcc::EPI_BIAS, s), "vit qkv");
+        STEP(lcc::vit_rope_apply(vqkv, 3 * dim, vcos, vsin, N, c.vit_heads, hd, s), "vit rope");
+        STEP(lcc::vit_attention(vqkv, 3 * dim, vattn, dim, vcu, t, h * w, c.vit_heads, hd, s), "vit attention");
+        STEP(gemm(m, vattn, dim, b.proj_w, dim, vh, dim, N, dim, dim, b.proj_b, vh, dim, lcc::EPI_BIAS_RESIDUAL, s), "vit proj");
+        STEP(lcc::layernorm(vh, dim, (const bf16*)b.norm2_w, (const bf16*)b.norm2_b, vn, dim, N, dim, 1e-6f, s), "vit norm2");
+        STEP(gemm(m, vn, dim, b.fc1_w, dim, vmlp, c.vit_mlp, N, c.vit_mlp, dim, b.fc1_b, nullptr, 0, lcc::EPI_BIAS_QUICKGELU, s), "vit fc1");
+        STEP(gemm(m, vmlp, c.vit_mlp, b.fc2_w, c.vit_mlp, vh, dim, N, dim, c.vit_mlp, b.fc2_b, vh, dim, lcc::EPI_BIAS_RESIDUAL, s), "vit fc2");
+    }
+    // PatchMerger (mq2vl.py:313-326): LN, view [N/4, 4*dim], Linear+GELU, Linear
+    const int md = dim * c.merge * c.merge, NM = N / (c.merge * c.merge);
+    STEP(lcc::layernorm(vh, dim, (const bf16*)m->w.merger_ln_w, (const bf16*)m->w.merger_ln_b, vn, dim, N, dim, 1e-6f, s), "merger ln");
+    STEP(gemm(m, vn, md, m->w.merger_fc1_w, md, vmlp, md, NM, md, md, m->w.merger_fc1_b, nullptr, 0, lcc::EPI_BIAS_GELU, s), "merger fc1");
+    STEP(gemm(m, vmlp, md, m->w.merger_fc2_w, md, out, c.vit_out, NM, c.vit_out, md, m->w.merger_fc2_b, nullptr, 0, lcc::EPI_BIAS, s), "merger fc2");
+    LCC_CHECK_LAUNCH(m->ctx, "lcc_vit_forward");
+    return 0;
+}
+
+int lcc_prefill(lcc_model* m, const lcc_stream_state* st, const int64_t* ids, const int32_t* pos3, int S,
+                int past, const void* video_embeds, const lcc_sampling* sp, lcc_stream_t stream) {
+    if (!m || !st || !sp) return -1;
+    const lcc_model_config& c = m->cfg;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (S <= 0) LCC_FAIL(m->ctx, -2, "lcc_prefill: S must be positive");
+    WsLayout L;
+    if (get_layout(m, 0, S, &L)) LCC_FAIL(m->ctx, -3, "lcc_prefill: no workspace bound or too small for %d tokens", S);
+    uint8_t* ws = m->ws;
+    bf16* hid = (bf16*)(ws + L.hid); bf16* normed = (bf16*)(ws + L.normed); bf16* qkv = (bf16*)(ws + L.qkv);
+    bf16* attn = (bf16*)(ws + L.attn); bf16* act = (bf16*)(ws + L.act); int* rank = (int*)(ws + L.rank);
+    const int H = c.hidden, Hq = c.q_heads, Hkv = c.kv_heads, qkv_dim = (Hq + 2 * Hkv) * 128;
+
+    STEP(lcc::embed_gather(ids, (const bf16*)m->w.embed, (const bf16*)video_embeds, c.video_token_id, hid, rank,
+                           st->scalars + LCC_SC_VIDEO_TOKENS, S, H, c.vocab, s), "embed gather");
+    for (int i = 0; i < c.layers; ++i) {
+        const lcc_layer_weights& lw = m->layers[i];
+        bf16* kc = (bf16*)st->k_pool + (size_t)i * st->layer_stride;
+        bf16* vc = (bf16*)st->v_pool + (size_t)i * st->layer_stride;
+        STEP(lcc::rmsnorm(hid, H, (const bf16*)lw.ln1_w, normed, H, S, H, c.rms_eps, s), "input_layernorm");
+        STEP(gemm(m, normed, H, lw.qkv_w, H, qkv, qkv_dim, S, qkv_dim, H, lw.qkv_b, nullptr, 0, lcc::EPI_BIAS, s), "qkv proj");
+        STEP(lcc::mrope_kv_write(qkv, qkv_dim, pos3, S, m->w.text_inv_freq, c.mrope_t, c.mrope_h, Hq, Hkv, kc, vc,
+                                 st->page_table, LCC_PAGE_SIZE, past, s), "mrope + kv write");
+        STEP(lcc::attn_prefill_paged(qkv, qkv_dim, kc, vc, st->page_table, LCC_PAGE_SIZE, Hq, Hkv, S, past, attn,
+                                     Hq * 128, s), "prefill attention");
+        STEP(gemm(m, attn, Hq * 128, lw.o_w, Hq * 128, hid, H, S, H, Hq * 128, nullptr, hid, H, lcc::EPI_RESIDUAL, s), "o_proj");
+        STEP(lcc::rmsnorm(hid, H, (const bf16*)lw.ln2_w, normed, H, S, H, c.rms_eps, s), "post_attention_layernorm");
+        STEP(gemm(m, normed, H, lw.gate_up_w, H, act, c.inter, S, 2 * c.inter, H, nullptr, nullptr, 0, lcc::EPI_SWIGLU, s), "gate_up");
+        STEP(gemm(m, act, c.inter, lw.down_w, c.inter, hid, H, S, H, c.inter, nullptr, hid, H, lcc::EPI_RESIDUAL, s), "down_proj");
+    }
+    // final norm + lm_head on the last position only (logits_to_keep = 1, gen/utils.py:2487-2491)
+    STEP(lcc::gemv_norm_logits((const bf16*)m->w.lm_head, H, hid + (size_t)(S - 1) * H, (const bf16*)m->w.final_norm_w,
+                               c.rms_eps, (float*)(ws + L.logits_raw), (float*)(ws + L.logits_proc), c.vocab, H,
+                               nullptr, s), "lm_head");
+    STEP(lcc::sample_greedy(make_sample(m, st, sp, ws, L, 0), s), "token selection");
+    LCC_CHECK_LAUNCH(m->ctx, "lcc_prefill");
+    return 0;
+}
+
+int lcc_decode_steps(lcc_model* m, const lcc_stream_state* st, int n_steps, int nsplit, const lcc_sampling* sp,
+                     lcc_stream_t stream) {
+    if (!m || !st || !sp) return -1;
+    const lcc_model_config& c = m->cfg;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (nsplit < 1 || nsplit > kMaxSplit) LCC_FAIL(m->ctx, -2, "lcc_decode_steps: nsplit must be in [1,%d]", kMaxSplit);
+    WsLayout L;
+    if (get_layout(m, 0, 0, &L)) LCC_FAIL(m->ctx, -3, "lcc_decode_steps: no workspace bound");
+    uint8_t* ws = m->ws;
+    bf16* h = (bf16*)(ws + L.h1); bf16* qkv = (bf16*)(ws + L.qkv1); bf16* attn = (bf16*)(ws + L.attn1);
+    bf16* act = (bf16*)(ws + L.act1);
+    float* part_o = (float*)(ws + L.part_o); float* part_ml = (float*)(ws + L.part_ml);
+    const int H = c.hidden, Hq = c.q_heads, Hkv = c.kv_heads, qkv_dim = (Hq + 2 * Hkv) * 128;
+    const int* fin = st->scalars + LCC_SC_FINISHED;
+    for (int step = 0; step < n_steps; ++step) {
+        for (int i = 0; i < c.layers; ++i) {
+            const lcc_layer_weights& lw = m->layers[i];
+            bf16* kc = (bf16*)st->k_pool + (size_t)i * st->layer_stride;
+            bf16* vc = (bf16*)st->v_pool + (size_t)i * st->layer_stride;
+            STEP(lcc::gemv_norm_bias((const bf16*)lw.qkv_w, H, h, (const bf16*)lw.ln1_w, c.rms_eps, (const bf16*)lw.qkv_b,
+                                     qkv, qkv_dim, H, fin, s), "decode qkv");
+            STEP(lcc::attn_decode(qkv, kc, vc, st->page_table, LCC_PAGE_SIZE, st->scalars + LCC_SC_KV_LEN,
+                                  st->scalars + LCC_SC_ROPE_POS, fin, m->w.text_inv_freq, Hq, Hkv, nsplit, part_o,
+                                  part_ml, attn, s), "decode attention");
+            STEP(lcc::gemv_residual((const bf16*)lw.o_w, Hq * 128, attn, h, H, Hq * 128, fin, s), "decode o_proj");
+            STEP(lcc::gemv_norm_swiglu((const bf16*)lw.gate_up_w, H, h, (const bf16*)lw.ln2_w, c.rms_eps, act,
+                                       2 * c.inter, H, fin, s), "decode gate_up");
+            STEP(lcc::gemv_residual((const bf16*)lw.down_w, c.inter, act, h, H, c.inter, fin, s), "decode down_proj");
+        }
+        STEP(lcc::gemv_norm_logits((const bf16*)m->w.lm_head, H, h, (const bf16*)m->w.final_norm_w, c.rms_eps,
+                                   (float*)(ws + L.logits_raw), (float*)(ws + L.logits_proc), c.vocab, H, fin, s),
+             "decode lm_head");
+        STEP(lcc::sample_greedy(make_sample(m, st, sp, ws, L, 1), s), "decode token selection");
+    }
+    LCC_CHECK_LAUNCH(m->ctx, "lcc_decode_steps");
+    return 0;
+}
+
+}  // extern "C"
+
+namespace {
+int get_layout(const lcc_model* m, int need_patches, int need_tokens, WsLayout* out) {
+    if (!m->ws) return -1;
+    if (need_patches > m->cap_patches || need_tokens > m->cap_tokens) return -2;
+    *out = make_layout(m->cfg, m->cap_patches, m->cap_tokens);
+    return out->total > m->ws_bytes ? -3 : 0;
+}
+}  // namespace
+
+extern "C" int lcc_model_bind_workspace(lcc_model* m, void* ws, size_t ws_bytes, int max_patches, int max_tokens) {
+    if (!m || !ws) return -1;
+    if (make_layout(m->cfg, max_patches, max_tokens).total > ws_bytes)
+        LCC_FAIL(m->ctx, -2, "lcc_model_bind_workspace: %zu bytes is too small", ws_bytes);
+    m->ws = reinterpret_cast<uint8_t*>(ws);
+    m->ws_bytes = ws_bytes;
+    m->cap_patches = max_patches;
+    m->cap_tokens = max_tokens;
+    return 0;
+}

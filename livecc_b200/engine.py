@@ -1,0 +1,374 @@
+"""B1/B2 of the drop-in boundary: a model object with the surface
+`LiveCCDemoInfer` uses on `Qwen2VLForConditionalGeneration` (REF/demo/infer.py:43-50,158,165-174):
+
+    model = LiveCCB200ForConditionalGeneration.from_pretrained(path, torch_dtype="auto", device_map="cuda")
+    model.device, model.config.eos_token_id, model.config.video_token_id
+    model.prepare_inputs_for_generation = functools.partial(fn, model)     # accepted, semantics are native
+    out = model.generate(**inputs, past_key_values=state.get('past_key_values'), return_dict_in_generate=True,
+                         do_sample=..., repetition_penalty=..., logits_processor=..., max_new_tokens=16,
+                         pad_token_id=model.config.eos_token_id)
+    out.sequences  [1, L+n] int64 on device ;  out.past_key_values -> pass back next call
+
+Everything numeric runs in liblivecc_sm100a.so (hand-written sm_100a kernels) through the C ABI; this
+file is host orchestration: argument checking, position bookkeeping, page allocation, CUDA-graph
+replay of the decode step. There is no CPU or eager fallback: without the library or an sm_100 GPU
+construction fails.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from typing import List, Optional
+
+import torch
+
+from . import _cabi
+from .checkpoint import EngineWeights, load_engine_weights, synthetic_tensors
+from .config import LiveCCConfig
+from .kv_cache import PagedKVCache, PagePool
+from .positions import get_rope_index
+
+
+class ThresholdLogitsProcessor:
+    """Same constructor and meaning as REF/demo/infer.py:10-23; evaluated inside the sampling kernel
+    (softmax(scores)[token_id] <= base_threshold + step * n_generated  ->  scores[token_id] = -inf)."""
+
+    def __init__(self, token_id: int, base_threshold: float, step: float):
+        self.token_id = int(token_id)
+        self.base_threshold = float(base_threshold)
+        self.step = float(step)
+        self.count = 0
+
+
+@dataclass
+class GenerateOutput:
+    """The two fields of GenerateDecoderOnlyOutput the reference reads (REF/demo/infer.py:173-175)."""
+    sequences: torch.Tensor
+    past_key_values: PagedKVCache
+    logits: Optional[List[torch.Tensor]] = None  # raw fp32 logits per step (only with output_logits=True)
+
+
+@dataclass
+class GenerationDefaults:
+    """generation_config.json of the Qwen2-VL family [public-config]: sampling is top_k = 1, i.e. greedy."""
+    do_sample: bool = True
+    top_k: int = 1
+    top_p: float = 0.001
+    temperature: float = 0.01
+    repetition_penalty: float = 1.0
+
+
+class LiveCCB200ForConditionalGeneration:
+    # ------------------------------------------------------------------------------------------
+    # construction
+    # ------------------------------------------------------------------------------------------
+    def __init__(self, config: LiveCCConfig, weights: EngineWeights, device: torch.device):
+        config.validate()
+        if device.type != "cuda":
+            raise _cabi.LiveCCNativeError("LiveCCB200ForConditionalGeneration needs a CUDA (sm_100a) device; "
+                                          "there is no CPU path")
+        self.config = config
+        self.device = device
+        self.generation_config = GenerationDefaults()
+        self.legacy_4x_positions = False
+        self.prepare_inputs_for_generation = None  # assignable (REF/demo/infer.py:50); semantics are built in
+        self.weights = weights
+        torch.cuda.set_device(device)
+        self.ctx = _cabi.Context(device.index if device.index is not None else torch.cuda.current_device())
+        t, v = config.text_config, config.vision_config
+        # rotary tables, computed exactly like the reference does (mq2vl.py:175-183, 274-279)
+        self.text_inv_freq = (1.0 / (t.rope_theta ** (torch.arange(0, t.head_dim, 2, dtype=torch.int64).to(torch.float)
+                                                      / t.head_dim))).to(device)
+        hd2 = v.head_dim // 2
+        self.vit_inv_freq = (1.0 / (10000.0 ** (torch.arange(0, hd2, 2, dtype=torch.float) / hd2))).to(device)
+        self._native = self._build_native()
+        self.pool = PagePool(t.num_hidden_layers, t.num_key_value_heads, device)
+        self._cap_patches, self._cap_tokens = 0, 0
+        self._ensure_workspace(3072, 1024)
+        self._graphs = {}
+        self.use_cuda_graph = os.environ.get("LIVECC_B200_NO_GRAPH", "0") != "1"
+        self.nsplit = max(1, min(64, (self.ctx.num_sms + t.num_key_value_heads - 1) // t.num_key_value_heads))
+        self.last_stats = {}
+
+    @classmethod
+    def from_synthetic(cls, config: LiveCCConfig, seed: int = 1234, device="cuda"):
+        """Synthetic checkpoint (livecc_b200.checkpoint): no weights exist offline."""
+        device = torch.device(device if ":" in str(device) else f"{device}:{torch.cuda.current_device()}")
+        w = load_engine_weights(config, synthetic_tensors(config, seed, torch.bfloat16, device, gen_device=device), device)
+        return cls(config, w, device)
+
+    @classmethod
+    def from_state_dict(cls, config: LiveCCConfig, tensors, device="cuda"):
+        device = torch.device(device if ":" in str(device) else f"{device}:{torch.cuda.current_device()}")
+        return cls(config, load_engine_weights(config, tensors, device), device)
+
+    @classmethod
+    def from_pretrained(cls, model_path: str, torch_dtype="auto", device_map="cuda", attn_implementation=None, **_):
+        """Loads an HF Qwen2-VL / LiveCC safetensors checkpoint directory (REF/demo/infer.py:43-47).
+        `attn_implementation` is accepted and ignored (attention is always the native kernels)."""
+        import glob
+        import json
+
+        from safetensors import safe_open
+
+        files = sorted(glob.glob(os.path.join(model_path, "*.safetensors")))
+        if not files:
+            raise FileNotFoundError(f"no *.safetensors under {model_path!r} (checkpoints cannot be downloaded offline)")
+        cfg = LiveCCConfig.livecc_7b()
+        cfg_path = os.path.join(model_path, "config.json")
+        if os.path.exists(cfg_path):
+            cfg = _config_from_hf_json(json.load(open(cfg_path)))
+
+        def it():
+            for f in files:
+                with safe_open(f, framework="pt") as sf:
+                    for name in sf.keys():
+                        n = name
+                        if n.startswith("visual."):
+                            n = "model." + n  # pre-5.x naming
+                        elif n.startswith("model.") and not n.startswith(("model.visual.", "model.language_model.")):
+                            n = "model.language_model." + n[len("model."):]
+                        yield n, sf.get_tensor(name)
+
+        return cls.from_state_dict(cfg, it(), device_map if isinstance(device_map, str) else "cuda")
+
+    def _build_native(self) -> _cabi.NativeModel:
+        t, v, w = self.config.text_config, self.config.vision_config, self.weights
+        cfg = _cabi.ModelConfig(
+            vit_depth=v.depth, vit_dim=v.embed_dim, vit_heads=v.num_heads, vit_mlp=v.mlp_dim, patch_dim=v.patch_dim,
+            merge=v.spatial_merge_size, vit_out=v.hidden_size, hidden=t.hidden_size, inter=t.intermediate_size,
+            layers=t.num_hidden_layers, q_heads=t.num_attention_heads, kv_heads=t.num_key_value_heads,
+            vocab=t.vocab_size, rms_eps=t.rms_norm_eps, rope_theta=t.rope_theta, mrope_t=t.mrope_section[0],
+            mrope_h=t.mrope_section[1], video_token_id=self.config.video_token_id)
+        p = lambda x: x.data_ptr()
+        vit_arr = (_cabi.VitBlockW * v.depth)(*[
+            _cabi.VitBlockW(p(b.norm1_w), p(b.norm1_b), p(b.norm2_w), p(b.norm2_b), p(b.qkv_w), p(b.qkv_b), p(b.proj_w),
+                            p(b.proj_b), p(b.fc1_w), p(b.fc1_b), p(b.fc2_w), p(b.fc2_b)) for b in w.vit_blocks])
+        lay_arr = (_cabi.LayerW * t.num_hidden_layers)(*[
+            _cabi.LayerW(p(l.ln1_w), p(l.qkv_w), p(l.qkv_b), p(l.o_w), p(l.ln2_w), p(l.gate_up_w), p(l.down_w))
+            for l in w.layers])
+        mw = _cabi.ModelWeights(
+            p(w.patch_w), vit_arr, p(w.merger_ln_w), p(w.merger_ln_b), p(w.merger_fc1_w), p(w.merger_fc1_b),
+            p(w.merger_fc2_w), p(w.merger_fc2_b), p(w.embed), lay_arr, p(w.final_norm_w), p(w.lm_head),
+            p(self.text_inv_freq), p(self.vit_inv_freq))
+        return _cabi.NativeModel(self.ctx, cfg, mw, keepalive=(vit_arr, lay_arr, w))
+
+    def _ensure_workspace(self, patches: int, tokens: int):
+        if patches <= self._cap_patches and tokens <= self._cap_tokens:
+            return
+        self._cap_patches = max(self._cap_patches, patches)
+        self._cap_tokens = max(self._cap_tokens, tokens)
+        torch.cuda.synchronize(self.device)
+        self._native.bind_workspace(self._cap_patches, self._cap_tokens, self.device)
+        self._graphs = {}
+
+    # ------------------------------------------------------------------------------------------
+    # HF-surface helpers
+    # ------------------------------------------------------------------------------------------
+    def eval(self):
+        return self
+
+    def to(self, *_, **__):
+        return self
+
+    def new_cache(self) -> PagedKVCache:
+        return PagedKVCache(self.pool)
+
+    def _sampling(self, repetition_penalty, logits_processor, max_new_tokens) -> _cabi.Sampling:
+        thr_token, thr_base, thr_step = -1, 0.0, 0.0
+        for proc in logits_processor or []:
+            if isinstance(proc, ThresholdLogitsProcessor) or all(hasattr(proc, a) for a in ("token_id", "base_threshold", "step")):
+                thr_token, thr_base, thr_step = int(proc.token_id), float(proc.base_threshold), float(proc.step)
+            else:
+                raise NotImplementedError(f"logits processor {type(proc).__name__} is not supported by the native "
+                                          "sampling kernel (supported: ThresholdLogitsProcessor)")
+        return _cabi.Sampling(float(repetition_penalty), thr_token, thr_base, thr_step, int(self.config.eos_token_id),
+                              int(max_new_tokens))
+
+    # ------------------------------------------------------------------------------------------
+    # the hot path
+    # ------------------------------------------------------------------------------------------
+    @torch.inference_mode()
+    def get_video_features(self, pixel_values_videos: torch.Tensor, video_grid_thw: torch.Tensor) -> torch.Tensor:
+        """ViT + merger for the videos of one call (mq2vl.py:1094-1112): [sum t*h*w, 1176] f32 -> [n_tok, H] bf16."""
+        grids = video_grid_thw.tolist() if isinstance(video_grid_thw, torch.Tensor) else list(video_grid_thw)
+        v = self.config.vision_config
+        m2 = v.spatial_merge_size ** 2
+        n_rows = sum(t * h * w for t, h, w in grids)
+        if pixel_values_videos.shape != (n_rows, v.patch_dim):
+            raise ValueError(f"pixel_values_videos has shape {tuple(pixel_values_videos.shape)}, expected {(n_rows, v.patch_dim)}")
+        px = pixel_values_videos.to(device=self.device, dtype=torch.float32, non_blocking=True).contiguous()
+        self._ensure_workspace(max(t * h * w for t, h, w in grids), 0)
+        out = torch.empty((n_rows // m2, v.hidden_size), dtype=torch.bfloat16, device=self.device)
+        r0 = 0
+        for t, h, w in grids:
+            n = t * h * w
+            self._native.vit_forward(px[r0:r0 + n], t, h, w, out[r0 // m2:(r0 + n) // m2])
+            r0 += n
+        return out
+
+    @torch.inference_mode()
+    def generate(self, input_ids: torch.Tensor = None, pixel_values_videos: Optional[torch.Tensor] = None,
+                 video_grid_thw: Optional[torch.Tensor] = None, past_key_values: Optional[PagedKVCache] = None,
+                 return_dict_in_generate: bool = True, do_sample: Optional[bool] = None,
+                 repetition_penalty: float = 1.0, logits_processor=None, max_new_tokens: int = 16,
+                 pad_token_id: Optional[int] = None, attention_mask=None, mm_token_type_ids=None,
+                 pixel_values=None, image_grid_thw=None, output_logits: bool = False,
+                 _forced_ids: Optional[List[int]] = None, **unsupported):
+        """The subset of GenerationMixin.generate that LiveCC's streaming loop uses (see module docstring).
+        input_ids: [1, L] int64 = full id history (REF/demo/infer.py:159-160); the cache decides how many
+        trailing ids are new (gen/utils.py:3747-3758). Greedy decoding (do_sample=True is accepted only with
+        the Qwen2-VL generation defaults, top_k = 1, which is greedy)."""
+        if unsupported:
+            raise TypeError(f"generate() got unsupported arguments {sorted(unsupported)}")
+        if pixel_values is not None or image_grid_thw is not None:
+            raise NotImplementedError("image inputs are outside the LiveCC streaming path (video only)")
+        if input_ids is None or input_ids.dim() != 2 or input_ids.shape[0] != 1:
+            raise ValueError("input_ids must be [1, L] (one stream per call)")
+        if do_sample is None:
+            do_sample = False
+        if do_sample and self.generation_config.top_k != 1:
+            raise NotImplementedError("do_sample=True is only supported with top_k=1 (the Qwen2-VL generation default)")
+        if max_new_tokens < 1:
+            raise ValueError("max_new_tokens must be >= 1")
+        cfg = self.config
+        cache = past_key_values if past_key_values is not None else self.new_cache()
+        if not isinstance(cache, PagedKVCache) or cache.pool is not self.pool:
+            raise TypeError("past_key_values must be a PagedKVCache returned by this model's generate()")
+        ids_dev = input_ids.to(self.device)
+        L = ids_dev.shape[1]
+        past = cache.seq_len
+        S = L - past
+        if S <= 0:
+            raise ValueError(f"input_ids has {L} ids but the cache already holds {past}")
+
+        # ---- positions (host integers; first turn only needs the ids on the host) ----
+        if past == 0 or cache.rope_delta is None:
+            ids_host = ids_dev[0].tolist()
+            grids = video_grid_thw.tolist() if video_grid_thw is not None else []
+            pos3, delta = get_rope_index(ids_host, grids, cfg.video_token_id, cfg.image_token_id,
+                                         cfg.vision_config.spatial_merge_size, self.legacy_4x_positions)
+            cache.rope_delta = delta
+            pos3_dev = pos3.to(torch.int32).to(self.device).contiguous()
+        else:
+            base = torch.arange(past + cache.rope_delta, past + cache.rope_delta + S, dtype=torch.int32, device=self.device)
+            pos3_dev = base.view(1, -1).expand(3, -1).contiguous()
+
+        # ---- vision tower ----
+        video_embeds = None
+        n_video_expected = -1
+        if pixel_values_videos is not None:
+            if video_grid_thw is None:
+                raise ValueError("video_grid_thw is required with pixel_values_videos")
+            video_embeds = self.get_video_features(pixel_values_videos, video_grid_thw)
+            n_video_expected = video_embeds.shape[0]
+
+        # ---- capacity, buffers, device scalars ----
+        self._ensure_workspace(0, S)
+        cache.ensure_tokens(past + S + max_new_tokens)
+        cache.ensure_seq_capacity(L + max_new_tokens + 1)
+        cache.seq_buf[:L].copy_(ids_dev[0])
+        sc_host = torch.tensor([past + S, past + S + cache.rope_delta, 0, 0, L, 0, 0, 0], dtype=torch.int32)
+        cache.scalars.copy_(sc_host, non_blocking=False)
+        sp = self._sampling(repetition_penalty, logits_processor, max_new_tokens)
+        st = cache.stream_state()
+        new_ids = cache.seq_buf[past:L]
+
+        # ---- prefill + first token ----
+        self._native.prefill(st, new_ids, pos3_dev, S, past, video_embeds, sp)
+        logits_out = [self._raw_logits().clone()] if output_logits else None
+        if _forced_ids is not None:
+            self._force_token(cache, L, 0, _forced_ids, max_new_tokens)
+
+        # ---- decode steps ----
+        n_steps = max_new_tokens - 1
+        if output_logits or _forced_ids is not None:
+            for i in range(n_steps):
+                self._native.decode_steps(st, 1, self.nsplit, sp)
+                if output_logits:
+                    logits_out.append(self._raw_logits().clone())
+                if _forced_ids is not None and i + 1 < len(_forced_ids):
+                    self._force_token(cache, L, i + 1, _forced_ids, max_new_tokens)
+        elif n_steps > 0:
+            self._run_decode(cache, st, sp, n_steps)
+
+        # ---- one host sync per generate(): read the stream scalars ----
+        sc = cache.scalars.tolist()
+        n_gen = sc[_cabi.SC_N_GENERATED]
+        cache.seq_len = sc[_cabi.SC_KV_LEN]
+        if n_video_expected >= 0:
+            n_video_ids = sc[_cabi.SC_VIDEO_TOKENS]
+            if n_video_ids != n_video_expected:
+                raise ValueError(f"Video features and video tokens do not match, tokens: {n_video_ids}, "
+                                 f"features: {n_video_expected}")  # mq2vl.py:1169-1175
+        sequences = cache.seq_buf[: L + n_gen].clone().view(1, -1)
+        self.last_stats = {"prefill_tokens": S, "generated": n_gen, "kv_len": cache.seq_len}
+        if output_logits and logits_out is not None:
+            logits_out = logits_out[:n_gen]
+        out = GenerateOutput(sequences=sequences, past_key_values=cache, logits=logits_out)
+        return out if return_dict_in_generate else sequences
+
+    # ------------------------------------------------------------------------------------------
+    def _run_decode(self, cache: PagedKVCache, st, sp: _cabi.Sampling, n_steps: int):
+        if not self.use_cuda_graph:
+            self._native.decode_steps(st, n_steps, self.nsplit, sp)
+            return
+        key = (cache.graph_key(), self._native.workspace.data_ptr(), self.nsplit, sp.repetition_penalty, sp.thr_token,
+               sp.thr_base, sp.thr_step, sp.eos_token_id, sp.max_new_tokens)
+        g = self._graphs.get(key)
+        if g is None:
+            # capture ONE decode step (28 layers + lm_head + token selection); replay it n_steps times.
+            # All step-varying state (kv_len, position, token, finished flag) lives in device memory.
+            if len(self._graphs) > 16:
+                self._graphs.clear()
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(side):
+                with torch.cuda.graph(g, stream=side, capture_error_mode="thread_local"):
+                    self._native.decode_steps(st, 1, self.nsplit, sp)
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            self._graphs[key] = g
+        for _ in range(n_steps):
+            g.replay()
+
+    def _raw_logits(self) -> torch.Tensor:
+        off = self._native.logits_offset
+        V = self.config.text_config.vocab_size
+        return self._native.workspace[off:off + 4 * V].view(torch.float32)
+
+    def _force_token(self, cache: PagedKVCache, L: int, step: int, forced: List[int], max_new_tokens: int):
+        """Teacher forcing (parity tests): replace the token just selected by the oracle's token."""
+        tok = int(forced[step])
+        cache.seq_buf[L + step] = tok
+        off = self._native.decode_hidden_offset
+        H = self.config.text_config.hidden_size
+        self._native.workspace[off:off + 2 * H].view(torch.bfloat16).copy_(self.weights.embed[tok])
+        cache.scalars[_cabi.SC_LAST_TOKEN] = tok
+        done = tok == self.config.eos_token_id or step + 1 >= max_new_tokens or step + 1 >= len(forced)
+        cache.scalars[_cabi.SC_FINISHED] = 1 if done else 0
+
+
+def _config_from_hf_json(d: dict) -> LiveCCConfig:
+    from .config import TextConfig, VisionConfig
+
+    tc = d.get("text_config", d)
+    vc = d.get("vision_config", {})
+    rp = tc.get("rope_parameters") or tc.get("rope_scaling") or d.get("rope_scaling") or {}
+    text = TextConfig(
+        vocab_size=tc.get("vocab_size", 152064), hidden_size=tc.get("hidden_size", 3584),
+        intermediate_size=tc.get("intermediate_size", 18944), num_hidden_layers=tc.get("num_hidden_layers", 28),
+        num_attention_heads=tc.get("num_attention_heads", 28), num_key_value_heads=tc.get("num_key_value_heads", 4),
+        rms_norm_eps=tc.get("rms_norm_eps", 1e-6), rope_theta=rp.get("rope_theta", tc.get("rope_theta", 1e6)),
+        mrope_section=tuple(rp.get("mrope_section", (16, 24, 24))))
+    vis = VisionConfig(
+        depth=vc.get("depth", 32), embed_dim=vc.get("embed_dim", 1280), hidden_size=vc.get("hidden_size", 3584),
+        mlp_ratio=vc.get("mlp_ratio", 4), num_heads=vc.get("num_heads", 16), in_channels=vc.get("in_channels", 3),
+        patch_size=vc.get("patch_size", 14), spatial_merge_size=vc.get("spatial_merge_size", 2),
+        temporal_patch_size=vc.get("temporal_patch_size", 2))
+    return LiveCCConfig(
+        text_config=text, vision_config=vis, image_token_id=d.get("image_token_id", 151655),
+        video_token_id=d.get("video_token_id", 151656), vision_start_token_id=d.get("vision_start_token_id", 151652),
+        vision_end_token_id=d.get("vision_end_token_id", 151653), bos_token_id=d.get("bos_token_id", 151643),
+        eos_token_id=d.get("eos_token_id", 151645), name=d.get("_name_or_path", "livecc"))

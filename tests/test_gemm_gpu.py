@@ -68,7 +68,8 @@ def test_gemm_activation_epilogues(ctx, M, N, K):
     out = ctx.gemm(a, b, bias=bias, epilogue=A.EPI_BIAS_GELU)
     assert _close(out, torch.nn.functional.gelu(lin)) < 1e-3
     out = ctx.gemm(a, b, bias=bias, epilogue=A.EPI_BIAS)
-    assert _close(out, lin, ulps=1) < 1e-3
+    assert _close(out, lin, ulps=1) < 5e-3  # accumulation-order flips at the bf16 rounding boundary
+    assert _close(out, lin, ulps=2) == 0
 
 
 @pytest.mark.parametrize("M,I,K", [(281, 18944, 3584), (64, 2432, 896), (300, 96, 64)])
