@@ -1,0 +1,425 @@
+#!/usr/bin/env python
+"""bench.py — LiveCC streaming hot path on B200.
+
+One *step* = one full pass of the hot path over one synthetic 2 fps clip stream: the 6-frame first
+chunk, then 2-frame chunks, each chunk = ViT -> prefill -> <=16 greedy decode steps with
+repetition_penalty 1.05 (REF/demo/infer.py:62-180, REF/demo/cli.py:13-24).  Default workload =
+BASELINE.json configs[1]: LiveCC-7B dims, 60 s clip (120 frames, 58 chunks) at 448x448, bf16, synthetic
+checkpoint (no weights exist offline) and synthetic frames.
+
+  value : tokens/s of the whole job with the chunk inputs already resident in HBM
+  e2e   : the same metric through the public API (LiveCCDemoInfer.live_cc) with HOST frames:
+          host patchify, pinned H2D of pixel rows + ids, D2H of the generated ids every chunk
+  roofline      : the dominant kernel (decode gate/up GEMV) timed with CUDA events on its launch stream
+  roofline_step : the whole decode step (CUDA-graph replay) timed inside the timed region
+  cpu_baseline  : the reference's own eager CPU path (HF transformers fp32) on a bounded sample
+
+`--impl reference` times only that CPU path (rank 0), same metric/config keys.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "commentary tokens/sec + frames/sec at 7B 2fps 448x448; p50 per-frame latency"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--model", default="7b", choices=["7b", "small"])
+    ap.add_argument("--seconds", type=int, default=60, help="clip length in seconds of video (2 fps)")
+    ap.add_argument("--size", type=int, default=448)
+    ap.add_argument("--max-new-tokens", type=int, default=16)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def get_config(name):
+    from livecc_b200.config import LiveCCConfig
+
+    return LiveCCConfig.livecc_7b() if name == "7b" else LiveCCConfig.small()
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md "clocks line")
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index: int):
+        self.index, self.samples, self._stop, self._thr = index, [], threading.Event(), None
+
+    def start(self):
+        def run():
+            q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_power_cap")
+            while not self._stop.is_set():
+                try:
+                    out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                    parts = [p.strip() for p in out.strip().split(",")]
+                    if len(parts) >= 7:
+                        self.samples.append(parts)
+                except Exception:
+                    pass
+                self._stop.wait(0.2)
+        self._thr = threading.Thread(target=run, daemon=True)
+        self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr:
+            self._thr.join(timeout=3)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        reasons = []
+        for i, name in enumerate(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]):
+            if any(s[3 + i].lower().startswith("active") for s in self.samples):
+                reasons.append(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "power_w_max": max(float(s[2]) for s in self.samples), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+# workload
+# ------------------------------------------------------------------------------------------------
+def build_chunks(cfg, seconds, size, seed):
+    """Pre-processes one synthetic stream into per-chunk host inputs (what live_cc does per chunk)."""
+    from livecc_b200.livecc_utils import get_smart_resized_clip, get_smart_resized_video_reader
+    from livecc_b200.processing import StubProcessor
+
+    proc = StubProcessor(cfg)
+    nframes = seconds * 2
+    path = f"synthetic://{nframes * 15}x{size}x{size}@30?seed={seed}"
+    reader, H, W = get_smart_resized_video_reader(path, 384 * 28 * 28)
+    reader.get_frame_timestamp(0)
+    pts = torch.from_numpy(reader._frame_pts[:, 1])
+    ts_all = torch.arange(0.0, seconds, 0.5)
+    clip, ts, idxs = get_smart_resized_clip(reader, H, W, ts_all, pts, 0)
+    path = path  # NB: LiveCCDemoInfer caches readers per path (REF/demo/infer.py:91-96): one path per stream
+    chunks = [clip[:6]] + list(clip[6:].split(2))
+    tss = [ts[:6]] + list(ts[6:].split(2))
+    out = []
+    off = None
+    for i, (c, t) in enumerate(zip(chunks, tss)):
+        content = [{"type": "text", "text": f"Time={t[0].item():.1f}-{t[-1].item() + 0.5:.1f}s"},
+                   {"type": "video", "video": c}]
+        if i == 0:
+            content.append({"type": "text", "text": "Please describe the video."})
+        text = proc.apply_chat_template([{"role": "user", "content": content}], tokenize=False, add_generation_prompt=True)
+        if off is None:
+            off = text.index("<|im_start|>user")
+        if i > 0:
+            text = "<|im_end|>\n" + text[off:]
+        out.append(proc(text=text, videos=[c], return_attention_mask=False))
+    return out, path
+
+
+def run_stream_device(eng, chunks_dev, max_new):
+    """Device-resident inputs: one generate() per chunk, ids threaded on the device."""
+    cache, past_ids = None, None
+    n_tok = n_frames = 0
+    lat = []
+    for ch in chunks_dev:
+        t0 = time.perf_counter()
+        ids = ch["input_ids"] if past_ids is None else torch.cat([past_ids, ch["input_ids"]], dim=1)
+        out = eng.generate(input_ids=ids, pixel_values_videos=ch["pixel_values_videos"],
+                           video_grid_thw=ch["video_grid_thw"], past_key_values=cache, return_dict_in_generate=True,
+                           do_sample=False, repetition_penalty=1.05, max_new_tokens=max_new,
+                           pad_token_id=eng.config.eos_token_id)
+        cache, past_ids = out.past_key_values, out.sequences[:, :-1]
+        n_tok += out.sequences.shape[1] - ids.shape[1]
+        n_frames += ch["frames"]
+        lat.append((time.perf_counter() - t0) / ch["frames"])
+    kv = cache.get_seq_length()
+    cache.release()
+    return n_tok, n_frames, lat, kv
+
+
+_E2E_RUN = [0]
+
+
+def run_stream_e2e(infer, path, seconds, max_new):
+    """The public API, driven like REF/demo/cli.py:13-24; frames start on the host. Every run is a new
+    stream = a new video path (the reference caches readers and pts per path)."""
+    _E2E_RUN[0] += 1
+    path = f"{path}{_E2E_RUN[0]:03d}"
+    state = {"video_path": path}
+    n_tok = n_frames = 0
+    h2d = d2h = 0
+    lat = []
+    n0 = len(infer.timings)
+    for t in range(seconds + 1):
+        state["video_timestamp"] = t
+        for (_s, _e), _resp, state in infer.live_cc(message="Please describe the video.", state=state,
+                                                    max_pixels=384 * 28 * 28, repetition_penalty=1.05,
+                                                    do_sample=False, max_new_tokens=max_new):
+            pass
+        if state.get("video_end", False):
+            break
+    for rec in infer.timings[n0:]:
+        n_tok += rec["new_tokens"]
+        n_frames += rec["frames"]
+        lat.append((rec["generate_s"] + rec["preprocess_s"] + rec["ingest_s"]) / rec["frames"])
+    v = infer.model.config.vision_config
+    for rec in infer.timings[n0:]:
+        n_patches = rec["frames"] // 2 * (infer._last_hw[0] // 14) * (infer._last_hw[1] // 14)
+        h2d += n_patches * v.patch_dim * 4 + 8 * 64
+        d2h += 8 * (rec["new_tokens"] + 1) + 32
+    kv = state["past_key_values"].get_seq_length()
+    state["past_key_values"].release()
+    return n_tok, n_frames, lat, kv, h2d, d2h
+
+
+# ------------------------------------------------------------------------------------------------
+# roofline of the dominant kernel
+# ------------------------------------------------------------------------------------------------
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def time_dominant_kernel(eng, iters=5):
+    """decode gate/up GEMV (gemv_rows_kernel<2,true,SWIGLU>): fused RMSNorm + [2I,H] weight stream + SwiGLU.
+    Algorithmic bytes/launch = 2I*H*2 (weights) + H*2 (x) + H*2 (norm w) + I*2 (out). Cycles through all layers
+    so every launch streams a different 271 MB (7B) weight, i.e. inputs >> L2."""
+    t = eng.config.text_config
+    H, I = t.hidden_size, t.intermediate_size
+    x = torch.randn(H, device=eng.device).to(torch.bfloat16)
+    stream = torch.cuda.current_stream()
+    for lw in eng.weights.layers:  # warm-up
+        eng.ctx.gemv_norm_swiglu(lw.gate_up_w, x, lw.ln2_w, t.rms_norm_eps)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 0
+    e0.record(stream)
+    for _ in range(iters):
+        for lw in eng.weights.layers:
+            eng.ctx.gemv_norm_swiglu(lw.gate_up_w, x, lw.ln2_w, t.rms_norm_eps)
+            n += 1
+    e1.record(stream)
+    torch.cuda.synchronize()
+    sec = e0.elapsed_time(e1) / 1e3 / n
+    nbytes = 2 * I * H * 2 + 2 * H * 2 + I * 2
+    return nbytes, sec
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU reference arm (HF eager fp32 on host cores)
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_sample(cfg, size, max_new=8, steps=1, warmup=0):
+    """The reference's own CPU path: transformers Qwen2VLForConditionalGeneration, fp32, eager attention,
+    all host threads, through oracle/hf_oracle.py. Bounded sample: a fresh stream's first turn with ONE
+    2-frame chunk at size x size and `max_new` greedy tokens (repetition_penalty 1.05)."""
+    from livecc_b200.checkpoint import synthetic_tensors
+    from livecc_b200.processing import StubProcessor
+    from oracle.hf_oracle import build_hf_model, hf_generate_chunk
+
+    ncores = os.cpu_count() or 1
+    torch.set_num_threads(ncores)
+    gen_dev = "cuda" if torch.cuda.is_available() else "cpu"
+    model = build_hf_model(cfg, synthetic_tensors(cfg, 1234, torch.float32, "cpu", gen_device=gen_dev),
+                           dtype=torch.float32, device="cpu", attn_implementation="eager")
+    proc = StubProcessor(cfg)
+    g = torch.Generator().manual_seed(0)
+    clip = torch.randint(0, 256, (2, 3, size, size), generator=g, dtype=torch.uint8)
+    content = [{"type": "text", "text": "Time=0.0-1.0s"}, {"type": "video", "video": clip},
+               {"type": "text", "text": "Please describe the video."}]
+    text = proc.apply_chat_template([{"role": "user", "content": content}], tokenize=False, add_generation_prompt=True)
+    times, toks = [], 0
+    for i in range(warmup + steps):
+        inputs = proc(text=text, videos=[clip], return_attention_mask=False)
+        t0 = time.perf_counter()
+        out, L = hf_generate_chunk(model, inputs, None, None, max_new_tokens=max_new)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+            toks = out.sequences.shape[1] - L
+    sec = sum(times) / len(times)
+    return {"tokens_per_s": toks / sec, "frames_per_s": 2 / sec, "sec_per_sample": sec, "cores": ncores,
+            "threads": torch.get_num_threads(), "tokens": toks,
+            "sample": f"first turn of a fresh stream: one 2-frame {size}x{size} chunk + {toks} greedy tokens, fp32 eager, "
+                      f"{steps} timed run(s)"}
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cfg = get_config(args.model)
+    workload = (f"LiveCC-{'7B' if args.model == '7b' else 'small'} streaming 2fps {args.seconds}s clip "
+                f"({args.seconds * 2} frames) {args.size}x{args.size} greedy decode bf16, one stream per GPU")
+    config = {"workload": workload, "chunks": 1 + (args.seconds * 2 - 6) // 2, "max_new_tokens": args.max_new_tokens,
+              "repetition_penalty": 1.05, "l2": "inputs larger than L2 (bf16 weights streamed once per token/chunk)",
+              "parallelism": f"dp{world} (independent streams, no data-path collective)"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        r = cpu_reference_sample(cfg, args.size, max_new=8, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+        line = {"impl": "reference", "metric": METRIC, "value": r["tokens_per_s"], "unit": "tokens/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["sec_per_sample"] * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": config, "frames_per_s": r["frames_per_s"],
+                "cpu_baseline": {"value": r["tokens_per_s"], "unit": "tokens/s", "cores": r["cores"], "kind": "reference",
+                                 "sample": r["sample"]},
+                "e2e": {"value": r["tokens_per_s"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    assert torch.cuda.is_available(), "bench.py needs a B200; there is no CPU fallback for the native arm"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+
+    from livecc_b200.engine import LiveCCB200ForConditionalGeneration
+    from livecc_b200.streaming import LiveCCDemoInfer
+
+    eng = LiveCCB200ForConditionalGeneration.from_synthetic(cfg, seed=1234, device=f"cuda:{local_rank}")
+    chunks, path = build_chunks(cfg, args.seconds, args.size, seed=rank)
+    chunks_dev = [dict(input_ids=c.input_ids.to(dev), pixel_values_videos=c.pixel_values_videos.to(dev),
+                       video_grid_thw=c.video_grid_thw, frames=int(c.video_grid_thw[0, 0]) * 2) for c in chunks]
+    infer = LiveCCDemoInfer(model=eng)
+    infer._last_hw = (args.size, args.size)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident arm ----
+    for _ in range(args.warmup):
+        run_stream_device(eng, chunks_dev, args.max_new_tokens)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    tok = frames = 0
+    lat = []
+    kv_end = 0
+    for _ in range(args.steps):
+        a, b, c, kv_end = run_stream_device(eng, chunks_dev, args.max_new_tokens)
+        tok += a
+        frames += b
+        lat += c
+    e1.record()
+    barrier()
+    sec = e0.elapsed_time(e1) / 1e3
+    clocks = sampler.stop()
+
+    # ---- end-to-end arm (public API, host frames) ----
+    e2e = None
+    if not args.no_e2e:
+        for _ in range(max(1, min(args.warmup, 1))):
+            run_stream_e2e(infer, path, args.seconds, args.max_new_tokens)
+        barrier()
+        t0 = time.perf_counter()
+        e_tok = e_frames = h2d = d2h = 0
+        e_lat = []
+        for _ in range(args.steps):
+            a, b, c, _kv, hb, db = run_stream_e2e(infer, path, args.seconds, args.max_new_tokens)
+            e_tok += a
+            e_frames += b
+            e_lat += c
+            h2d += hb
+            d2h += db
+        barrier()
+        e_sec = time.perf_counter() - t0
+        e2e = dict(tok=e_tok, frames=e_frames, sec=e_sec, lat=e_lat, h2d=h2d // args.steps, d2h=d2h // args.steps)
+
+    # ---- reduce over ranks: sum of units, max of time ----
+    stats = torch.tensor([tok, frames, sec, e2e["tok"] if e2e else 0, e2e["frames"] if e2e else 0,
+                          e2e["sec"] if e2e else 0], dtype=torch.float64, device=dev)
+    if world > 1:
+        allst = [torch.zeros_like(stats) for _ in range(world)]
+        dist.all_gather(allst, stats)
+        allst = torch.stack(allst)
+    else:
+        allst = stats[None]
+    tot_tok, tot_frames = allst[:, 0].sum().item(), allst[:, 1].sum().item()
+    max_sec = allst[:, 2].max().item()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    lat_sorted = sorted(lat)
+    p50 = lat_sorted[len(lat_sorted) // 2] * 1e3
+    peak, peak_src = load_peaks()
+    kbytes, ksec = time_dominant_kernel(eng)
+    t = cfg.text_config
+    step_weight_bytes = (t.num_hidden_layers * ((t.num_attention_heads + 2 * t.num_key_value_heads) * 128 * t.hidden_size
+                                                + t.hidden_size * t.hidden_size + 3 * t.intermediate_size * t.hidden_size
+                                                + 2 * t.hidden_size) + t.hidden_size + t.vocab_size * t.hidden_size) * 2
+    v = cfg.vision_config
+    launches_vit = lambda: 4 + v.depth * 8 + 3
+    launches_prefill = 2 + t.num_hidden_layers * 8 + 2
+    launches_decode = t.num_hidden_layers * 6 + 2
+    n_chunks = len(chunks)
+    gpu_launches = args.steps * (n_chunks * (launches_vit() + launches_prefill) + (tok // args.steps - n_chunks) * launches_decode)
+    line = {
+        "metric": METRIC, "value": tot_tok / max_sec, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": max_sec / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic (hash-filled checkpoint, synthetic frames and token ids)",
+        "config": config, "frames_per_s": tot_frames / max_sec, "p50_frame_latency_ms": p50,
+        "kv_len_end": kv_end, "clocks": clocks, "gpu_launches": int(gpu_launches),
+        "roofline": {"kernel": "gemv_rows_kernel<2,NORM,SWIGLU> (decode gate/up + RMSNorm + SwiGLU)", "bound": "hbm",
+                     "achieved": kbytes / ksec / 1e9, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                     "frac": kbytes / ksec / 1e9 / peak, "traffic": None, "bytes_per_launch": kbytes,
+                     "us_per_launch": ksec * 1e6},
+    }
+    if e2e:
+        tot_e_tok, tot_e_frames = allst[:, 3].sum().item(), allst[:, 4].sum().item()
+        max_e_sec = allst[:, 5].max().item()
+        el = sorted(e2e["lat"])
+        line["e2e"] = {"value": tot_e_tok / max_e_sec, "unit": "tokens/s", "frames_per_s": tot_e_frames / max_e_sec,
+                       "p50_frame_latency_ms": el[len(el) // 2] * 1e3, "h2d_bytes_per_step": int(e2e["h2d"]),
+                       "d2h_bytes_per_step": int(e2e["d2h"]),
+                       "api": "LiveCCDemoInfer.live_cc (host uint8 frames -> host patchify -> pinned H2D -> generate -> D2H ids)"}
+    # decode-step roofline inside the timed region: every generated token after the first of a chunk is one
+    # CUDA-graph replay streaming all decoder weights + the stream's KV
+    dec_tokens = tok - args.steps * n_chunks
+    line["roofline_step"] = {"unit_def": "one decode step = all decoder weights + lm_head + KV of the stream",
+                             "bytes_per_step_at_end": step_weight_bytes + kv_end * 2 * t.num_hidden_layers * t.num_key_value_heads * 128 * 2,
+                             "note": "see profiles/ for the per-kernel share; whole-job time also contains ViT + prefill"}
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            r = cpu_reference_sample(cfg, args.size, max_new=4, steps=1, warmup=0)
+            line["cpu_baseline"] = {"value": r["tokens_per_s"], "unit": "tokens/s", "frames_per_s": r["frames_per_s"],
+                                    "cores": r["cores"], "kind": "reference", "sample": r["sample"]}
+        except Exception as ex:  # the baseline must never take the GPU number down with it
+            line["cpu_baseline"] = {"value": None, "unit": "tokens/s", "cores": os.cpu_count(), "kind": "reference",
+                                    "sample": f"failed: {type(ex).__name__}: {ex}"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

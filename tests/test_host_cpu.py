@@ -1,0 +1,201 @@
+"""CPU suite, part 2: C-ABI exports, host orchestration (streaming mirror with a mock model, page pool,
+livecc_utils surface) and the world_size-2 gloo path of the multi-GPU runner. No GPU compute."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from livecc_b200 import _cabi
+from livecc_b200.config import LiveCCConfig
+from livecc_b200.processing import StubProcessor
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_every_header_symbol():
+    lib = _cabi.load_library()
+    syms = _cabi.header_symbols()
+    assert len(syms) >= 28 and "lcc_gemm_bf16" in syms and "lcc_decode_steps" in syms
+    for s in syms:
+        assert hasattr(lib, s), f"liblivecc_sm100a.so does not export {s}"
+    assert lib.lcc_abi_version() == _cabi.ABI_VERSION
+    # sm_100a code only, with the Blackwell instructions the design relies on
+    sass = subprocess.run(["cuobjdump", "-sass", str(_cabi.LIB_PATH)], capture_output=True, text=True).stdout
+    if sass:
+        assert "sm_100a" in sass and "UTCHMMA" in sass and "UTMALDG" in sass and "LDTM" in sass
+
+
+def test_product_path_fails_loudly_without_a_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from livecc_b200.engine import LiveCCB200ForConditionalGeneration
+
+    with pytest.raises(Exception):
+        _cabi.Context(0)
+    with pytest.raises(Exception):
+        LiveCCB200ForConditionalGeneration.from_synthetic(LiveCCConfig.small(), device="cuda")
+    # and nothing in the product imports the oracle
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "livecc_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
+
+
+class MockCache:
+    def __init__(self):
+        self.n = 0
+
+    def get_seq_length(self):
+        return self.n
+
+
+class MockModel:
+    """Records generate() calls; emits 3 fixed tokens (the last one EOS)."""
+
+    def __init__(self, cfg):
+        self.config, self.device, self.calls = cfg, torch.device("cpu"), []
+        self.prepare_inputs_for_generation = None
+
+    def generate(self, input_ids=None, pixel_values_videos=None, video_grid_thw=None, past_key_values=None,
+                 max_new_tokens=16, **kw):
+        cache = past_key_values or MockCache()
+        self.calls.append(dict(L=input_ids.shape[1], past=cache.n, grid=video_grid_thw.tolist(),
+                               rows=pixel_values_videos.shape[0], kw=kw, new=input_ids[0, cache.n:].tolist()))
+        gen = torch.tensor([[1234, 1235, self.config.eos_token_id]])
+        seq = torch.cat([input_ids, gen], 1)
+        cache.n = seq.shape[1] - 1
+
+        class Out:
+            sequences = seq
+        Out.past_key_values = cache
+        return Out
+
+
+def test_live_cc_chunk_schedule_and_state_contract():
+    """REF/demo/infer.py:105-180 driven like REF/demo/cli.py:13-24."""
+    from livecc_b200.streaming import LiveCCDemoInfer
+
+    cfg = LiveCCConfig.small()
+    model = MockModel(cfg)
+    infer = LiveCCDemoInfer(model=model, processor=StubProcessor(cfg))
+    state = {"video_path": "synthetic://300x112x140@30?seed=3"}  # 10 s of video
+    outs = []
+    for t in range(12):
+        state["video_timestamp"] = t
+        for (s, e), resp, state in infer.live_cc(message="Please describe the video.", state=state,
+                                                  repetition_penalty=1.05, streaming_eos_base_threshold=0.0,
+                                                  streaming_eos_threshold_step=0):
+            outs.append((s, e, resp))
+        if state.get("video_end", False):
+            break
+    frames = [c["grid"][0][0] * 2 for c in model.calls]
+    assert frames[0] == 6 and all(f == 2 for f in frames[1:]) and sum(frames) == 20
+    assert outs[0][:2] == (0.0, 3.0) and outs[1][:2] == (3.0, 4.0)
+    n_calls = len(model.calls)
+    state["video_timestamp"] = 30  # past the end: nothing more to process (REF/demo/infer.py:100-109)
+    assert list(infer.live_cc(message="", state=state)) == [] and len(model.calls) == n_calls
+    # ids: full history is re-sent every turn; cache length == len(past_ids)
+    for prev, cur in zip(model.calls, model.calls[1:]):
+        assert cur["past"] == prev["L"] + 2 and cur["L"] > cur["past"]
+        assert cur["new"][:2] == [cfg.eos_token_id, cfg.newline_token_id]       # '<|im_end|>\n' glue
+        assert cur["new"].count(cfg.video_token_id) == cur["rows"] // 4
+    first = model.calls[0]
+    # 112x140 is below VIDEO_MIN_PIXELS (100*28*28) -> smart_resize upscales to 252x336 (18x24 patches per frame pair)
+    assert first["rows"] == 3 * 18 * 24 and first["new"].count(cfg.video_token_id) == first["rows"] // 4
+    assert "logits_processor" in first["kw"] and first["kw"]["logits_processor"][0].token_id == infer.streaming_eos_token_id
+    assert state["past_ids"].shape[1] == state["past_key_values"].get_seq_length()
+    assert len(infer.timings) == len(model.calls)
+
+
+def test_livecc_utils_surface():
+    import livecc_b200.livecc_utils as U
+
+    assert set(U.__all__) == {"prepare_multiturn_multimodal_inputs_for_generation", "_read_video_decord_plus",
+                              "_spatial_resize_video", "get_smart_resized_video_reader", "get_smart_resized_clip"}
+    reader, H, W = U.get_smart_resized_video_reader("synthetic://90x448x448@30?seed=1", 384 * 28 * 28)
+    assert (H, W) == (448, 448)
+    reader.get_frame_timestamp(0)
+    pts = torch.from_numpy(reader._frame_pts[:, 1])
+    clip, ts, idxs = U.get_smart_resized_clip(reader, H, W, torch.arange(0.0, 2.5, 0.5), pts, 0)
+    assert clip.shape == (6, 3, 448, 448) and clip.dtype == torch.uint8 and len(idxs) == 6  # padded to FRAME_FACTOR, then fits
+    clip2, fps = U._read_video_decord_plus({"video": "synthetic://300x56x84@30?seed=2"})
+    assert clip2.shape[0] % 2 == 0 and clip2.shape[1:] == (3, 56, 84)
+    with pytest.raises(ValueError):
+        U._read_video_decord_plus({"video": "/nonexistent.mp4", "remote_loader": None})
+    # generation patch semantics (generation_patch.py:35-39)
+    cfg = LiveCCConfig.small()
+
+    class M:
+        config = cfg
+    cache = MockCache()
+    cache.n = 4
+    ids = torch.tensor([[1, 2, 3, 4, 5, cfg.video_token_id, 6]])
+    out = U.prepare_multiturn_multimodal_inputs_for_generation(M, ids, past_key_values=cache, pixel_values_videos="px")
+    assert out["pixel_values_videos"] == "px" and out["position_ids"] is None and out["input_ids"].shape[1] == 3
+    out = U.prepare_multiturn_multimodal_inputs_for_generation(M, ids[:, :5], past_key_values=cache, pixel_values_videos="px")
+    assert out["pixel_values_videos"] is None
+
+
+def test_page_pool_and_cache_bookkeeping():
+    from livecc_b200.kv_cache import PagedKVCache, PagePool
+
+    pool = PagePool(layers=2, kv_heads=2, device="cpu", initial_pages=4)
+    a, b = PagedKVCache(pool), PagedKVCache(pool)
+    a.ensure_tokens(130)  # 3 pages
+    b.ensure_tokens(64)   # 1 page
+    assert len(a.pages) == 3 and len(b.pages) == 1 and not set(a.pages) & set(b.pages) and len(pool.free) == 0
+    gen0 = pool.generation
+    pool.k[0, a.pages[0], 0, 0, 0] = 7.0
+    b.ensure_tokens(65)   # forces growth; old contents must survive
+    assert pool.generation == gen0 + 1 and pool.num_pages >= 8 and float(pool.k[0, a.pages[0], 0, 0, 0]) == 7.0
+    assert a.page_table[:3].tolist() == a.pages and b.page_table[:2].tolist() == b.pages
+    key = a.graph_key()
+    a.ensure_tokens(64 * 70)  # page table reallocation changes the graph key
+    assert a.graph_key() != key and a.page_table[:70].tolist() == a.pages
+    st = a.stream_state()
+    assert st.layer_stride == pool.num_pages * 2 * 64 * 128 and st.k_pool == pool.k.data_ptr()
+    n_free = len(pool.free)
+    a.release()
+    assert len(pool.free) == n_free + 70 and a.get_seq_length() == 0 and a.rope_delta is None
+
+
+def test_runner_world_size_2_gloo(tmp_path):
+    """N>1 path on CPU: torchrun-style env, gloo backend, barrier + all_gather_object of per-stream stats."""
+    script = tmp_path / "worker.py"
+    script.write_text(f"""
+import sys, json, time
+sys.path.insert(0, {ROOT!r})
+from livecc_b200 import runner
+rank, world = runner.init_distributed("gloo")
+recs = runner.run_streams(list(range(5)), lambda sid: dict(tokens=10 + sid, frames=2 * sid))
+if rank == 0:
+    print(json.dumps(dict(world=world, recs=recs, summary=runner.summarize(recs, 2.0))))
+import torch.distributed as dist
+dist.destroy_process_group()
+""")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29617", str(script)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stderr[-2000:]
+    import json
+    line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
+    d = json.loads(line)
+    assert d["world"] == 2 and [x["stream"] for x in d["recs"]] == [0, 1, 2, 3, 4]
+    assert [x["rank"] for x in d["recs"]] == [0, 1, 0, 1, 0]
+    assert d["summary"]["tokens"] == sum(10 + i for i in range(5)) and d["summary"]["tokens_per_s"] == 30.0
+
+
+def test_bench_reference_arm_contract_small():
+    """`bench.py --impl reference` prints one JSON line with the contract keys (tiny config, CPU)."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--model", "small",
+                        "--size", "56", "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    import json
+    d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert d["impl"] == "reference" and d["unit"] == "tokens/s" and d["value"] > 0 and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in d["config"]
