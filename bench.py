@@ -322,6 +322,8 @@ def main():
     tok = frames = 0
     lat = []
     kv_end = 0
+    for k in eng.phase_ms_total:
+        eng.phase_ms_total[k] = 0
     for _ in range(args.steps):
         a, b, c, kv_end = run_stream_device(eng, chunks_dev, args.max_new_tokens)
         tok += a
@@ -331,6 +333,7 @@ def main():
     barrier()
     sec = e0.elapsed_time(e1) / 1e3
     clocks = sampler.stop()
+    phases = dict(eng.phase_ms_total)
 
     # ---- end-to-end arm (public API, host frames) ----
     e2e = None
@@ -403,10 +406,18 @@ def main():
                        "api": "LiveCCDemoInfer.live_cc (host uint8 frames -> host patchify -> pinned H2D -> generate -> D2H ids)"}
     # decode-step roofline inside the timed region: every generated token after the first of a chunk is one
     # CUDA-graph replay streaming all decoder weights + the stream's KV
-    dec_tokens = tok - args.steps * n_chunks
-    line["roofline_step"] = {"unit_def": "one decode step = all decoder weights + lm_head + KV of the stream",
-                             "bytes_per_step_at_end": step_weight_bytes + kv_end * 2 * t.num_hidden_layers * t.num_key_value_heads * 128 * 2,
-                             "note": "see profiles/ for the per-kernel share; whole-job time also contains ViT + prefill"}
+    kv_bytes_tok = 2 * t.num_hidden_layers * t.num_key_value_heads * 128 * 2
+    dsteps = max(int(phases["decode_steps"]), 1)
+    ms_per_dstep = phases["decode"] / dsteps
+    bytes_avg = step_weight_bytes + (kv_end / 2) * kv_bytes_tok  # KV grows ~linearly over the clip: mean length ~ end/2
+    line["phases_ms_per_chunk"] = {"vit": phases["vit"] / max(phases["calls"], 1), "prefill": phases["prefill"] / max(phases["calls"], 1),
+                                   "decode": phases["decode"] / max(phases["calls"], 1), "host_and_sync": max_sec * 1e3 / (args.steps * n_chunks)
+                                   - (phases["vit"] + phases["prefill"] + phases["decode"]) / max(phases["calls"], 1)}
+    line["roofline_step"] = {"unit_def": "one decode step (CUDA-graph replay): all decoder weights + lm_head + the stream's KV, "
+                                         "timed with CUDA events inside the timed region",
+                             "bound": "hbm", "bytes_per_step_mean": int(bytes_avg), "ms_per_step": ms_per_dstep,
+                             "achieved": bytes_avg / (ms_per_dstep / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": bytes_avg / (ms_per_dstep / 1e3) / 1e9 / peak, "decode_steps": dsteps}
     if not args.no_cpu_baseline and world == 1:
         try:
             r = cpu_reference_sample(cfg, args.size, max_new=4, steps=1, warmup=0)

@@ -90,6 +90,9 @@ class LiveCCB200ForConditionalGeneration:
         self.use_cuda_graph = os.environ.get("LIVECC_B200_NO_GRAPH", "0") != "1"
         self.nsplit = max(1, min(64, (self.ctx.num_sms + t.num_key_value_heads - 1) // t.num_key_value_heads))
         self.last_stats = {}
+        # per-phase device time of the last generate() (CUDA events on the launch stream) and running totals
+        self.phase_ms_total = {"vit": 0.0, "prefill": 0.0, "decode": 0.0, "calls": 0, "decode_steps": 0}
+        self._ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
 
     @classmethod
     def from_synthetic(cls, config: LiveCCConfig, seed: int = 1234, device="cuda"):
@@ -256,6 +259,7 @@ class LiveCCB200ForConditionalGeneration:
             pos3_dev = base.view(1, -1).expand(3, -1).contiguous()
 
         # ---- vision tower ----
+        self._ev[0].record()
         video_embeds = None
         n_video_expected = -1
         if pixel_values_videos is not None:
@@ -264,6 +268,7 @@ class LiveCCB200ForConditionalGeneration:
             video_embeds = self.get_video_features(pixel_values_videos, video_grid_thw)
             n_video_expected = video_embeds.shape[0]
 
+        self._ev[1].record()
         # ---- capacity, buffers, device scalars ----
         self._ensure_workspace(0, S)
         cache.ensure_tokens(past + S + max_new_tokens)
@@ -281,6 +286,7 @@ class LiveCCB200ForConditionalGeneration:
         if _forced_ids is not None:
             self._force_token(cache, L, 0, _forced_ids, max_new_tokens)
 
+        self._ev[2].record()
         # ---- decode steps ----
         n_steps = max_new_tokens - 1
         if output_logits or _forced_ids is not None:
@@ -293,6 +299,7 @@ class LiveCCB200ForConditionalGeneration:
         elif n_steps > 0:
             self._run_decode(cache, st, sp, n_steps)
 
+        self._ev[3].record()
         # ---- one host sync per generate(): read the stream scalars ----
         sc = cache.scalars.tolist()
         n_gen = sc[_cabi.SC_N_GENERATED]
@@ -303,7 +310,12 @@ class LiveCCB200ForConditionalGeneration:
                 raise ValueError(f"Video features and video tokens do not match, tokens: {n_video_ids}, "
                                  f"features: {n_video_expected}")  # mq2vl.py:1169-1175
         sequences = cache.seq_buf[: L + n_gen].clone().view(1, -1)
-        self.last_stats = {"prefill_tokens": S, "generated": n_gen, "kv_len": cache.seq_len}
+        ph = [self._ev[i].elapsed_time(self._ev[i + 1]) for i in range(3)]
+        self.last_stats = {"prefill_tokens": S, "generated": n_gen, "kv_len": cache.seq_len, "vit_ms": ph[0],
+                           "prefill_ms": ph[1], "decode_ms": ph[2]}
+        tot = self.phase_ms_total
+        tot["vit"] += ph[0]; tot["prefill"] += ph[1]; tot["decode"] += ph[2]
+        tot["calls"] += 1; tot["decode_steps"] += max(n_gen - 1, 0)
         if output_logits and logits_out is not None:
             logits_out = logits_out[:n_gen]
         out = GenerateOutput(sequences=sequences, past_key_values=cache, logits=logits_out)
