@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define LCC_ABI_VERSION 2
+#define LCC_ABI_VERSION 3
 #define LCC_PAGE_SIZE 64
 
 typedef struct lcc_ctx lcc_ctx;
@@ -123,10 +123,11 @@ int lcc_attn_prefill(lcc_ctx* ctx, const void* q, int q_ld, const void* k_cache,
 
 /* One-token attention: RoPE of q, RoPE + append of the new k/v at slot scalars[LCC_SC_KV_LEN],
  * split-KV attention over the paged cache and merge. qkv: raw projections(+bias) of the new token.
- * part_o: f32[nsplit,Hq,128], part_ml: f32[nsplit,Hq,2] scratch; out: bf16[Hq*128]. */
+ * part_o: f32[nsplit,Hq,128], part_ml: f32[nsplit,Hq,2] scratch; counters: int32[Hkv], zero-initialised
+ * once by the caller (the kernel leaves them zero); out: bf16[Hq*128]. */
 int lcc_attn_decode(lcc_ctx* ctx, void* qkv, void* k_cache, void* v_cache, const int32_t* page_table,
                     const int32_t* scalars, const float* inv_freq, int Hq, int Hkv, int nsplit, float* part_o,
-                    float* part_ml, void* out, lcc_stream_t stream);
+                    float* part_ml, int32_t* counters, void* out, lcc_stream_t stream);
 
 /* Decode-step projections (M = 1), each fused with its neighbours in the layer
  * (Qwen2VLDecoderLayer.forward, mq2vl.py:613-662). `scalars` may be NULL (no early-exit flag). */

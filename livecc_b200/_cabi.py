@@ -13,7 +13,7 @@ PKG_DIR = Path(__file__).resolve().parent
 LIB_PATH = PKG_DIR / "liblivecc_sm100a.so"
 HEADER_PATH = PKG_DIR.parent / "include" / "livecc_b200.h"
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 PAGE_SIZE = 64
 
 # epilogue codes (LCC_EPI_*)
@@ -244,8 +244,11 @@ class Context:
         part_o = torch.empty((nsplit, Hq, 128), dtype=torch.float32, device=dev)
         part_ml = torch.empty((nsplit, Hq, 2), dtype=torch.float32, device=dev)
         out = torch.empty((Hq * 128,), dtype=torch.bfloat16, device=dev)
+        if getattr(self, "_attn_counters", None) is None:
+            self._attn_counters = torch.zeros(64, dtype=torch.int32, device=dev)
         self.call("lcc_attn_decode", _ptr(qkv), _ptr(k_cache), _ptr(v_cache), _ptr(page_table), _ptr(scalars),
-                  _ptr(inv_freq), _i(Hq), _i(Hkv), _i(nsplit), _ptr(part_o), _ptr(part_ml), _ptr(out), self.stream_ptr())
+                  _ptr(inv_freq), _i(Hq), _i(Hkv), _i(nsplit), _ptr(part_o), _ptr(part_ml), _ptr(self._attn_counters),
+                  _ptr(out), self.stream_ptr())
         return out
 
     def gemv_norm_bias(self, W, x, norm_w, eps, bias, scalars=None):

@@ -9,9 +9,10 @@
 //        Qwen2VLAttention, mq2vl.py:572-594 + eager_attention_forward :353-375.
 //  * attn_decode_kernel: one new token, split-KV over the paged cache; the 7 query heads of a KV
 //    group form one 16-row MMA tile; fuses the 1-D RoPE of q, the RoPE + append of the new k/v.
-//  * attn_combine_kernel: merges the split-KV partials.
+//    The last CTA of a KV group to finish merges the split-KV partials (no separate combine launch).
 // Softmax statistics are fp32; P is rounded to bf16 before P·V (as the reference does, :370).
 #include "common.cuh"
+#include "launch.h"
 #include "ops.h"
 
 namespace lcc {
@@ -364,7 +365,9 @@ struct DecodeAttnParams {
     const float* inv_freq;  // [64]
     int Hq, Hkv, nsplit;
     float* part_o;      // [nsplit, Hq, 128]
-    float* part_ml;     // [nsplit, Hq, 2]  (m in log2 domain already scaled, l)
+    float* part_ml;     // [nsplit, Hq, 2]  (running max (unscaled), l)
+    int* counters;      // [Hkv] arrival counters, zero between launches (last CTA of a group merges the splits)
+    bf16* out;          // [Hq * 128]
     float scale_log2;
 };
 
@@ -380,6 +383,8 @@ __device__ __forceinline__ void rope1d_row(const bf16* src, bf16* dst, int lane_
 
 __global__ void __launch_bounds__(128) attn_decode_kernel(const DecodeAttnParams p) {
     constexpr int D = 128, LDS = D + 8, BN = 64;
+    pdl_launch_dependents();
+    pdl_wait();  // qkv of this token comes from the previous kernel
     if (p.finished && *p.finished) return;
     extern __shared__ __align__(16) uint8_t smem_attn[];
     bf16* sq = reinterpret_cast<bf16*>(smem_attn);  // [16][LDS]
@@ -399,10 +404,10 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const DecodeAttnParams
 
     float* po = p.part_o + ((size_t)split * p.Hq + (size_t)g * G) * D;
     float* pml = p.part_ml + ((size_t)split * p.Hq + (size_t)g * G) * 2;
-    if (tile_begin >= tile_end) {  // empty split: neutral partial
+    const bool empty = tile_begin >= tile_end;
+    if (empty) {  // empty split: neutral partial
         if (threadIdx.x < G) { pml[threadIdx.x * 2] = -INFINITY; pml[threadIdx.x * 2 + 1] = 0.f; }
-        return;
-    }
+    } else {
 
     // ---- q: rotate the G heads of this group into smem (rows >= G zero) ----
     for (int i = threadIdx.x; i < 16 * 64; i += 128) {
@@ -515,30 +520,58 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const DecodeAttnParams
         po[(size_t)r * D + d] = acc;
         if (d == 0) { pml[r * 2] = M; pml[r * 2 + 1] = L; }
     }
-}
+    }  // !empty
 
-__global__ void __launch_bounds__(128) attn_combine_kernel(const float* __restrict__ part_o,
-                                                           const float* __restrict__ part_ml, int nsplit,
-                                                           int Hq, float scale_log2, bf16* __restrict__ out,
-                                                           const int* finished) {
-    if (finished && *finished) return;
-    const int h = blockIdx.x, d = threadIdx.x;
-    float M = -INFINITY;
-    for (int s = 0; s < nsplit; ++s) M = fmaxf(M, part_ml[((size_t)s * Hq + h) * 2]);
-    float acc = 0.f, L = 0.f;
-    for (int s = 0; s < nsplit; ++s) {
-        const float ms = part_ml[((size_t)s * Hq + h) * 2];
-        if (ms == -INFINITY) continue;
-        const float f = exp2f((ms - M) * scale_log2);
-        acc += f * part_o[((size_t)s * Hq + h) * 128 + d];
-        L += f * part_ml[((size_t)s * Hq + h) * 2 + 1];
+    // ---- the last CTA of this KV group to arrive merges all splits (replaces a separate combine launch) ----
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int prev = atomicAdd(&p.counters[g], 1);
+        s_last = (prev == p.nsplit - 1) ? 1 : 0;
     }
-    out[(size_t)h * 128 + d] = f2bf(L > 0.f ? acc / L : 0.f);
+    __syncthreads();
+    if (!s_last) return;
+    if (threadIdx.x == 0) p.counters[g] = 0;  // ready for the next launch
+    __threadfence();
+    float* sm_m = reinterpret_cast<float*>(smem_attn);  // [8][64]
+    float* sm_l = sm_m + 8 * 64;                         // [8][64]
+    for (int i = threadIdx.x; i < G * p.nsplit; i += 128) {
+        const int r = i / p.nsplit, sp = i % p.nsplit;
+        const float* ml = p.part_ml + ((size_t)sp * p.Hq + (size_t)g * G + r) * 2;
+        sm_m[r * 64 + sp] = __ldcg(ml);
+        sm_l[r * 64 + sp] = __ldcg(ml + 1);
+    }
+    __syncthreads();
+    // warp w merges rows w, w+4; a lane owns 4 consecutive dims (float4 loads, all splits independent)
+    for (int r = warp; r < G; r += 4) {
+        float M = -INFINITY;
+        for (int sp = 0; sp < p.nsplit; ++sp) M = fmaxf(M, sm_m[r * 64 + sp]);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        float L = 0.f;
+        const float* base = p.part_o + ((size_t)g * G + r) * D + lane * 4;
+        const size_t sp_stride = (size_t)p.Hq * D;
+#pragma unroll 8
+        for (int sp = 0; sp < p.nsplit; ++sp) {
+            const float ms = sm_m[r * 64 + sp];
+            const bool live = ms != -INFINITY;
+            const float f = live ? exp2f((ms - M) * p.scale_log2) : 0.f;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (live) v = __ldcg(reinterpret_cast<const float4*>(base + sp * sp_stride));
+            acc.x += f * v.x; acc.y += f * v.y; acc.z += f * v.z; acc.w += f * v.w;
+            L += f * sm_l[r * 64 + sp];
+        }
+        const float inv = L > 0.f ? 1.f / L : 0.f;
+        uint2 o;
+        o.x = pack_bf16x2(acc.x * inv, acc.y * inv);
+        o.y = pack_bf16x2(acc.z * inv, acc.w * inv);
+        *reinterpret_cast<uint2*>(p.out + (size_t)(g * G + r) * D + lane * 4) = o;
+    }
 }
 
 int attn_decode(bf16* qkv, bf16* kc, bf16* vc, const int* page_table, int page_size, const int* kv_len,
                 const int* rope_pos, const int* finished, const float* inv_freq, int Hq, int Hkv, int nsplit,
-                float* part_o, float* part_ml, bf16* out, cudaStream_t s) {
+                float* part_o, float* part_ml, int* counters, bf16* out, bool pdl, cudaStream_t s) {
     if (page_size != 64 || Hq % Hkv || Hq / Hkv > 8) return -1;
     constexpr int smem = (16 + 4 * 64) * 136 * 2;
     static bool set = false;
@@ -550,10 +583,9 @@ int attn_decode(bf16* qkv, bf16* kc, bf16* vc, const int* page_table, int page_s
     DecodeAttnParams p{};
     p.qkv = qkv; p.kc = kc; p.vc = vc; p.page_table = page_table; p.kv_len = kv_len; p.rope_pos = rope_pos;
     p.finished = finished; p.inv_freq = inv_freq; p.Hq = Hq; p.Hkv = Hkv; p.nsplit = nsplit;
-    p.part_o = part_o; p.part_ml = part_ml;
+    p.part_o = part_o; p.part_ml = part_ml; p.counters = counters; p.out = out;
     p.scale_log2 = 1.4426950408889634f / sqrtf(128.f);
-    attn_decode_kernel<<<dim3(Hkv, nsplit), 128, smem, s>>>(p);
-    attn_combine_kernel<<<Hq, 128, 0, s>>>(part_o, part_ml, nsplit, Hq, p.scale_log2, out, finished);
+    if (launch_kernel(attn_decode_kernel, dim3(Hkv, nsplit), dim3(128), (size_t)smem, s, pdl, p) != cudaSuccess) return -3;
     return 0;
 }
 

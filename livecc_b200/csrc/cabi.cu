@@ -115,11 +115,12 @@ int lcc_attn_prefill(lcc_ctx* ctx, const void* q, int q_ld, const void* k_cache,
 
 int lcc_attn_decode(lcc_ctx* ctx, void* qkv, void* k_cache, void* v_cache, const int32_t* page_table,
                     const int32_t* scalars, const float* inv_freq, int Hq, int Hkv, int nsplit, float* part_o,
-                    float* part_ml, void* out, lcc_stream_t stream) {
+                    float* part_ml, int32_t* counters, void* out, lcc_stream_t stream) {
     if (nsplit < 1 || nsplit > 64) LCC_FAIL(ctx, -2, "lcc_attn_decode: nsplit out of range");
     OP_RET(ctx, lcc::attn_decode((bf16*)qkv, (bf16*)k_cache, (bf16*)v_cache, page_table, LCC_PAGE_SIZE,
                                  scalars + LCC_SC_KV_LEN, scalars + LCC_SC_ROPE_POS, scalars + LCC_SC_FINISHED,
-                                 inv_freq, Hq, Hkv, nsplit, part_o, part_ml, (bf16*)out, (cudaStream_t)stream),
+                                 inv_freq, Hq, Hkv, nsplit, part_o, part_ml, counters, (bf16*)out, false,
+                                 (cudaStream_t)stream),
            "lcc_attn_decode");
 }
 
@@ -128,26 +129,26 @@ static inline const int* fin_ptr(const int32_t* scalars) { return scalars ? scal
 int lcc_gemv_norm_bias(lcc_ctx* ctx, const void* W, int ldw, const void* x, const void* norm_w, float eps,
                        const void* bias, void* out, int N, int K, const int32_t* scalars, lcc_stream_t stream) {
     OP_RET(ctx, lcc::gemv_norm_bias((const bf16*)W, ldw, (const bf16*)x, (const bf16*)norm_w, eps, (const bf16*)bias,
-                                    (bf16*)out, N, K, fin_ptr(scalars), (cudaStream_t)stream), "lcc_gemv_norm_bias");
+                                    (bf16*)out, N, K, fin_ptr(scalars), ctx->num_sms, false, (cudaStream_t)stream), "lcc_gemv_norm_bias");
 }
 
 int lcc_gemv_residual(lcc_ctx* ctx, const void* W, int ldw, const void* x, void* h_inout, int N, int K,
                       const int32_t* scalars, lcc_stream_t stream) {
-    OP_RET(ctx, lcc::gemv_residual((const bf16*)W, ldw, (const bf16*)x, (bf16*)h_inout, N, K, fin_ptr(scalars),
+    OP_RET(ctx, lcc::gemv_residual((const bf16*)W, ldw, (const bf16*)x, (bf16*)h_inout, N, K, fin_ptr(scalars), ctx->num_sms, false,
                                    (cudaStream_t)stream), "lcc_gemv_residual");
 }
 
 int lcc_gemv_norm_swiglu(lcc_ctx* ctx, const void* W_gate_up, int ldw, const void* x, const void* norm_w,
                          float eps, void* act, int N2, int K, const int32_t* scalars, lcc_stream_t stream) {
     OP_RET(ctx, lcc::gemv_norm_swiglu((const bf16*)W_gate_up, ldw, (const bf16*)x, (const bf16*)norm_w, eps, (bf16*)act,
-                                      N2, K, fin_ptr(scalars), (cudaStream_t)stream), "lcc_gemv_norm_swiglu");
+                                      N2, K, fin_ptr(scalars), ctx->num_sms, false, (cudaStream_t)stream), "lcc_gemv_norm_swiglu");
 }
 
 int lcc_gemv_norm_logits(lcc_ctx* ctx, const void* W, int ldw, const void* x, const void* norm_w, float eps,
                          float* logits, float* logits_copy, int N, int K, const int32_t* scalars,
                          lcc_stream_t stream) {
     OP_RET(ctx, lcc::gemv_norm_logits((const bf16*)W, ldw, (const bf16*)x, (const bf16*)norm_w, eps, logits,
-                                      logits_copy, N, K, fin_ptr(scalars), (cudaStream_t)stream),
+                                      logits_copy, N, K, fin_ptr(scalars), ctx->num_sms, false, (cudaStream_t)stream),
            "lcc_gemv_norm_logits");
 }
 

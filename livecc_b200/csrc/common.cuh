@@ -200,6 +200,16 @@ __device__ __forceinline__ void tmem_ld_wait() {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization
+// attribute may start while its predecessor is still running. pdl_launch_dependents() lets the NEXT
+// kernel start early; pdl_wait() blocks until the PREVIOUS kernel has completed and its writes are
+// visible. Everything before pdl_wait() may only touch data no kernel of the step writes (weights).
+// Both are no-ops for ordinary launches.
+__device__ __forceinline__ void pdl_launch_dependents() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred = 0;
     asm volatile(

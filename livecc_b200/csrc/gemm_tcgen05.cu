@@ -5,11 +5,12 @@
 // fc1 / fc2 / merger (mq2vl.py:304-337,385-458) and the decoder prefill projections
 // (mq2vl.py:491-504,539-594, lm_head :1437).
 //
-// Structure (one CTA per SM, 256 threads):
+// Structure (one CTA per SM, 384 threads):
 //   warp 0      : TMA producer  (cp.async.bulk.tensor, SWIZZLE_128B tiles, mbarrier complete_tx)
 //   warp 1      : MMA issuer    (one elected lane issues tcgen05.mma, fp32 accumulators in TMEM)
 //   warp 2      : TMEM allocator
-//   warps 4..7  : epilogue      (tcgen05.ld 32x32b -> registers -> fused epilogue -> bf16 stores)
+//   warps 4..11 : epilogue      (tcgen05.ld 32x32b -> registers -> fused epilogue -> bf16 stores);
+//                 warp w reads TMEM lane quarter w%4 and the column half (w-4)/4 of the tile
 // Pipelines: smem ring (full/empty mbarriers, STAGES deep) between TMA and MMA; a 2-deep TMEM
 // accumulator ring (tmem_full/tmem_empty) between MMA and epilogue so the epilogue of tile i
 // overlaps the main loop of tile i+1.
@@ -38,16 +39,16 @@ __device__ __forceinline__ float quick_gelu_bf16(float x) {
     // ACT2FN["quick_gelu"]: input * sigmoid(1.702 * input), every op rounded to bf16
     // (SP/transformers/activations.py:117-123).
     float t1 = rbf(1.702f * x);
-    float t2 = rbf(1.0f / (1.0f + expf(-t1)));
+    float t2 = rbf(__fdividef(1.0f, 1.0f + __expf(-t1)));
     return rbf(x * t2);
 }
 __device__ __forceinline__ float gelu_erf_bf16(float x) {
     return rbf(0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)));
 }
-__device__ __forceinline__ float silu_bf16(float x) { return rbf(x / (1.0f + expf(-x))); }
+__device__ __forceinline__ float silu_bf16(float x) { return rbf(__fdividef(x, 1.0f + __expf(-x))); }
 
 template <int BLOCK_N, int EPI>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     const __grid_constant__ CUtensorMap tmap_b, bf16* C, int M, int N,
                     int K, int ldc, const bf16* __restrict__ bias,
@@ -83,7 +84,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full[i], 1);
-            mbar_init(&tmem_empty[i], 4);  // one arrive per epilogue warp
+            mbar_init(&tmem_empty[i], 8);  // one arrive per epilogue warp
         }
         fence_barrier_init();
     }
@@ -149,7 +150,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
         }
     } else if (warp >= 4) {
         // ===================== Epilogue =====================
-        const int q = warp - 4;  // TMEM lane quarter this warp may access
+        const int q = warp & 3;          // TMEM lane quarter this warp may access (warp id mod 4)
+        const int half = (warp - 4) >> 2;  // which half of the tile's columns this warp converts
+        constexpr int CHUNKS_PER_HALF = BLOCK_N / 64;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -159,7 +162,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
             const int row = m_blk * BLOCK_M + q * 32 + lane;
             const bool row_ok = row < M;
 #pragma unroll 1
-            for (int c = 0; c < BLOCK_N / 32; ++c) {
+            for (int c = half * CHUNKS_PER_HALF; c < (half + 1) * CHUNKS_PER_HALF; ++c) {
                 uint32_t v[32];
                 const uint32_t taddr =
                     tmem_base + (uint32_t)(acc * BLOCK_N + c * 32) + ((uint32_t)(q * 32) << 16);
@@ -299,7 +302,7 @@ static int launch_cfg(const GemmArgs& a, int num_sms, cudaStream_t stream) {
     const int m_tiles = (a.M + BLOCK_M - 1) / BLOCK_M, n_tiles = (a.N + BLOCK_N - 1) / BLOCK_N;
     const int tiles = m_tiles * n_tiles;
     const int grid = tiles < num_sms ? tiles : num_sms;
-    kern<<<grid, 256, Cfg::SMEM_BYTES, stream>>>(ta, tb, (bf16*)a.C, a.M, a.N, a.K, a.ldc,
+    kern<<<grid, 384, Cfg::SMEM_BYTES, stream>>>(ta, tb, (bf16*)a.C, a.M, a.N, a.K, a.ldc,
                                                  (const bf16*)a.bias, (const bf16*)a.residual,
                                                  a.ldr);
     return cudaGetLastError() == cudaSuccess ? 0 : -13;
@@ -326,13 +329,15 @@ int gemm_bf16_tn(const GemmArgs& a, int num_sms, cudaStream_t stream) {
     if ((a.epi == EPI_RESIDUAL || a.epi == EPI_BIAS_RESIDUAL) && (!a.residual || (a.ldr % 8))) return -4;
     if ((a.epi == EPI_BIAS || a.epi == EPI_BIAS_QUICKGELU || a.epi == EPI_BIAS_GELU ||
          a.epi == EPI_BIAS_RESIDUAL) && !a.bias) return -5;
-    // Tile-shape heuristic: widest N tile that still yields >= one wave of CTAs.
+    // Tile-shape heuristic. Narrow tiles re-read the A tile from L2 once per N tile and are L2->SM
+    // bandwidth bound (128x64 tiles need ~190 B/clk/SM; the L2 delivers ~40), so prefer the widest
+    // tile that still occupies at least half of the SMs.
     int block_n = a.block_n;
     if (block_n == 0) {
         const int m_tiles = (a.M + BLOCK_M - 1) / BLOCK_M;
-        if (m_tiles * ((a.N + 255) / 256) >= num_sms) block_n = 256;
-        else if (m_tiles * ((a.N + 127) / 128) >= num_sms || a.N < 64 * 2) block_n = 128;
-        else block_n = 64;
+        if (m_tiles * ((a.N + 255) / 256) * 2 >= num_sms) block_n = 256;
+        else if (m_tiles * ((a.N + 127) / 128) * 2 >= num_sms) block_n = 128;
+        else block_n = (a.N >= 1024) ? 128 : 64;
         if (a.N <= 64) block_n = 64;
     }
     switch (block_n) {

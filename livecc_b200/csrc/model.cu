@@ -3,6 +3,8 @@
 //   lcc_prefill       — Qwen2VLModel.forward over S new tokens + first token selection (mq2vl.py:1230-1300)
 //   lcc_decode_steps  — the loop body of GenerationMixin._sample         (gen/utils.py:2743-2805)
 // The host (Python) owns every buffer; this file only sequences kernel launches.
+#include <stdlib.h>
+
 #include <vector>
 
 #include "../../include/livecc_b200.h"
@@ -22,6 +24,7 @@ struct lcc_model {
     uint8_t* ws = nullptr;
     size_t ws_bytes = 0;
     int cap_patches = 0, cap_tokens = 0;
+    bool use_pdl = false;  // programmatic dependent launch between the decode-step kernels (LIVECC_B200_PDL=1 enables)
 };
 
 namespace {
@@ -35,7 +38,7 @@ int get_layout(const lcc_model* m, int need_patches, int need_tokens, WsLayout* 
 struct WsLayout {
     size_t vx, vh, vn, vqkv, vattn, vmlp, vcos, vsin, vcu;  // ViT
     size_t hid, normed, qkv, attn, act, rank;                // prefill
-    size_t h1, qkv1, attn1, act1, logits_raw, logits_proc, part_o, part_ml;  // decode
+    size_t h1, qkv1, attn1, act1, logits_raw, logits_proc, part_o, part_ml, attn_cnt;  // decode
     size_t total;
 };
 
@@ -70,6 +73,7 @@ WsLayout make_layout(const lcc_model_config& c, int NP, int NT) {
     L.logits_proc = take((size_t)c.vocab * 4);
     L.part_o = take((size_t)kMaxSplit * c.q_heads * 128 * 4);
     L.part_ml = take((size_t)kMaxSplit * c.q_heads * 2 * 4);
+    L.attn_cnt = take(64 * 4);
     L.total = off;
     return L;
 }
@@ -133,6 +137,8 @@ lcc_model* lcc_model_create(lcc_ctx* ctx, const lcc_model_config* cfg, const lcc
     m->layers.assign(w->layers, w->layers + cfg->layers);
     m->w.vit_blocks = m->vit_blocks.data();
     m->w.layers = m->layers.data();
+    const char* pdl_env = getenv("LIVECC_B200_PDL");
+    m->use_pdl = pdl_env && pdl_env[0] == '1';
     return m;
 }
 
@@ -226,7 +232,7 @@ int lcc_prefill(lcc_model* m, const lcc_stream_state* st, const int64_t* ids, co
     // final norm + lm_head on the last position only (logits_to_keep = 1, gen/utils.py:2487-2491)
     STEP(lcc::gemv_norm_logits((const bf16*)m->w.lm_head, H, hid + (size_t)(S - 1) * H, (const bf16*)m->w.final_norm_w,
                                c.rms_eps, (float*)(ws + L.logits_raw), (float*)(ws + L.logits_proc), c.vocab, H,
-                               nullptr, s), "lm_head");
+                               nullptr, m->ctx->num_sms, false, s), "lm_head");
     STEP(lcc::sample_greedy(make_sample(m, st, sp, ws, L, 0), s), "token selection");
     LCC_CHECK_LAUNCH(m->ctx, "lcc_prefill");
     return 0;
@@ -244,6 +250,8 @@ int lcc_decode_steps(lcc_model* m, const lcc_stream_state* st, int n_steps, int 
     bf16* h = (bf16*)(ws + L.h1); bf16* qkv = (bf16*)(ws + L.qkv1); bf16* attn = (bf16*)(ws + L.attn1);
     bf16* act = (bf16*)(ws + L.act1);
     float* part_o = (float*)(ws + L.part_o); float* part_ml = (float*)(ws + L.part_ml);
+    int* attn_cnt = (int*)(ws + L.attn_cnt);
+    const bool pdl = m->use_pdl;
     const int H = c.hidden, Hq = c.q_heads, Hkv = c.kv_heads, qkv_dim = (Hq + 2 * Hkv) * 128;
     const int* fin = st->scalars + LCC_SC_FINISHED;
     for (int step = 0; step < n_steps; ++step) {
@@ -252,17 +260,17 @@ int lcc_decode_steps(lcc_model* m, const lcc_stream_state* st, int n_steps, int 
             bf16* kc = (bf16*)st->k_pool + (size_t)i * st->layer_stride;
             bf16* vc = (bf16*)st->v_pool + (size_t)i * st->layer_stride;
             STEP(lcc::gemv_norm_bias((const bf16*)lw.qkv_w, H, h, (const bf16*)lw.ln1_w, c.rms_eps, (const bf16*)lw.qkv_b,
-                                     qkv, qkv_dim, H, fin, s), "decode qkv");
+                                     qkv, qkv_dim, H, fin, m->ctx->num_sms, pdl, s), "decode qkv");
             STEP(lcc::attn_decode(qkv, kc, vc, st->page_table, LCC_PAGE_SIZE, st->scalars + LCC_SC_KV_LEN,
                                   st->scalars + LCC_SC_ROPE_POS, fin, m->w.text_inv_freq, Hq, Hkv, nsplit, part_o,
-                                  part_ml, attn, s), "decode attention");
-            STEP(lcc::gemv_residual((const bf16*)lw.o_w, Hq * 128, attn, h, H, Hq * 128, fin, s), "decode o_proj");
+                                  part_ml, attn_cnt, attn, pdl, s), "decode attention");
+            STEP(lcc::gemv_residual((const bf16*)lw.o_w, Hq * 128, attn, h, H, Hq * 128, fin, m->ctx->num_sms, pdl, s), "decode o_proj");
             STEP(lcc::gemv_norm_swiglu((const bf16*)lw.gate_up_w, H, h, (const bf16*)lw.ln2_w, c.rms_eps, act,
-                                       2 * c.inter, H, fin, s), "decode gate_up");
-            STEP(lcc::gemv_residual((const bf16*)lw.down_w, c.inter, act, h, H, c.inter, fin, s), "decode down_proj");
+                                       2 * c.inter, H, fin, m->ctx->num_sms, pdl, s), "decode gate_up");
+            STEP(lcc::gemv_residual((const bf16*)lw.down_w, c.inter, act, h, H, c.inter, fin, m->ctx->num_sms, pdl, s), "decode down_proj");
         }
         STEP(lcc::gemv_norm_logits((const bf16*)m->w.lm_head, H, h, (const bf16*)m->w.final_norm_w, c.rms_eps,
-                                   (float*)(ws + L.logits_raw), (float*)(ws + L.logits_proc), c.vocab, H, fin, s),
+                                   (float*)(ws + L.logits_raw), (float*)(ws + L.logits_proc), c.vocab, H, fin, m->ctx->num_sms, pdl, s),
              "decode lm_head");
         STEP(lcc::sample_greedy(make_sample(m, st, sp, ws, L, 1), s), "decode token selection");
     }
@@ -287,6 +295,9 @@ extern "C" int lcc_model_bind_workspace(lcc_model* m, void* ws, size_t ws_bytes,
         LCC_FAIL(m->ctx, -2, "lcc_model_bind_workspace: %zu bytes is too small", ws_bytes);
     m->ws = reinterpret_cast<uint8_t*>(ws);
     m->ws_bytes = ws_bytes;
+    // split-KV arrival counters start at zero (the attention kernel re-zeroes them itself)
+    if (cudaMemset(m->ws + make_layout(m->cfg, max_patches, max_tokens).attn_cnt, 0, 64 * 4) != cudaSuccess)
+        LCC_FAIL(m->ctx, -3, "lcc_model_bind_workspace: cudaMemset failed");
     m->cap_patches = max_patches;
     m->cap_tokens = max_tokens;
     return 0;

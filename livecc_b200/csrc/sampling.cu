@@ -25,6 +25,7 @@ __global__ void __launch_bounds__(1024) sample_greedy_kernel(const SampleArgs a)
     if (a.repetition_penalty != 1.0f) {
         // torch's CUDA tensor/scalar division multiplies by the fp32 reciprocal; mirror it bit for bit
         const float inv_pen = 1.0f / a.repetition_penalty;
+#pragma unroll 4
         for (int i = tid; i < hist; i += blockDim.x) {
             const int64_t id = a.seq[i];
             if (id >= 0 && id < a.V) {
@@ -69,12 +70,23 @@ __global__ void __launch_bounds__(1024) sample_greedy_kernel(const SampleArgs a)
         __syncthreads();
     }
 
-    // 3. argmax, lowest index on ties
+    // 3. argmax, lowest index on ties. float4 loads, 8 independent loads in flight per thread.
     float bv = -INFINITY;
     int bi = 0x7fffffff;
-    for (int i = tid; i < a.V; i += blockDim.x) {
+    const int V4 = a.V >> 2;
+    const float4* lp4 = reinterpret_cast<const float4*>(a.logits_proc);
+#pragma unroll 8
+    for (int i = tid; i < V4; i += blockDim.x) {
+        const float4 v = lp4[i];
+        const int b = i << 2;
+        if (v.x > bv) { bv = v.x; bi = b; }  // indices increase per thread => first max kept
+        if (v.y > bv) { bv = v.y; bi = b + 1; }
+        if (v.z > bv) { bv = v.z; bi = b + 2; }
+        if (v.w > bv) { bv = v.w; bi = b + 3; }
+    }
+    for (int i = (V4 << 2) + tid; i < a.V; i += blockDim.x) {
         const float v = a.logits_proc[i];
-        if (v > bv) { bv = v; bi = i; }  // i increases per thread => first max kept
+        if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
