@@ -375,6 +375,13 @@ def main():
     p50 = lat_sorted[len(lat_sorted) // 2] * 1e3
     peak, peak_src = load_peaks()
     kbytes, ksec = time_dominant_kernel(eng)
+    traffic = None
+    try:  # dram bytes of the same kernel from the committed `ncu --set full` capture (7B dims only)
+        if args.model == "7b":
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_gateup_ncu.json")))
+            traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+    except Exception:
+        traffic = None
     t = cfg.text_config
     step_weight_bytes = (t.num_hidden_layers * ((t.num_attention_heads + 2 * t.num_key_value_heads) * 128 * t.hidden_size
                                                 + t.hidden_size * t.hidden_size + 3 * t.intermediate_size * t.hidden_size
@@ -393,7 +400,7 @@ def main():
         "kv_len_end": kv_end, "clocks": clocks, "gpu_launches": int(gpu_launches),
         "roofline": {"kernel": "gemv_rows_kernel<2,NORM,SWIGLU> (decode gate/up + RMSNorm + SwiGLU)", "bound": "hbm",
                      "achieved": kbytes / ksec / 1e9, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                     "frac": kbytes / ksec / 1e9 / peak, "traffic": None, "bytes_per_launch": kbytes,
+                     "frac": kbytes / ksec / 1e9 / peak, "traffic": traffic, "bytes_per_launch": kbytes,
                      "us_per_launch": ksec * 1e6},
     }
     if e2e:

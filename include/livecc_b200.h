@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define LCC_ABI_VERSION 3
+#define LCC_ABI_VERSION 4
 #define LCC_PAGE_SIZE 64
 
 typedef struct lcc_ctx lcc_ctx;
@@ -150,6 +150,8 @@ typedef struct {
     float thr_base, thr_step;
     int32_t eos_token_id;
     int32_t max_new_tokens;
+    float inv_repetition_penalty; /* fp32(1.0 / (double)penalty): torch's CUDA `tensor / python_float` multiplies by
+                                     this value (measured: tools/penalty_probe.py); 0 = derive as 1.0f / repetition_penalty */
 } lcc_sampling;
 
 int lcc_sample_greedy(lcc_ctx* ctx, const float* logits_raw, float* logits_proc, int V, int64_t* seq,

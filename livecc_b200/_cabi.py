@@ -13,7 +13,7 @@ PKG_DIR = Path(__file__).resolve().parent
 LIB_PATH = PKG_DIR / "liblivecc_sm100a.so"
 HEADER_PATH = PKG_DIR.parent / "include" / "livecc_b200.h"
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 PAGE_SIZE = 64
 
 # epilogue codes (LCC_EPI_*)
@@ -29,7 +29,8 @@ class LiveCCNativeError(RuntimeError):
 
 class Sampling(C.Structure):
     _fields_ = [("repetition_penalty", C.c_float), ("thr_token", C.c_int32), ("thr_base", C.c_float),
-                ("thr_step", C.c_float), ("eos_token_id", C.c_int32), ("max_new_tokens", C.c_int32)]
+                ("thr_step", C.c_float), ("eos_token_id", C.c_int32), ("max_new_tokens", C.c_int32),
+                ("inv_repetition_penalty", C.c_float)]
 
 
 class ModelConfig(C.Structure):

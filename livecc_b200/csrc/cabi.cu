@@ -158,7 +158,7 @@ int lcc_sample_greedy(lcc_ctx* ctx, const float* logits_raw, float* logits_proc,
     if (!sp) return -1;
     lcc::SampleArgs a{};
     a.logits_raw = logits_raw; a.logits_proc = logits_proc; a.V = V; a.seq = seq; a.scalars = scalars;
-    a.repetition_penalty = sp->repetition_penalty; a.thr_token = sp->thr_token; a.thr_base = sp->thr_base;
+    a.repetition_penalty = sp->repetition_penalty; a.inv_repetition_penalty = sp->inv_repetition_penalty; a.thr_token = sp->thr_token; a.thr_base = sp->thr_base;
     a.thr_step = sp->thr_step; a.eos_token_id = sp->eos_token_id; a.max_new_tokens = sp->max_new_tokens;
     a.advance_kv = advance_kv; a.embed = (const bf16*)embed; a.h = (bf16*)h; a.H = H;
     OP_RET(ctx, lcc::sample_greedy(a, (cudaStream_t)stream), "lcc_sample_greedy");

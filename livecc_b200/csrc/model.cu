@@ -106,6 +106,7 @@ lcc::SampleArgs make_sample(const lcc_model* m, const lcc_stream_state* st, cons
     a.seq = st->seq;
     a.scalars = st->scalars;
     a.repetition_penalty = sp->repetition_penalty;
+    a.inv_repetition_penalty = sp->inv_repetition_penalty;
     a.thr_token = sp->thr_token;
     a.thr_base = sp->thr_base;
     a.thr_step = sp->thr_step;

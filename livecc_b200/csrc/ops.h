@@ -51,6 +51,7 @@ struct SampleArgs {
     int64_t* seq;             // device [cap]: input ids followed by generated ids
     int* scalars;             // device int32: see LCC_SC_* in include/livecc_b200.h
     float repetition_penalty;
+    float inv_repetition_penalty;  // see lcc_sampling
     int thr_token;            // < 0: disabled (ThresholdLogitsProcessor, REF/demo/infer.py:10-23)
     float thr_base, thr_step;
     int eos_token_id;

@@ -23,8 +23,8 @@ __global__ void __launch_bounds__(1024) sample_greedy_kernel(const SampleArgs a)
 
     // 1. repetition penalty: gather from raw, scatter to proc (idempotent under duplicate ids)
     if (a.repetition_penalty != 1.0f) {
-        // torch's CUDA tensor/scalar division multiplies by the fp32 reciprocal; mirror it bit for bit
-        const float inv_pen = 1.0f / a.repetition_penalty;
+        // torch's CUDA `scores / penalty` multiplies by fp32(1.0 / (double)penalty); the host passes that value
+        const float inv_pen = a.inv_repetition_penalty != 0.f ? a.inv_repetition_penalty : 1.0f / a.repetition_penalty;
 #pragma unroll 4
         for (int i = tid; i < hist; i += blockDim.x) {
             const int64_t id = a.seq[i];

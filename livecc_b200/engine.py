@@ -187,7 +187,7 @@ class LiveCCB200ForConditionalGeneration:
                 raise NotImplementedError(f"logits processor {type(proc).__name__} is not supported by the native "
                                           "sampling kernel (supported: ThresholdLogitsProcessor)")
         return _cabi.Sampling(float(repetition_penalty), thr_token, thr_base, thr_step, int(self.config.eos_token_id),
-                              int(max_new_tokens))
+                              int(max_new_tokens), 1.0 / float(repetition_penalty))
 
     # ------------------------------------------------------------------------------------------
     # the hot path

@@ -285,7 +285,7 @@ def test_sample_greedy(ctx):
     seq[:5000] = hist
     sc = torch.zeros(A.SC_COUNT, dtype=torch.int32, device=DEV)
     sc[A.SC_KV_LEN], sc[A.SC_ROPE_POS], sc[A.SC_SEQ_LEN] = 5000, 4000, 5000
-    sp = A.Sampling(1.05, -1, 0.0, 0.0, 7, 16)
+    sp = A.Sampling(1.05, -1, 0.0, 0.0, 7, 16, 1.0 / 1.05)
     proc = raw.clone()
     h = torch.empty(H, dtype=torch.bfloat16, device=DEV)
     ctx.sample_greedy(raw, proc, seq, sc, sp, 1, embed, h)
@@ -299,14 +299,14 @@ def test_sample_greedy(ctx):
         bad = (proc != ref).nonzero().flatten()
         print("penalty mismatches vs torch:", bad.numel(), "vs true division:", int((proc != ref_div).sum()),
               [(int(i), float(raw[i]), float(proc[i]), float(ref[i])) for i in bad[:4]])
-    assert torch.allclose(proc, ref, rtol=3e-7, atol=0)
+    assert torch.equal(proc, ref)  # bit-exact with torch's CUDA semantics (tools/penalty_probe.py)
     assert int(seq[5000]) == tok and torch.equal(h, embed[tok])
     assert sc.tolist()[:6] == [5001, 4001, 0, 1, 5001, tok]
     # threshold processor: force -inf on the would-be argmax token
     sc2 = torch.zeros(A.SC_COUNT, dtype=torch.int32, device=DEV)
     sc2[A.SC_SEQ_LEN] = 5000
     proc2 = raw.clone()
-    sp2 = A.Sampling(1.0, tok, 1.1, 0.0, 7, 1)
+    sp2 = A.Sampling(1.0, tok, 1.1, 0.0, 7, 1, 1.0)
     ctx.sample_greedy(raw, proc2, seq, sc2, sp2, 0, embed, h)
     ref2 = raw.clone()
     ref2[tok] = -float("inf")
