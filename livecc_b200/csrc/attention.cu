@@ -165,6 +165,10 @@ struct FlashParams {
     int past;           // paged+causal: number of cached tokens before the S new ones
     int G;              // query heads per KV head
     float scale_log2;   // softmax scale * log2(e)
+    // split-KV (paged mode only): blockIdx.z = split; partials are merged by flash_merge_kernel
+    int nsplit;
+    float* part_o;      // [nsplit, Hkv, S*G, D] unnormalised fp32
+    float* part_ml;     // [nsplit, Hkv, S*G, 2]
 };
 
 template <int D, bool CAUSAL, bool PAGED>
@@ -204,6 +208,21 @@ __global__ void __launch_bounds__(128) flash_fwd_kernel(const FlashParams p) {
         kv_len = min(kv_len, p.past + last_row / p.G + 1);
     }
     const int n_tiles = (kv_len + BN - 1) / BN;
+    int tile_lo = 0, tile_hi = n_tiles;
+    const bool split = PAGED && p.nsplit > 1;
+    if (split) {
+        const int tiles_total = (p.past + p.S + BN - 1) / BN;
+        const int tps = (tiles_total + p.nsplit - 1) / p.nsplit;
+        tile_lo = blockIdx.z * tps;
+        tile_hi = min(n_tiles, tile_lo + tps);
+        if (tile_lo >= tile_hi) {  // nothing to do for this split: neutral partial (m = -inf, l = 0)
+            cp_async_commit();
+            cp_async_wait<0>();
+            float* ml = p.part_ml + (((size_t)blockIdx.z * p.Hkv + g) * rows_total + row0) * 2;
+            for (int i = threadIdx.x; i < min(BM, rows_total - row0); i += 128) { ml[i * 2] = -INFINITY; ml[i * 2 + 1] = 0.f; }
+            return;
+        }
+    }
 
     auto load_kv = [&](int tile, int buf) {
         bf16* dk = sk + buf * BN * LDS;
@@ -229,7 +248,7 @@ __global__ void __launch_bounds__(128) flash_fwd_kernel(const FlashParams p) {
         }
     };
 
-    if (n_tiles > 0) load_kv(0, 0);
+    if (tile_lo < tile_hi) load_kv(tile_lo, 0);
     cp_async_commit();
 
     cp_async_wait<1>();  // Q landed
@@ -257,13 +276,14 @@ __global__ void __launch_bounds__(128) flash_fwd_kernel(const FlashParams p) {
         lim[r] = CAUSAL ? (p.past + rr / p.G) : (kv_len - 1);
     }
 
-    for (int t = 0; t < n_tiles; ++t) {
-        if (t + 1 < n_tiles) load_kv(t + 1, (t + 1) & 1);
+    for (int t = tile_lo; t < tile_hi; ++t) {
+        const int buf = (t - tile_lo) & 1;
+        if (t + 1 < tile_hi) load_kv(t + 1, buf ^ 1);
         cp_async_commit();
         cp_async_wait<1>();
         __syncthreads();
-        const bf16* ks = sk + (t & 1) * BN * LDS;
-        const bf16* vs = sv + (t & 1) * BN * LDS;
+        const bf16* ks = sk + buf * BN * LDS;
+        const bf16* vs = sv + buf * BN * LDS;
         float s[8][4];
         warp_qk<D, LDS, 4>(qf, ks, lane, s);
         // mask: key index beyond the causal limit or beyond kv_len
@@ -291,6 +311,20 @@ __global__ void __launch_bounds__(128) flash_fwd_kernel(const FlashParams p) {
         l[r] += __shfl_xor_sync(0xffffffffu, l[r], 1);
         l[r] += __shfl_xor_sync(0xffffffffu, l[r], 2);
     }
+    if (split) {  // unnormalised partial + (m, l) for the merge kernel
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int rr = row0 + warp * 16 + (lane >> 2) + r * 8;
+            if (rr >= rows_total) continue;
+            const size_t prow = ((size_t)blockIdx.z * p.Hkv + g) * rows_total + rr;
+            float* dst = p.part_o + prow * D + 2 * (lane & 3);
+#pragma unroll
+            for (int d = 0; d < D / 8; ++d)
+                *reinterpret_cast<float2*>(dst + d * 8) = make_float2(o[d][2 * r], o[d][2 * r + 1]);
+            if ((lane & 3) == 0) { p.part_ml[prow * 2] = m[r]; p.part_ml[prow * 2 + 1] = l[r]; }
+        }
+        return;
+    }
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
         const int rr = row0 + warp * 16 + (lane >> 2) + r * 8;
@@ -303,6 +337,37 @@ __global__ void __launch_bounds__(128) flash_fwd_kernel(const FlashParams p) {
             *reinterpret_cast<uint32_t*>(dst + d * 8) = pack_bf16x2(o[d][2 * r] * inv, o[d][2 * r + 1] * inv);
         }
     }
+}
+
+// Merge of the split-KV partials of the prefill attention: one CTA per packed row, one thread per dim.
+__global__ void __launch_bounds__(128) flash_merge_kernel(const float* __restrict__ part_o,
+                                                          const float* __restrict__ part_ml, int nsplit, int Hkv,
+                                                          int rows_total, int G, float scale_log2,
+                                                          bf16* __restrict__ out, int o_ld) {
+    const int rr = blockIdx.x, g = blockIdx.y, d = threadIdx.x;
+    float ms[8], ls[8];
+    float M = -INFINITY;
+#pragma unroll
+    for (int sp = 0; sp < 8; ++sp) {
+        if (sp < nsplit) {
+            const size_t prow = ((size_t)sp * Hkv + g) * rows_total + rr;
+            ms[sp] = part_ml[prow * 2];
+            ls[sp] = part_ml[prow * 2 + 1];
+            M = fmaxf(M, ms[sp]);
+        }
+    }
+    float acc = 0.f, L = 0.f;
+#pragma unroll
+    for (int sp = 0; sp < 8; ++sp) {
+        if (sp < nsplit && ms[sp] != -INFINITY) {
+            const size_t prow = ((size_t)sp * Hkv + g) * rows_total + rr;
+            const float f = exp2f((ms[sp] - M) * scale_log2);
+            acc += f * part_o[prow * 128 + d];
+            L += f * ls[sp];
+        }
+    }
+    const int pos = rr / G, hq = g * G + rr % G;
+    out[(size_t)pos * o_ld + (size_t)hq * 128 + d] = f2bf(L > 0.f ? acc / L : 0.f);
 }
 
 template <int D, bool CAUSAL, bool PAGED>
@@ -337,15 +402,31 @@ int vit_attention(const bf16* qkv, int ld, bf16* out, int o_ld, const int* cu_se
 // Decoder prefill: q rows of the fused qkv buffer (already rotated), K/V in the paged cache
 // (already containing the S new tokens at positions past..past+S-1).
 int attn_prefill_paged(const bf16* q, int q_ld, const bf16* kc, const bf16* vc, const int* page_table,
-                       int page_size, int Hq, int Hkv, int S, int past, bf16* out, int o_ld, cudaStream_t s) {
+                       int page_size, int Hq, int Hkv, int S, int past, bf16* out, int o_ld, float* part_o,
+                       float* part_ml, size_t part_capacity_rows, int num_sms, cudaStream_t s) {
     if (page_size != 64) return -1;
     if (S <= 0) return 0;
     FlashParams p{};
     p.q = q; p.q_ld = q_ld; p.kc = kc; p.vc = vc; p.page_table = page_table; p.Hkv = Hkv;
     p.out = out; p.o_ld = o_ld; p.cu_seqlens = nullptr; p.S = S; p.past = past; p.G = Hq / Hkv;
     p.scale_log2 = 1.4426950408889634f / sqrtf(128.f);
-    dim3 grid((S * p.G + 63) / 64, Hkv, 1);
-    return launch_flash<128, true, true>(p, grid, s);
+    const int q_tiles = (S * p.G + 63) / 64;
+    const int ctas = q_tiles * Hkv;
+    const int kv_tiles = (past + S + 63) / 64;
+    // split the KV range when a chunk-sized prefill over a long cache cannot fill two CTAs per SM
+    int nsplit = 1;
+    if (part_o && part_ml && ctas < 2 * num_sms) {
+        nsplit = (2 * num_sms + ctas - 1) / ctas;
+        if (nsplit > 8) nsplit = 8;
+        while (nsplit > 1 && kv_tiles < 8 * nsplit) --nsplit;  // keep >= 8 tiles of work per split
+        if ((size_t)nsplit * Hkv * S * p.G > part_capacity_rows) nsplit = 1;
+    }
+    p.nsplit = nsplit; p.part_o = part_o; p.part_ml = part_ml;
+    dim3 grid(q_tiles, Hkv, nsplit);
+    if (int r = launch_flash<128, true, true>(p, grid, s)) return r;
+    if (nsplit > 1)
+        flash_merge_kernel<<<dim3(S * p.G, Hkv), 128, 0, s>>>(part_o, part_ml, nsplit, Hkv, S * p.G, p.G, p.scale_log2, out, o_ld);
+    return 0;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -109,7 +109,8 @@ int lcc_attn_prefill(lcc_ctx* ctx, const void* q, int q_ld, const void* k_cache,
                      const int32_t* page_table, int Hq, int Hkv, int S, int past, void* out, int o_ld,
                      lcc_stream_t stream) {
     OP_RET(ctx, lcc::attn_prefill_paged((const bf16*)q, q_ld, (const bf16*)k_cache, (const bf16*)v_cache, page_table,
-                                        LCC_PAGE_SIZE, Hq, Hkv, S, past, (bf16*)out, o_ld, (cudaStream_t)stream),
+                                        LCC_PAGE_SIZE, Hq, Hkv, S, past, (bf16*)out, o_ld, nullptr, nullptr, 0,
+                                        ctx->num_sms, (cudaStream_t)stream),
            "lcc_attn_prefill");
 }
 
@@ -129,19 +130,21 @@ static inline const int* fin_ptr(const int32_t* scalars) { return scalars ? scal
 int lcc_gemv_norm_bias(lcc_ctx* ctx, const void* W, int ldw, const void* x, const void* norm_w, float eps,
                        const void* bias, void* out, int N, int K, const int32_t* scalars, lcc_stream_t stream) {
     OP_RET(ctx, lcc::gemv_norm_bias((const bf16*)W, ldw, (const bf16*)x, (const bf16*)norm_w, eps, (const bf16*)bias,
-                                    (bf16*)out, N, K, fin_ptr(scalars), ctx->num_sms, false, (cudaStream_t)stream), "lcc_gemv_norm_bias");
+                                    (bf16*)out, N, K, fin_ptr(scalars), nullptr, 0, ctx->num_sms, false, (cudaStream_t)stream),
+           "lcc_gemv_norm_bias");
 }
 
 int lcc_gemv_residual(lcc_ctx* ctx, const void* W, int ldw, const void* x, void* h_inout, int N, int K,
                       const int32_t* scalars, lcc_stream_t stream) {
-    OP_RET(ctx, lcc::gemv_residual((const bf16*)W, ldw, (const bf16*)x, (bf16*)h_inout, N, K, fin_ptr(scalars), ctx->num_sms, false,
+    OP_RET(ctx, lcc::gemv_residual((const bf16*)W, ldw, (const bf16*)x, (bf16*)h_inout, N, K, fin_ptr(scalars), nullptr, 0, ctx->num_sms, false,
                                    (cudaStream_t)stream), "lcc_gemv_residual");
 }
 
 int lcc_gemv_norm_swiglu(lcc_ctx* ctx, const void* W_gate_up, int ldw, const void* x, const void* norm_w,
                          float eps, void* act, int N2, int K, const int32_t* scalars, lcc_stream_t stream) {
     OP_RET(ctx, lcc::gemv_norm_swiglu((const bf16*)W_gate_up, ldw, (const bf16*)x, (const bf16*)norm_w, eps, (bf16*)act,
-                                      N2, K, fin_ptr(scalars), ctx->num_sms, false, (cudaStream_t)stream), "lcc_gemv_norm_swiglu");
+                                      N2, K, fin_ptr(scalars), nullptr, 0, ctx->num_sms, false, (cudaStream_t)stream),
+           "lcc_gemv_norm_swiglu");
 }
 
 int lcc_gemv_norm_logits(lcc_ctx* ctx, const void* W, int ldw, const void* x, const void* norm_w, float eps,

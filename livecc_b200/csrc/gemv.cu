@@ -80,7 +80,25 @@ struct GemvParams {
     float* out_f32;         // GV_LOGITS: raw logits [N]
     float* out_f32_b;       // GV_LOGITS: second copy (processed-logits buffer)
     const int* finished;
+    const uint8_t* pf_ptr;  // L2 prefetch of the NEXT kernel's weights, issued by the last CTAs of this grid
+    unsigned pf_bytes;
 };
+
+// The decode step is a strict chain of weight-streaming kernels. While the tail of one kernel drains (SM
+// imbalance, last-wave effects) HBM would idle; the last CTAs of every GEMV therefore prefetch the head of
+// the next kernel's weight matrix into the 126 MB L2 (fire-and-forget `prefetch.global.L2`), so the next
+// kernel's first megabytes come from L2 and the small matrices (qkv 33 MB, o_proj 26 MB) almost entirely.
+__device__ __forceinline__ void l2_prefetch_tail(const GemvParams& p) {
+    if (!p.pf_ptr || p.pf_bytes == 0) return;
+    const unsigned ntail = min(gridDim.x, 296u);
+    if (blockIdx.x + ntail < gridDim.x) return;
+    const unsigned part = blockIdx.x - (gridDim.x - ntail);
+    const unsigned lines = (p.pf_bytes + 127u) >> 7;
+    const unsigned per = (lines + ntail - 1) / ntail;
+    const unsigned l0 = part * per, l1 = min(lines, l0 + per);
+    for (unsigned l = l0 + threadIdx.x; l < l1; l += blockDim.x)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.pf_ptr + (size_t)l * 128));
+}
 
 template <int ROWS, bool NORM, int EPI>
 __global__ void __launch_bounds__(256) gemv_rows_kernel(const GemvParams p) {
@@ -115,7 +133,7 @@ __global__ void __launch_bounds__(256) gemv_rows_kernel(const GemvParams p) {
     pdl_wait();
     if (p.finished && *p.finished) return;
     stage_x<NORM>(xs, p.x, p.norm_w, p.eps, K, red);
-    if (!active) return;
+    if (!active) { l2_prefetch_tail(p); return; }
 
     float acc[ROWS];
 #pragma unroll
@@ -149,6 +167,7 @@ __global__ void __launch_bounds__(256) gemv_rows_kernel(const GemvParams p) {
     }
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) acc[r] = warp_sum(acc[r]);
+    l2_prefetch_tail(p);
     if (lane != 0) return;
     if (EPI == GV_SWIGLU) {
         const float gt = rbf(acc[0]), up = rbf(acc[ROWS - 1]);
@@ -229,6 +248,7 @@ __global__ void __launch_bounds__(256) gemv_splitk_kernel(const GemvParams p) {
         acc[r] = warp_sum(acc[r]);
         if (lane == 0) part[warp][r] = acc[r];
     }
+    l2_prefetch_tail(p);
     __syncthreads();
     if (threadIdx.x < ROWS) {
         const int n = row0 + threadIdx.x;
@@ -263,9 +283,10 @@ static int check_common(const GemvParams& p) {
 
 // qkv = W_qkv * rmsnorm(h) + b          (mq2vl.py:631, 559-565)
 int gemv_norm_bias(const bf16* W, int ldw, const bf16* x, const bf16* norm_w, float eps, const bf16* bias,
-                   bf16* out, int N, int K, const int* finished, int num_sms, bool pdl, cudaStream_t s) {
+                   bf16* out, int N, int K, const int* finished, const void* pf_ptr, size_t pf_bytes, int num_sms, bool pdl,
+                   cudaStream_t s) {
     GemvParams p{}; p.W = W; p.ldw = ldw; p.x = x; p.norm_w = norm_w; p.eps = eps; p.N = N; p.K = K;
-    p.bias = bias; p.out = out; p.finished = finished;
+    p.bias = bias; p.out = out; p.finished = finished; p.pf_ptr = (const uint8_t*)pf_ptr; p.pf_bytes = (unsigned)pf_bytes;
     if (int r = check_common(p)) return r;
     LCC_LAUNCH((gemv_rows_kernel<2, true, GV_BIAS>), (N + 15) / 16, K * 2);
     return 0;
@@ -273,8 +294,9 @@ int gemv_norm_bias(const bf16* W, int ldw, const bf16* x, const bf16* norm_w, fl
 
 // h += W * x                                (o_proj mq2vl.py:593,645; down_proj :504,660)
 int gemv_residual(const bf16* W, int ldw, const bf16* x, bf16* h_inout, int N, int K, const int* finished,
-                  int num_sms, bool pdl, cudaStream_t s) {
+                  const void* pf_ptr, size_t pf_bytes, int num_sms, bool pdl, cudaStream_t s) {
     GemvParams p{}; p.W = W; p.ldw = ldw; p.x = x; p.N = N; p.K = K; p.out = h_inout; p.finished = finished;
+    p.pf_ptr = (const uint8_t*)pf_ptr; p.pf_bytes = (unsigned)pf_bytes;
     if (int r = check_common(p)) return r;
     if (K > 8192) {
         LCC_LAUNCH((gemv_splitk_kernel<SPLITK_ROWS>), (N + SPLITK_ROWS - 1) / SPLITK_ROWS, K * 2);
@@ -286,9 +308,10 @@ int gemv_residual(const bf16* W, int ldw, const bf16* x, bf16* h_inout, int N, i
 
 // act = silu(Wg * rmsnorm(h)) * (Wu * rmsnorm(h)), gate/up rows interleaved by 16   (mq2vl.py:502-504, 657-659)
 int gemv_norm_swiglu(const bf16* W_gu, int ldw, const bf16* x, const bf16* norm_w, float eps, bf16* act,
-                     int N2 /* = 2*I */, int K, const int* finished, int num_sms, bool pdl, cudaStream_t s) {
+                     int N2 /* = 2*I */, int K, const int* finished, const void* pf_ptr, size_t pf_bytes, int num_sms,
+                     bool pdl, cudaStream_t s) {
     GemvParams p{}; p.W = W_gu; p.ldw = ldw; p.x = x; p.norm_w = norm_w; p.eps = eps; p.N = N2; p.K = K;
-    p.out = act; p.finished = finished;
+    p.out = act; p.finished = finished; p.pf_ptr = (const uint8_t*)pf_ptr; p.pf_bytes = (unsigned)pf_bytes;
     if (int r = check_common(p)) return r;
     if (N2 % 32) return -5;
     LCC_LAUNCH((gemv_rows_kernel<2, true, GV_SWIGLU>), (N2 + 15) / 16, K * 2);

@@ -37,12 +37,13 @@ int get_layout(const lcc_model* m, int need_patches, int need_tokens, WsLayout* 
 
 struct WsLayout {
     size_t vx, vh, vn, vqkv, vattn, vmlp, vcos, vsin, vcu;  // ViT
-    size_t hid, normed, qkv, attn, act, rank;                // prefill
+    size_t hid, normed, qkv, attn, act, rank, pf_part_o, pf_part_ml;  // prefill
     size_t h1, qkv1, attn1, act1, logits_raw, logits_proc, part_o, part_ml, attn_cnt;  // decode
     size_t total;
 };
 
 constexpr int kMaxSplit = 64;
+constexpr size_t kPrefillSplitRows = 8 * 1024;  // split-KV prefill partials: nsplit * S <= this many positions
 
 WsLayout make_layout(const lcc_model_config& c, int NP, int NT) {
     WsLayout L{};
@@ -65,6 +66,8 @@ WsLayout make_layout(const lcc_model_config& c, int NP, int NT) {
     L.attn = take(nt * c.q_heads * 128 * 2);
     L.act = take(nt * c.inter * 2);
     L.rank = take((nt + 2) * 4);
+    L.pf_part_o = take(kPrefillSplitRows * (size_t)c.q_heads * 128 * 4);
+    L.pf_part_ml = take(kPrefillSplitRows * (size_t)c.q_heads * 2 * 4);
     L.h1 = take((size_t)c.hidden * 2);
     L.qkv1 = take(qkv_dim * 2);
     L.attn1 = take((size_t)c.q_heads * 128 * 2);
@@ -224,7 +227,8 @@ int lcc_prefill(lcc_model* m, const lcc_stream_state* st, const int64_t* ids, co
         STEP(lcc::mrope_kv_write(qkv, qkv_dim, pos3, S, m->w.text_inv_freq, c.mrope_t, c.mrope_h, Hq, Hkv, kc, vc,
                                  st->page_table, LCC_PAGE_SIZE, past, s), "mrope + kv write");
         STEP(lcc::attn_prefill_paged(qkv, qkv_dim, kc, vc, st->page_table, LCC_PAGE_SIZE, Hq, Hkv, S, past, attn,
-                                     Hq * 128, s), "prefill attention");
+                                     Hq * 128, (float*)(ws + L.pf_part_o), (float*)(ws + L.pf_part_ml),
+                                     kPrefillSplitRows * (size_t)Hq, m->ctx->num_sms, s), "prefill attention");
         STEP(gemm(m, attn, Hq * 128, lw.o_w, Hq * 128, hid, H, S, H, Hq * 128, nullptr, hid, H, lcc::EPI_RESIDUAL, s), "o_proj");
         STEP(lcc::rmsnorm(hid, H, (const bf16*)lw.ln2_w, normed, H, S, H, c.rms_eps, s), "post_attention_layernorm");
         STEP(gemm(m, normed, H, lw.gate_up_w, H, act, c.inter, S, 2 * c.inter, H, nullptr, nullptr, 0, lcc::EPI_SWIGLU, s), "gate_up");
@@ -255,20 +259,29 @@ int lcc_decode_steps(lcc_model* m, const lcc_stream_state* st, int n_steps, int 
     const bool pdl = m->use_pdl;
     const int H = c.hidden, Hq = c.q_heads, Hkv = c.kv_heads, qkv_dim = (Hq + 2 * Hkv) * 128;
     const int* fin = st->scalars + LCC_SC_FINISHED;
+    // L2 prefetch window handed from each GEMV to its successor (see l2_prefetch_tail in gemv.cu)
+    const size_t kPf = 32u << 20;
+    const size_t qkv_bytes = (size_t)qkv_dim * H * 2, o_bytes = (size_t)H * Hq * 128 * 2;
+    const size_t gu_bytes = (size_t)2 * c.inter * H * 2, down_bytes = (size_t)H * c.inter * 2;
+    auto cap = [&](size_t b) { return b < kPf ? b : kPf; };
     for (int step = 0; step < n_steps; ++step) {
         for (int i = 0; i < c.layers; ++i) {
             const lcc_layer_weights& lw = m->layers[i];
             bf16* kc = (bf16*)st->k_pool + (size_t)i * st->layer_stride;
             bf16* vc = (bf16*)st->v_pool + (size_t)i * st->layer_stride;
+            const void* next_qkv = (i + 1 < c.layers) ? m->layers[i + 1].qkv_w : m->w.lm_head;
+            const size_t next_qkv_bytes = (i + 1 < c.layers) ? qkv_bytes : kPf;
             STEP(lcc::gemv_norm_bias((const bf16*)lw.qkv_w, H, h, (const bf16*)lw.ln1_w, c.rms_eps, (const bf16*)lw.qkv_b,
-                                     qkv, qkv_dim, H, fin, m->ctx->num_sms, pdl, s), "decode qkv");
+                                     qkv, qkv_dim, H, fin, lw.o_w, cap(o_bytes), m->ctx->num_sms, pdl, s), "decode qkv");
             STEP(lcc::attn_decode(qkv, kc, vc, st->page_table, LCC_PAGE_SIZE, st->scalars + LCC_SC_KV_LEN,
                                   st->scalars + LCC_SC_ROPE_POS, fin, m->w.text_inv_freq, Hq, Hkv, nsplit, part_o,
                                   part_ml, attn_cnt, attn, pdl, s), "decode attention");
-            STEP(lcc::gemv_residual((const bf16*)lw.o_w, Hq * 128, attn, h, H, Hq * 128, fin, m->ctx->num_sms, pdl, s), "decode o_proj");
+            STEP(lcc::gemv_residual((const bf16*)lw.o_w, Hq * 128, attn, h, H, Hq * 128, fin, lw.gate_up_w, cap(gu_bytes),
+                                    m->ctx->num_sms, pdl, s), "decode o_proj");
             STEP(lcc::gemv_norm_swiglu((const bf16*)lw.gate_up_w, H, h, (const bf16*)lw.ln2_w, c.rms_eps, act,
-                                       2 * c.inter, H, fin, m->ctx->num_sms, pdl, s), "decode gate_up");
-            STEP(lcc::gemv_residual((const bf16*)lw.down_w, c.inter, act, h, H, c.inter, fin, m->ctx->num_sms, pdl, s), "decode down_proj");
+                                       2 * c.inter, H, fin, lw.down_w, cap(down_bytes), m->ctx->num_sms, pdl, s), "decode gate_up");
+            STEP(lcc::gemv_residual((const bf16*)lw.down_w, c.inter, act, h, H, c.inter, fin, next_qkv, cap(next_qkv_bytes),
+                                    m->ctx->num_sms, pdl, s), "decode down_proj");
         }
         STEP(lcc::gemv_norm_logits((const bf16*)m->w.lm_head, H, h, (const bf16*)m->w.final_norm_w, c.rms_eps,
                                    (float*)(ws + L.logits_raw), (float*)(ws + L.logits_proc), c.vocab, H, fin, m->ctx->num_sms, pdl, s),

@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 
 namespace lcc {
@@ -28,18 +29,21 @@ int mrope_kv_write(bf16* qkv, int ld, const int* pos3, int S, const float* inv_f
 int vit_attention(const bf16* qkv, int ld, bf16* out, int o_ld, const int* cu_seqlens, int nseg,
                   int max_seg_len, int heads, int head_dim, cudaStream_t s);
 int attn_prefill_paged(const bf16* q, int q_ld, const bf16* kc, const bf16* vc, const int* page_table,
-                       int page_size, int Hq, int Hkv, int S, int past, bf16* out, int o_ld, cudaStream_t s);
+                       int page_size, int Hq, int Hkv, int S, int past, bf16* out, int o_ld, float* part_o,
+                       float* part_ml, size_t part_capacity_rows, int num_sms, cudaStream_t s);
 int attn_decode(bf16* qkv, bf16* kc, bf16* vc, const int* page_table, int page_size, const int* kv_len,
                 const int* rope_pos, const int* finished, const float* inv_freq, int Hq, int Hkv, int nsplit,
                 float* part_o, float* part_ml, int* counters, bf16* out, bool pdl, cudaStream_t s);
 
 // gemv.cu
 int gemv_norm_bias(const bf16* W, int ldw, const bf16* x, const bf16* norm_w, float eps, const bf16* bias,
-                   bf16* out, int N, int K, const int* finished, int num_sms, bool pdl, cudaStream_t s);
+                   bf16* out, int N, int K, const int* finished, const void* pf_ptr, size_t pf_bytes, int num_sms, bool pdl,
+                   cudaStream_t s);
 int gemv_residual(const bf16* W, int ldw, const bf16* x, bf16* h_inout, int N, int K, const int* finished,
-                  int num_sms, bool pdl, cudaStream_t s);
+                  const void* pf_ptr, size_t pf_bytes, int num_sms, bool pdl, cudaStream_t s);
 int gemv_norm_swiglu(const bf16* W_gu, int ldw, const bf16* x, const bf16* norm_w, float eps, bf16* act,
-                     int N2, int K, const int* finished, int num_sms, bool pdl, cudaStream_t s);
+                     int N2, int K, const int* finished, const void* pf_ptr, size_t pf_bytes, int num_sms, bool pdl,
+                     cudaStream_t s);
 int gemv_norm_logits(const bf16* W, int ldw, const bf16* x, const bf16* norm_w, float eps, float* logits,
                      float* logits_copy, int N, int K, const int* finished, int num_sms, bool pdl, cudaStream_t s);
 

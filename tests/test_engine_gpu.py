@@ -166,3 +166,29 @@ def test_generate_argument_surface(small):
     bad["input_ids"] = torch.cat([bad["input_ids"], torch.full((1, 1), cfg.video_token_id, device=DEV)], 1)
     with pytest.raises(ValueError):
         eng.generate(**bad, max_new_tokens=2)
+
+
+def test_long_cache_split_kv_prefill(small):
+    """A chunk-sized prefill over a long cache takes the split-KV attention path (+ merge kernel); parity
+    against the restatement (teacher forced) after a 3000-token text history."""
+    cfg, sd, eng, rs = small
+    proc = StubProcessor(cfg)
+    g = torch.Generator().manual_seed(11)
+    hist = torch.randint(1000, 9000, (1, 3000), generator=g).to(DEV)
+    seq_o, st_o, _ = rs.generate(hist, None, None, None, max_new_tokens=2, repetition_penalty=1.05, return_logits=True)
+    gen0 = seq_o[0, 3000:].tolist()
+    out = eng.generate(input_ids=hist, repetition_penalty=1.05, max_new_tokens=2, _forced_ids=gen0, output_logits=True)
+    cache, past = out.past_key_values, out.sequences[:, :-1]
+    past_o = seq_o[:, :-1]
+    inp = make_turn_inputs(proc, 1, 2, (112, 112), 7)
+    new_ids = inp.input_ids.to(DEV)
+    px, grid = inp.pixel_values_videos.to(DEV), inp.video_grid_thw
+    ids_o = torch.cat([past_o, new_ids], 1)
+    seq_o, st_o, logits_o = rs.generate(ids_o, px, grid, st_o, max_new_tokens=4, repetition_penalty=1.05, return_logits=True)
+    gen = seq_o[0, ids_o.shape[1]:].tolist()
+    out = eng.generate(input_ids=torch.cat([past, new_ids], 1), pixel_values_videos=px, video_grid_thw=grid,
+                       past_key_values=cache, repetition_penalty=1.05, max_new_tokens=len(gen), output_logits=True,
+                       _forced_ids=gen)
+    worst = max((a.float().flatten() - b.float().flatten()).abs().max().item() for a, b in zip(logits_o, out.logits))
+    assert worst < LOGIT_ATOL, worst
+    assert out.sequences[0, ids_o.shape[1]:].tolist() == gen
