@@ -464,7 +464,6 @@ __device__ __forceinline__ void rope1d_row(const bf16* src, bf16* dst, int lane_
 
 __global__ void __launch_bounds__(128) attn_decode_kernel(const DecodeAttnParams p) {
     constexpr int D = 128, LDS = D + 8, BN = 64;
-    pdl_launch_dependents();
     pdl_wait();  // qkv of this token comes from the previous kernel
     if (p.finished && *p.finished) return;
     extern __shared__ __align__(16) uint8_t smem_attn[];
@@ -604,6 +603,7 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const DecodeAttnParams
     }  // !empty
 
     // ---- the last CTA of this KV group to arrive merges all splits (replaces a separate combine launch) ----
+    pdl_launch_dependents();
     __shared__ int s_last;
     __threadfence();
     __syncthreads();

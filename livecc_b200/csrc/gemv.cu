@@ -100,14 +100,13 @@ __device__ __forceinline__ void l2_prefetch_tail(const GemvParams& p) {
         asm volatile("prefetch.global.L2 [%0];" ::"l"(p.pf_ptr + (size_t)l * 128));
 }
 
-template <int ROWS, bool NORM, int EPI>
+template <int ROWS, bool NORM, int EPI, int UNROLL>
 __global__ void __launch_bounds__(256) gemv_rows_kernel(const GemvParams p) {
-    pdl_launch_dependents();
     extern __shared__ __align__(16) uint8_t smem_gemv[];
     bf16* xs = reinterpret_cast<bf16*>(smem_gemv);
     __shared__ float red[32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int row0 = (blockIdx.x * 8 + warp) * ROWS;
+    const int row0 = (blockIdx.x * (blockDim.x >> 5) + warp) * ROWS;
     const bool active = row0 < p.N;
     // GV_SWIGLU: the warp's two rows are gate row and its matching up row (16 apart in a 32-row group)
     int rows[ROWS];
@@ -120,51 +119,44 @@ __global__ void __launch_bounds__(256) gemv_rows_kernel(const GemvParams p) {
         for (int r = 0; r < ROWS; ++r) rows[r] = min(row0 + r, p.N - 1);
     }
     const int K = p.K;
-    constexpr int UNROLL = 4;
-    // ---- weight prefetch: weights are never written during a step, so the first batch of loads is
-    //      issued before the activation vector of the previous kernel is even looked at ----
+    // ---- weight prefetch: weights are never written during a step, so the first batch of loads
+    //      (ROWS x UNROLL 16-byte loads per lane) is issued before the activation vector of the previous
+    //      kernel is even looked at. Loads past the end of the row are predicated off. ----
     uint4 w[ROWS][UNROLL];
-    const bool full_first = active && (lane * 8 + (UNROLL - 1) * 256) < K;
 #pragma unroll
     for (int r = 0; r < ROWS; ++r)
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u)
-            w[r][u] = full_first ? ld_stream16(p.W + (size_t)rows[r] * p.ldw + lane * 8 + u * 256) : make_uint4(0, 0, 0, 0);
+        for (int u = 0; u < UNROLL; ++u) {
+            const int cc = lane * 8 + u * 256;
+            w[r][u] = (active && cc < K) ? ld_stream16(p.W + (size_t)rows[r] * p.ldw + cc) : make_uint4(0, 0, 0, 0);
+        }
     pdl_wait();
     if (p.finished && *p.finished) return;
     stage_x<NORM>(xs, p.x, p.norm_w, p.eps, K, red);
-    if (!active) { l2_prefetch_tail(p); return; }
+    if (!active) { pdl_launch_dependents(); l2_prefetch_tail(p); return; }
 
     float acc[ROWS];
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) acc[r] = 0.f;
-    int c = lane * 8;
-    if (full_first) {
+    for (int c = lane * 8; c < K; c += UNROLL * 256) {
+        if (c != lane * 8) {
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
-            const uint4 xv = *reinterpret_cast<const uint4*>(xs + c + u * 256);
+            for (int r = 0; r < ROWS; ++r)
 #pragma unroll
-            for (int r = 0; r < ROWS; ++r) acc[r] += dot8(w[r][u], xv);
+                for (int u = 0; u < UNROLL; ++u) {
+                    const int cc = c + u * 256;
+                    w[r][u] = (cc < K) ? ld_stream16(p.W + (size_t)rows[r] * p.ldw + cc) : make_uint4(0, 0, 0, 0);
+                }
         }
-        c += UNROLL * 256;
-    }
-    for (; c + (UNROLL - 1) * 256 < K; c += UNROLL * 256) {
-#pragma unroll
-        for (int r = 0; r < ROWS; ++r)
-#pragma unroll
-            for (int u = 0; u < UNROLL; ++u) w[r][u] = ld_stream16(p.W + (size_t)rows[r] * p.ldw + c + u * 256);
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
-            const uint4 xv = *reinterpret_cast<const uint4*>(xs + c + u * 256);
+            const int cc = min(c + u * 256, K - 8);  // clamped read; the matching weights are zero past K
+            const uint4 xv = *reinterpret_cast<const uint4*>(xs + cc);
 #pragma unroll
             for (int r = 0; r < ROWS; ++r) acc[r] += dot8(w[r][u], xv);
         }
     }
-    for (; c < K; c += 256) {
-        const uint4 xv = *reinterpret_cast<const uint4*>(xs + c);
-#pragma unroll
-        for (int r = 0; r < ROWS; ++r) acc[r] += dot8(ld_stream16(p.W + (size_t)rows[r] * p.ldw + c), xv);
-    }
+    pdl_launch_dependents();  // this warp's weight stream is done: let the next kernel start its prefetch
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) acc[r] = warp_sum(acc[r]);
     l2_prefetch_tail(p);
@@ -191,7 +183,7 @@ __global__ void __launch_bounds__(256) gemv_rows_kernel(const GemvParams p) {
 
 template <int ROWS>
 __global__ void __launch_bounds__(256) gemv_splitk_kernel(const GemvParams p) {
-    pdl_launch_dependents();
+    static_assert(ROWS <= 8, "part[] is sized for <= 8 rows");
     extern __shared__ __align__(16) uint8_t smem_gemv[];
     bf16* xs = reinterpret_cast<bf16*>(smem_gemv);
     __shared__ float red[32];
@@ -243,6 +235,7 @@ __global__ void __launch_bounds__(256) gemv_splitk_kernel(const GemvParams p) {
         for (int r = 0; r < ROWS; ++r)
             acc[r] += dot8(ld_stream16(p.W + (size_t)min(row0 + r, p.N - 1) * p.ldw + c), xv);
     }
+    pdl_launch_dependents();
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
         acc[r] = warp_sum(acc[r]);
@@ -261,7 +254,6 @@ __global__ void __launch_bounds__(256) gemv_splitk_kernel(const GemvParams p) {
     }
 }
 
-constexpr int SPLITK_ROWS = 8;
 
 template <typename Kern>
 static int set_smem(Kern kern, int bytes) {
@@ -274,12 +266,29 @@ static int check_common(const GemvParams& p) {
     return 0;
 }
 
-#define LCC_LAUNCH(kern, grid, smem)                                                                   \
+#define LCC_LAUNCH_B(kern, grid, block, smem)                                                          \
     do {                                                                                               \
         static bool set_ = false;                                                                      \
         if (!set_) { if (set_smem(kern, 200 * 1024)) return -3; set_ = true; }                         \
-        if (launch_kernel(kern, dim3(grid), dim3(256), (size_t)(smem), s, pdl, p) != cudaSuccess) return -4; \
+        if (launch_kernel(kern, dim3(grid), dim3(block), (size_t)(smem), s, pdl, p) != cudaSuccess) return -4; \
     } while (0)
+#define LCC_LAUNCH(kern, grid, smem) LCC_LAUNCH_B(kern, grid, 256, smem)
+
+// Rows per CTA for a one-wave grid: all CTAs of these small kernels are resident at once, so the SM that
+// receives ceil(ctas/num_sms) CTAs finishes last. Pick the candidate with the best (max load / mean load);
+// ties go to the larger CTA (fewer copies of x staged).
+static int pick_rows_per_cta(int N, int num_sms, const int* cand, int ncand) {
+    int best = cand[0];
+    double best_ratio = 1e9;
+    for (int i = 0; i < ncand; ++i) {
+        const int r = cand[i];
+        const int ctas = (N + r - 1) / r;
+        const double mean = (double)ctas / num_sms;
+        const double ratio = (double)((ctas + num_sms - 1) / num_sms) / mean;
+        if (ratio < best_ratio - 1e-9 || (ratio < best_ratio + 1e-9 && r > best)) { best_ratio = ratio; best = r; }
+    }
+    return best;
+}
 
 // qkv = W_qkv * rmsnorm(h) + b          (mq2vl.py:631, 559-565)
 int gemv_norm_bias(const bf16* W, int ldw, const bf16* x, const bf16* norm_w, float eps, const bf16* bias,
@@ -288,7 +297,7 @@ int gemv_norm_bias(const bf16* W, int ldw, const bf16* x, const bf16* norm_w, fl
     GemvParams p{}; p.W = W; p.ldw = ldw; p.x = x; p.norm_w = norm_w; p.eps = eps; p.N = N; p.K = K;
     p.bias = bias; p.out = out; p.finished = finished; p.pf_ptr = (const uint8_t*)pf_ptr; p.pf_bytes = (unsigned)pf_bytes;
     if (int r = check_common(p)) return r;
-    LCC_LAUNCH((gemv_rows_kernel<2, true, GV_BIAS>), (N + 15) / 16, K * 2);
+    LCC_LAUNCH((gemv_rows_kernel<2, true, GV_BIAS, 8>), (N + 15) / 16, K * 2);
     return 0;
 }
 
@@ -299,9 +308,18 @@ int gemv_residual(const bf16* W, int ldw, const bf16* x, bf16* h_inout, int N, i
     p.pf_ptr = (const uint8_t*)pf_ptr; p.pf_bytes = (unsigned)pf_bytes;
     if (int r = check_common(p)) return r;
     if (K > 8192) {
-        LCC_LAUNCH((gemv_splitk_kernel<SPLITK_ROWS>), (N + SPLITK_ROWS - 1) / SPLITK_ROWS, K * 2);
+        static const int cand[] = {4, 5, 6, 8};
+        switch (pick_rows_per_cta(N, num_sms, cand, 4)) {
+            case 4: LCC_LAUNCH((gemv_splitk_kernel<4>), (N + 3) / 4, K * 2); break;
+            case 5: LCC_LAUNCH((gemv_splitk_kernel<5>), (N + 4) / 5, K * 2); break;
+            case 6: LCC_LAUNCH((gemv_splitk_kernel<6>), (N + 5) / 6, K * 2); break;
+            default: LCC_LAUNCH((gemv_splitk_kernel<8>), (N + 7) / 8, K * 2); break;
+        }
     } else {
-        LCC_LAUNCH((gemv_rows_kernel<2, false, GV_RESIDUAL>), (N + 15) / 16, K * 2);
+        static const int cand[] = {5, 6, 7, 8, 10, 12, 14, 16};  // warps x rows-per-warp
+        const int r = pick_rows_per_cta(N, num_sms, cand, 8);
+        if (r <= 8) LCC_LAUNCH_B((gemv_rows_kernel<1, false, GV_RESIDUAL, 8>), (N + r - 1) / r, r * 32, K * 2);
+        else LCC_LAUNCH_B((gemv_rows_kernel<2, false, GV_RESIDUAL, 8>), (N + r - 1) / r, (r / 2) * 32, K * 2);
     }
     return 0;
 }
@@ -314,7 +332,7 @@ int gemv_norm_swiglu(const bf16* W_gu, int ldw, const bf16* x, const bf16* norm_
     p.out = act; p.finished = finished; p.pf_ptr = (const uint8_t*)pf_ptr; p.pf_bytes = (unsigned)pf_bytes;
     if (int r = check_common(p)) return r;
     if (N2 % 32) return -5;
-    LCC_LAUNCH((gemv_rows_kernel<2, true, GV_SWIGLU>), (N2 + 15) / 16, K * 2);
+    LCC_LAUNCH((gemv_rows_kernel<2, true, GV_SWIGLU, 4>), (N2 + 15) / 16, K * 2);
     return 0;
 }
 
@@ -324,7 +342,7 @@ int gemv_norm_logits(const bf16* W, int ldw, const bf16* x, const bf16* norm_w, 
     GemvParams p{}; p.W = W; p.ldw = ldw; p.x = x; p.norm_w = norm_w; p.eps = eps; p.N = N; p.K = K;
     p.out_f32 = logits; p.out_f32_b = logits_copy; p.finished = finished;
     if (int r = check_common(p)) return r;
-    LCC_LAUNCH((gemv_rows_kernel<4, true, GV_LOGITS>), (N + 31) / 32, K * 2);
+    LCC_LAUNCH((gemv_rows_kernel<4, true, GV_LOGITS, 4>), (N + 31) / 32, K * 2);
     return 0;
 }
 

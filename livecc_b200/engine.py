@@ -88,7 +88,9 @@ class LiveCCB200ForConditionalGeneration:
         self._ensure_workspace(3072, 1024)
         self._graphs = {}
         self.use_cuda_graph = os.environ.get("LIVECC_B200_NO_GRAPH", "0") != "1"
-        self.nsplit = max(1, min(64, (self.ctx.num_sms + t.num_key_value_heads - 1) // t.num_key_value_heads))
+        # split-KV factor of the decode attention: at most one CTA per SM, at least ~8 KV tiles (512 tokens) per split
+        self.max_nsplit = max(1, min(64, (self.ctx.num_sms + t.num_key_value_heads - 1) // t.num_key_value_heads))
+        self.nsplit = self.max_nsplit
         self.last_stats = {}
         # per-phase device time of the last generate() (CUDA events on the launch stream) and running totals
         self.phase_ms_total = {"vit": 0.0, "prefill": 0.0, "decode": 0.0, "calls": 0, "decode_steps": 0}
@@ -288,16 +290,19 @@ class LiveCCB200ForConditionalGeneration:
 
         self._ev[2].record()
         # ---- decode steps ----
+        kv_tiles = (past + S + max_new_tokens + 63) // 64
+        nsplit = max(1, min(self.max_nsplit, (kv_tiles + 7) // 8))
+        self.nsplit = nsplit
         n_steps = max_new_tokens - 1
         if output_logits or _forced_ids is not None:
             for i in range(n_steps):
-                self._native.decode_steps(st, 1, self.nsplit, sp)
+                self._native.decode_steps(st, 1, nsplit, sp)
                 if output_logits:
                     logits_out.append(self._raw_logits().clone())
                 if _forced_ids is not None and i + 1 < len(_forced_ids):
                     self._force_token(cache, L, i + 1, _forced_ids, max_new_tokens)
         elif n_steps > 0:
-            self._run_decode(cache, st, sp, n_steps)
+            self._run_decode(cache, st, sp, n_steps, nsplit)
 
         self._ev[3].record()
         # ---- one host sync per generate(): read the stream scalars ----
@@ -322,11 +327,11 @@ class LiveCCB200ForConditionalGeneration:
         return out if return_dict_in_generate else sequences
 
     # ------------------------------------------------------------------------------------------
-    def _run_decode(self, cache: PagedKVCache, st, sp: _cabi.Sampling, n_steps: int):
+    def _run_decode(self, cache: PagedKVCache, st, sp: _cabi.Sampling, n_steps: int, nsplit: int):
         if not self.use_cuda_graph:
-            self._native.decode_steps(st, n_steps, self.nsplit, sp)
+            self._native.decode_steps(st, n_steps, nsplit, sp)
             return
-        key = (cache.graph_key(), self._native.workspace.data_ptr(), self.nsplit, sp.repetition_penalty, sp.thr_token,
+        key = (cache.graph_key(), self._native.workspace.data_ptr(), nsplit, sp.repetition_penalty, sp.thr_token,
                sp.thr_base, sp.thr_step, sp.eos_token_id, sp.max_new_tokens)
         g = self._graphs.get(key)
         if g is None:
@@ -339,7 +344,7 @@ class LiveCCB200ForConditionalGeneration:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.stream(side):
                 with torch.cuda.graph(g, stream=side, capture_error_mode="thread_local"):
-                    self._native.decode_steps(st, 1, self.nsplit, sp)
+                    self._native.decode_steps(st, 1, nsplit, sp)
             torch.cuda.current_stream(self.device).wait_stream(side)
             self._graphs[key] = g
         for _ in range(n_steps):

@@ -22,3 +22,12 @@ def ctx():
 
     torch.cuda.set_device(0)
     return Context(0)
+
+
+@pytest.fixture(autouse=True)
+def _seed_everything():
+    import torch
+
+    torch.manual_seed(1234)
+    if torch.cuda.is_available():
+        torch.cuda.manual_seed_all(1234)

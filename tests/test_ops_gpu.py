@@ -114,6 +114,7 @@ def test_embed_gather(ctx):
     table = _rand((V, H), 5)
     ids = torch.randint(0, V, (S,), device=DEV)
     vid_id = 4987
+    ids[ids == vid_id] = 0  # random ids must not collide with the placeholder id
     ids[40:296] = vid_id
     ids[500:564] = vid_id
     video = _rand((320, H), 6)

@@ -40,3 +40,18 @@ wbytes = (t.num_hidden_layers * ((t.num_attention_heads + 2 * t.num_key_value_he
 kvb = st["kv_len"] * 2 * t.num_hidden_layers * t.num_key_value_heads * 128 * 2
 ms = st["decode_ms"] / max(st["generated"] - 1, 1)
 print(f"bytes/step {(wbytes + kvb) / 1e9:.2f} GB -> {(wbytes + kvb) / ms / 1e6:.0f} GB/s")
+
+# ---- launch-overhead probe: replay the captured decode-step graph with the finished flag set, so every kernel
+#      exits right after its flag check. What remains is the per-node launch/scheduling cost of the 170-node graph.
+g = list(eng._graphs.values())[-1]
+with torch.inference_mode():
+    cache.scalars[_cabi.SC_FINISHED] = 1
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(50):
+    g.replay()
+e1.record()
+torch.cuda.synchronize()
+print(f"no-op graph replay (all kernels early-exit): {e0.elapsed_time(e1) / 50:.3f} ms per step "
+      f"for {cfg.text_config.num_hidden_layers * 5 + 2} kernel nodes")
