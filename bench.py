@@ -225,16 +225,18 @@ def time_dominant_kernel(eng, iters=5):
 # ------------------------------------------------------------------------------------------------
 # CPU reference arm (HF eager fp32 on host cores)
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_sample(cfg, size, max_new=8, steps=1, warmup=0):
-    """The reference's own CPU path: transformers Qwen2VLForConditionalGeneration, fp32, eager attention,
-    all host threads, through oracle/hf_oracle.py. Bounded sample: a fresh stream's first turn with ONE
-    2-frame chunk at size x size and `max_new` greedy tokens (repetition_penalty 1.05)."""
+def cpu_reference_sample(cfg, size, max_new=8, steps=1, warmup=0, budget_s=150.0):
+    """The reference's own CPU path: transformers Qwen2VLForConditionalGeneration, fp32, eager attention, through
+    oracle/hf_oracle.py. Bounded sample: a fresh stream's first turn with ONE 2-frame chunk at size x size and
+    `max_new` greedy tokens (repetition_penalty 1.05). Threads: min(host cores, 32) — oversubscribing a
+    128-core box made the eager path several times slower. Stops early once `budget_s` of samples were timed."""
     from livecc_b200.checkpoint import synthetic_tensors
     from livecc_b200.processing import StubProcessor
     from oracle.hf_oracle import build_hf_model, hf_generate_chunk
 
     ncores = os.cpu_count() or 1
-    torch.set_num_threads(ncores)
+    nthreads = max(1, min(ncores, int(os.environ.get("LIVECC_CPU_THREADS", "32"))))
+    torch.set_num_threads(nthreads)
     gen_dev = "cuda" if torch.cuda.is_available() else "cpu"
     model = build_hf_model(cfg, synthetic_tensors(cfg, 1234, torch.float32, "cpu", gen_device=gen_dev),
                            dtype=torch.float32, device="cpu", attn_implementation="eager")
@@ -245,19 +247,24 @@ def cpu_reference_sample(cfg, size, max_new=8, steps=1, warmup=0):
                {"type": "text", "text": "Please describe the video."}]
     text = proc.apply_chat_template([{"role": "user", "content": content}], tokenize=False, add_generation_prompt=True)
     times, toks = [], 0
+    spent = 0.0
     for i in range(warmup + steps):
         inputs = proc(text=text, videos=[clip], return_attention_mask=False)
+        model.model.rope_deltas = None
         t0 = time.perf_counter()
         out, L = hf_generate_chunk(model, inputs, None, None, max_new_tokens=max_new)
         dt = time.perf_counter() - t0
-        if i >= warmup:
+        spent += dt
+        if i >= warmup or spent > budget_s:
             times.append(dt)
             toks = out.sequences.shape[1] - L
+        if spent > budget_s:
+            break
     sec = sum(times) / len(times)
-    return {"tokens_per_s": toks / sec, "frames_per_s": 2 / sec, "sec_per_sample": sec, "cores": ncores,
-            "threads": torch.get_num_threads(), "tokens": toks,
+    return {"tokens_per_s": toks / sec, "frames_per_s": 2 / sec, "sec_per_sample": sec, "cores": nthreads,
+            "host_cores": ncores, "tokens": toks, "timed_samples": len(times),
             "sample": f"first turn of a fresh stream: one 2-frame {size}x{size} chunk + {toks} greedy tokens, fp32 eager, "
-                      f"{steps} timed run(s)"}
+                      f"{nthreads} threads, {len(times)} timed sample(s)"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -276,7 +283,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        r = cpu_reference_sample(cfg, args.size, max_new=8, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+        r = cpu_reference_sample(cfg, args.size, max_new=4, steps=max(1, args.steps), warmup=min(args.warmup, 1))
         line = {"impl": "reference", "metric": METRIC, "value": r["tokens_per_s"], "unit": "tokens/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["sec_per_sample"] * 1e3,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -427,7 +434,7 @@ def main():
                              "frac": bytes_avg / (ms_per_dstep / 1e3) / 1e9 / peak, "decode_steps": dsteps}
     if not args.no_cpu_baseline and world == 1:
         try:
-            r = cpu_reference_sample(cfg, args.size, max_new=4, steps=1, warmup=0)
+            r = cpu_reference_sample(cfg, args.size, max_new=4, steps=1, warmup=0, budget_s=60.0)
             line["cpu_baseline"] = {"value": r["tokens_per_s"], "unit": "tokens/s", "frames_per_s": r["frames_per_s"],
                                     "cores": r["cores"], "kind": "reference", "sample": r["sample"]}
         except Exception as ex:  # the baseline must never take the GPU number down with it

@@ -138,19 +138,40 @@ __global__ void __launch_bounds__(256) gemv_rows_kernel(const GemvParams p) {
     float acc[ROWS];
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) acc[r] = 0.f;
-    for (int c = lane * 8; c < K; c += UNROLL * 256) {
-        if (c != lane * 8) {
+    // first batch: already in registers (loads past K were predicated to zero; x reads are clamped)
 #pragma unroll
-            for (int r = 0; r < ROWS; ++r)
+    for (int u = 0; u < UNROLL; ++u) {
+        const int cc = min(lane * 8 + u * 256, K - 8);
+        const uint4 xv = *reinterpret_cast<const uint4*>(xs + cc);
 #pragma unroll
-                for (int u = 0; u < UNROLL; ++u) {
-                    const int cc = c + u * 256;
-                    w[r][u] = (cc < K) ? ld_stream16(p.W + (size_t)rows[r] * p.ldw + cc) : make_uint4(0, 0, 0, 0);
-                }
-        }
+        for (int r = 0; r < ROWS; ++r) acc[r] += dot8(w[r][u], xv);
+    }
+    int c = lane * 8 + UNROLL * 256;
+    // full batches: plain loads, no predication
+    for (; (c - lane * 8) + UNROLL * 256 <= K; c += UNROLL * 256) {
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) w[r][u] = ld_stream16(p.W + (size_t)rows[r] * p.ldw + c + u * 256);
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
-            const int cc = min(c + u * 256, K - 8);  // clamped read; the matching weights are zero past K
+            const uint4 xv = *reinterpret_cast<const uint4*>(xs + c + u * 256);
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) acc[r] += dot8(w[r][u], xv);
+        }
+    }
+    // remainder (< UNROLL chunks per lane): one predicated batch, all loads in flight together
+    if ((c - lane * 8) < K) {
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const int cc = c + u * 256;
+                w[r][u] = (cc < K) ? ld_stream16(p.W + (size_t)rows[r] * p.ldw + cc) : make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const int cc = min(c + u * 256, K - 8);
             const uint4 xv = *reinterpret_cast<const uint4*>(xs + cc);
 #pragma unroll
             for (int r = 0; r < ROWS; ++r) acc[r] += dot8(w[r][u], xv);

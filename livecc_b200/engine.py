@@ -291,7 +291,11 @@ class LiveCCB200ForConditionalGeneration:
         self._ev[2].record()
         # ---- decode steps ----
         kv_tiles = (past + S + max_new_tokens + 63) // 64
-        nsplit = max(1, min(self.max_nsplit, (kv_tiles + 7) // 8))
+        want = max(1, (kv_tiles + 7) // 8)          # >= ~8 KV tiles (512 tokens) per split
+        nsplit = 1
+        while nsplit < want and nsplit < self.max_nsplit:  # quantised to powers of two: at most 7 captured graphs
+            nsplit *= 2
+        nsplit = min(nsplit, self.max_nsplit)
         self.nsplit = nsplit
         n_steps = max_new_tokens - 1
         if output_logits or _forced_ids is not None:
@@ -337,7 +341,7 @@ class LiveCCB200ForConditionalGeneration:
         if g is None:
             # capture ONE decode step (28 layers + lm_head + token selection); replay it n_steps times.
             # All step-varying state (kv_len, position, token, finished flag) lives in device memory.
-            if len(self._graphs) > 16:
+            if len(self._graphs) > 32:
                 self._graphs.clear()
             side = torch.cuda.Stream(device=self.device)
             side.wait_stream(torch.cuda.current_stream(self.device))

@@ -54,8 +54,25 @@ class PagePool:
     def release(self, pages: List[int]):
         self.free.extend(pages)
 
+    # Per-stream device buffers (page table, scalars, id buffer) are recycled through the pool so that their
+    # addresses — which are baked into captured decode graphs — stay stable from one stream to the next.
+    def acquire_buffers(self) -> "StreamBuffers":
+        free = self.__dict__.setdefault("_free_buffers", [])
+        return free.pop() if free else StreamBuffers(self.device)
+
+    def release_buffers(self, b: "StreamBuffers"):
+        self.__dict__.setdefault("_free_buffers", []).append(b)
+
     def bytes_per_token(self) -> int:
         return 2 * self.layers * self.kv_heads * 128 * 2
+
+
+class StreamBuffers:
+    def __init__(self, device):
+        self.page_table = torch.zeros(512, dtype=torch.int32, device=device)   # 32k tokens before the first growth
+        self.scalars = torch.zeros(SC_COUNT, dtype=torch.int32, device=device)
+        self.seq_buf = torch.zeros(32768, dtype=torch.int64, device=device)
+        self.generation = 0
 
 
 class PagedKVCache:
@@ -66,12 +83,25 @@ class PagedKVCache:
         self.pages: List[int] = []
         self.seq_len = 0                       # tokens whose K/V are in the cache
         self.rope_delta: Optional[int] = None  # turn-0 value, never updated (mq2vl.py:1207,1518)
-        dev = pool.device
-        self.page_table = torch.zeros(64, dtype=torch.int32, device=dev)
+        self._buf = pool.acquire_buffers()
         self._pages_uploaded = 0
-        self.scalars = torch.zeros(SC_COUNT, dtype=torch.int32, device=dev)
-        self.seq_buf = torch.zeros(2048, dtype=torch.int64, device=dev)
-        self.buffers_generation = 0  # bumped when page_table / seq_buf storage moves
+
+    # the buffers live in a recyclable slot; expose them under their old names
+    @property
+    def page_table(self):
+        return self._buf.page_table
+
+    @property
+    def scalars(self):
+        return self._buf.scalars
+
+    @property
+    def seq_buf(self):
+        return self._buf.seq_buf
+
+    @property
+    def buffers_generation(self):
+        return self._buf.generation
 
     # -- HF Cache surface used by callers (gen/utils.py:3748) -----------------------------------
     def get_seq_length(self, layer_idx: int = 0) -> int:
@@ -86,10 +116,10 @@ class PagedKVCache:
         if need > len(self.pages):
             self.pages.extend(self.pool.alloc(need - len(self.pages)))
         if need > self.page_table.numel():
-            new = torch.zeros(max(need, 2 * self.page_table.numel()), dtype=torch.int32, device=self.pool.device)
-            self.page_table = new
+            self._buf.page_table = torch.zeros(max(need, 2 * self.page_table.numel()), dtype=torch.int32,
+                                               device=self.pool.device)
             self._pages_uploaded = 0
-            self.buffers_generation += 1
+            self._buf.generation += 1
         if self._pages_uploaded < len(self.pages):
             host = torch.tensor(self.pages[self._pages_uploaded:], dtype=torch.int32)
             self.page_table[self._pages_uploaded:len(self.pages)].copy_(host, non_blocking=False)
@@ -97,8 +127,9 @@ class PagedKVCache:
 
     def ensure_seq_capacity(self, n_ids: int):
         if n_ids > self.seq_buf.numel():
-            self.seq_buf = torch.zeros(max(n_ids, 2 * self.seq_buf.numel()), dtype=torch.int64, device=self.pool.device)
-            self.buffers_generation += 1
+            self._buf.seq_buf = torch.zeros(max(n_ids, 2 * self.seq_buf.numel()), dtype=torch.int64,
+                                            device=self.pool.device)
+            self._buf.generation += 1
 
     def stream_state(self) -> StreamState:
         p = self.pool
@@ -114,6 +145,9 @@ class PagedKVCache:
         if self.pages:
             self.pool.release(self.pages)
             self.pages = []
+        if self._buf is not None:
+            self.pool.release_buffers(self._buf)
+            self._buf = None
         self.seq_len = 0
         self.rope_delta = None
         self._pages_uploaded = 0

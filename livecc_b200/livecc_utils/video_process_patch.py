@@ -77,7 +77,7 @@ class _Batch:
 
 class SyntheticVideoReader:
     """`synthetic://<frames>x<height>x<width>@<fps>?seed=<n>`: deterministic uint8 THWC frames.
-    Frames are low-pass noise plus a per-frame drift so that attention is not degenerate."""
+    Frames are moving crops of a low-pass noise canvas, so that attention is not degenerate."""
 
     def __init__(self, path: str, num_threads: int = 0):
         m = re.match(r"synthetic://(\d+)x(\d+)x(\d+)@([\d.]+)(?:\?seed=(\d+))?$", path)
@@ -101,12 +101,29 @@ class SyntheticVideoReader:
             self._frame_pts = np.stack([start, start + 1.0 / self.fps], axis=1)
         return self._frame_pts[idx]
 
+    _BASE_CACHE = {}
+
+    def _base(self) -> torch.Tensor:
+        """One smooth noise canvas per (size, seed), cached per process; frames are moving crops of it, so
+        producing a frame costs a 0.6 MB copy (the synthetic source must not dominate the ingest time)."""
+        key = (self.h, self.w, self.seed)
+        base = self._BASE_CACHE.get(key)
+        if base is None:
+            g = torch.Generator().manual_seed(self.seed * 1000003 + 17)
+            hh, ww = self.h + 64, self.w + 64
+            low = torch.rand((1, 3, max(2, hh // 16), max(2, ww // 16)), generator=g)
+            img = torch.nn.functional.interpolate(low, size=(hh, ww), mode="bilinear", align_corners=False)[0]
+            base = (img * 200 + 25).clamp(0, 255).to(torch.uint8).permute(1, 2, 0).contiguous()  # HWC
+            if len(self._BASE_CACHE) > 64:
+                self._BASE_CACHE.clear()
+            self._BASE_CACHE[key] = base
+        return base
+
     def _frame(self, i: int) -> np.ndarray:
-        g = torch.Generator().manual_seed(self.seed * 1000003 + int(i))
-        low = torch.rand((1, 3, max(2, self.h // 16), max(2, self.w // 16)), generator=g)
-        img = torch.nn.functional.interpolate(low, size=(self.h, self.w), mode="bilinear", align_corners=False)[0]
-        img = (img * 200 + 25 + 10 * math.sin(i / 7.0)).clamp(0, 255)
-        return img.permute(1, 2, 0).to(torch.uint8).numpy()
+        base = self._base()
+        dy = (int(i) * 7) % 64
+        dx = (int(i) * 13) % 64
+        return base[dy:dy + self.h, dx:dx + self.w].numpy().copy()
 
     def next(self):
         f = self._frame(self._cursor)
