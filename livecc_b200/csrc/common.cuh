@@ -205,10 +205,17 @@ __device__ __forceinline__ void tmem_ld_wait() {
 // kernel start early; pdl_wait() blocks until the PREVIOUS kernel has completed and its writes are
 // visible. Everything before pdl_wait() may only touch data no kernel of the step writes (weights).
 // Both are no-ops for ordinary launches.
+// Measured on B200: PDL made the decode step slower in every variant tried, so the instructions are
+// compiled in only with -DLCC_ENABLE_PDL; by default both helpers are empty.
+#ifdef LCC_ENABLE_PDL
 __device__ __forceinline__ void pdl_launch_dependents() {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#else
+__device__ __forceinline__ void pdl_launch_dependents() {}
+__device__ __forceinline__ void pdl_wait() {}
+#endif
 
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred = 0;

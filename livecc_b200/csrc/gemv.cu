@@ -132,8 +132,15 @@ __global__ void __launch_bounds__(256) gemv_rows_kernel(const GemvParams p) {
         }
     pdl_wait();
     if (p.finished && *p.finished) return;
-    stage_x<NORM>(xs, p.x, p.norm_w, p.eps, K, red);
+    // NORM: x is normalised once per CTA into shared memory. Otherwise x is read straight from global memory
+    // through the read-only path (L1-resident after the first touch on an SM): no staging, no block barrier.
+    const bf16* xsrc = xs;
+    if (NORM) stage_x<true>(xs, p.x, p.norm_w, p.eps, K, red);
+    else xsrc = p.x;
     if (!active) { pdl_launch_dependents(); l2_prefetch_tail(p); return; }
+    auto ldx = [&](int off) -> uint4 {
+        return NORM ? *reinterpret_cast<const uint4*>(xsrc + off) : __ldg(reinterpret_cast<const uint4*>(xsrc + off));
+    };
 
     float acc[ROWS];
 #pragma unroll
@@ -142,7 +149,7 @@ __global__ void __launch_bounds__(256) gemv_rows_kernel(const GemvParams p) {
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
         const int cc = min(lane * 8 + u * 256, K - 8);
-        const uint4 xv = *reinterpret_cast<const uint4*>(xs + cc);
+        const uint4 xv = ldx(cc);
 #pragma unroll
         for (int r = 0; r < ROWS; ++r) acc[r] += dot8(w[r][u], xv);
     }
@@ -155,7 +162,7 @@ __global__ void __launch_bounds__(256) gemv_rows_kernel(const GemvParams p) {
             for (int u = 0; u < UNROLL; ++u) w[r][u] = ld_stream16(p.W + (size_t)rows[r] * p.ldw + c + u * 256);
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
-            const uint4 xv = *reinterpret_cast<const uint4*>(xs + c + u * 256);
+            const uint4 xv = ldx(c + u * 256);
 #pragma unroll
             for (int r = 0; r < ROWS; ++r) acc[r] += dot8(w[r][u], xv);
         }
@@ -172,7 +179,7 @@ __global__ void __launch_bounds__(256) gemv_rows_kernel(const GemvParams p) {
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
             const int cc = min(c + u * 256, K - 8);
-            const uint4 xv = *reinterpret_cast<const uint4*>(xs + cc);
+            const uint4 xv = ldx(cc);
 #pragma unroll
             for (int r = 0; r < ROWS; ++r) acc[r] += dot8(w[r][u], xv);
         }
@@ -202,12 +209,13 @@ __global__ void __launch_bounds__(256) gemv_rows_kernel(const GemvParams p) {
     }
 }
 
+// Large-K residual GEMV (down_proj). A CTA owns ROWS rows; its 8 warps split K. The activation vector is NOT
+// staged in shared memory: a 16-byte x chunk is loaded once per lane (read-only path, L1-resident after the
+// first touch on an SM) and reused for all ROWS rows, so a CTA starts streaming weights immediately and the
+// 717 CTAs do not each copy 37 KB of x through L2.
 template <int ROWS>
 __global__ void __launch_bounds__(256) gemv_splitk_kernel(const GemvParams p) {
     static_assert(ROWS <= 8, "part[] is sized for <= 8 rows");
-    extern __shared__ __align__(16) uint8_t smem_gemv[];
-    bf16* xs = reinterpret_cast<bf16*>(smem_gemv);
-    __shared__ float red[32];
     __shared__ float part[8][ROWS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row0 = blockIdx.x * ROWS;
@@ -224,14 +232,14 @@ __global__ void __launch_bounds__(256) gemv_splitk_kernel(const GemvParams p) {
                                  : make_uint4(0, 0, 0, 0);
     pdl_wait();
     if (p.finished && *p.finished) return;
-    stage_x<false>(xs, p.x, nullptr, 0.f, K, red);
+    const bf16* __restrict__ xg = p.x;
     float acc[ROWS];
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) acc[r] = 0.f;
     if (full_first) {
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
-            const uint4 xv = *reinterpret_cast<const uint4*>(xs + c + u * 2048);
+            const uint4 xv = __ldg(reinterpret_cast<const uint4*>(xg + c + u * 2048));
 #pragma unroll
             for (int r = 0; r < ROWS; ++r) acc[r] += dot8(w[r][u], xv);
         }
@@ -245,13 +253,13 @@ __global__ void __launch_bounds__(256) gemv_splitk_kernel(const GemvParams p) {
                 w[r][u] = ld_stream16(p.W + (size_t)min(row0 + r, p.N - 1) * p.ldw + c + u * 2048);
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
-            const uint4 xv = *reinterpret_cast<const uint4*>(xs + c + u * 2048);
+            const uint4 xv = __ldg(reinterpret_cast<const uint4*>(xg + c + u * 2048));
 #pragma unroll
             for (int r = 0; r < ROWS; ++r) acc[r] += dot8(w[r][u], xv);
         }
     }
     for (; c < K; c += 2048) {
-        const uint4 xv = *reinterpret_cast<const uint4*>(xs + c);
+        const uint4 xv = __ldg(reinterpret_cast<const uint4*>(xg + c));
 #pragma unroll
         for (int r = 0; r < ROWS; ++r)
             acc[r] += dot8(ld_stream16(p.W + (size_t)min(row0 + r, p.N - 1) * p.ldw + c), xv);
@@ -274,7 +282,6 @@ __global__ void __launch_bounds__(256) gemv_splitk_kernel(const GemvParams p) {
         }
     }
 }
-
 
 template <typename Kern>
 static int set_smem(Kern kern, int bytes) {
@@ -331,10 +338,10 @@ int gemv_residual(const bf16* W, int ldw, const bf16* x, bf16* h_inout, int N, i
     if (K > 8192) {
         static const int cand[] = {4, 5, 6, 8};
         switch (pick_rows_per_cta(N, num_sms, cand, 4)) {
-            case 4: LCC_LAUNCH((gemv_splitk_kernel<4>), (N + 3) / 4, K * 2); break;
-            case 5: LCC_LAUNCH((gemv_splitk_kernel<5>), (N + 4) / 5, K * 2); break;
-            case 6: LCC_LAUNCH((gemv_splitk_kernel<6>), (N + 5) / 6, K * 2); break;
-            default: LCC_LAUNCH((gemv_splitk_kernel<8>), (N + 7) / 8, K * 2); break;
+            case 4: LCC_LAUNCH((gemv_splitk_kernel<4>), (N + 3) / 4, 0); break;
+            case 5: LCC_LAUNCH((gemv_splitk_kernel<5>), (N + 4) / 5, 0); break;
+            case 6: LCC_LAUNCH((gemv_splitk_kernel<6>), (N + 5) / 6, 0); break;
+            default: LCC_LAUNCH((gemv_splitk_kernel<8>), (N + 7) / 8, 0); break;
         }
     } else {
         static const int cand[] = {5, 6, 7, 8, 10, 12, 14, 16};  // warps x rows-per-warp

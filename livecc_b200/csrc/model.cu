@@ -141,8 +141,12 @@ lcc_model* lcc_model_create(lcc_ctx* ctx, const lcc_model_config* cfg, const lcc
     m->layers.assign(w->layers, w->layers + cfg->layers);
     m->w.vit_blocks = m->vit_blocks.data();
     m->w.layers = m->layers.data();
+#ifdef LCC_ENABLE_PDL
     const char* pdl_env = getenv("LIVECC_B200_PDL");
     m->use_pdl = pdl_env && pdl_env[0] == '1';
+#else
+    m->use_pdl = false;  // griddepcontrol is compiled out (see common.cuh)
+#endif
     return m;
 }
 

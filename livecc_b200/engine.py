@@ -291,7 +291,8 @@ class LiveCCB200ForConditionalGeneration:
         self._ev[2].record()
         # ---- decode steps ----
         kv_tiles = (past + S + max_new_tokens + 63) // 64
-        want = max(1, (kv_tiles + 7) // 8)          # >= ~8 KV tiles (512 tokens) per split
+        div = int(os.environ.get("LIVECC_B200_NSPLIT_DIV", "8"))
+        want = max(1, (kv_tiles + div - 1) // div)   # >= ~8 KV tiles (512 tokens) per split
         nsplit = 1
         while nsplit < want and nsplit < self.max_nsplit:  # quantised to powers of two: at most 7 captured graphs
             nsplit *= 2
