@@ -17,8 +17,8 @@ from typing import Optional
 import torch
 
 from .engine import LiveCCB200ForConditionalGeneration, ThresholdLogitsProcessor
-from .livecc_utils import (get_smart_resized_clip, get_smart_resized_video_reader,
-                           prepare_multiturn_multimodal_inputs_for_generation)
+from .livecc_utils import (_read_video_decord_plus, _spatial_resize_video, get_smart_resized_clip,
+                           get_smart_resized_video_reader, prepare_multiturn_multimodal_inputs_for_generation)
 from .processing import StubProcessor
 
 
@@ -178,3 +178,121 @@ class LiveCCDemoInfer:
                 yield (start_timestamp, stop_timestamp), response, light_state
             else:
                 yield (start_timestamp, stop_timestamp), response, state
+
+    @torch.inference_mode()
+    def video_qa(
+        self,
+        message: str,
+        history: list,
+        state: dict,
+        do_sample: bool = False,
+        repetition_penalty: float = 1.05,
+        hf_spaces: bool = False,
+        max_new_tokens: int = 512,
+        **kwargs,
+    ):
+        """REF/demo/infer.py:183-242: multi-turn QA over one video. The whole video enters on the first turn
+        (the reference goes through qwen_vl_utils.process_vision_info -> the 'decord+' reader registered by
+        livecc_utils, i.e. `_read_video_decord_plus` + `_spatial_resize_video`); later turns reuse the KV cache."""
+        video_path = state.get("video_path", None)
+        conversation = []
+        if hf_spaces:
+            for past_message in history:
+                content = [{"type": "text", "text": past_message["content"]}]
+                if video_path:  # only use once
+                    content.insert(0, {"type": "video", "video": video_path})
+                    video_path = None
+                conversation.append({"role": past_message["role"], "content": content})
+        past_ids = state.get("past_ids", None)
+        content = [{"type": "text", "text": message}]
+        if past_ids is None and video_path:  # only use once
+            content.insert(0, {"type": "video", "video": video_path})
+        conversation.append({"role": "user", "content": content})
+        video_inputs = []
+        for msg in conversation:  # process_vision_info equivalent for the video-only path
+            for item in msg["content"]:
+                if item["type"] == "video":
+                    clip, _fps = _read_video_decord_plus({"video": item["video"], "remote_loader": None})
+                    video_inputs.append(_spatial_resize_video(clip))  # float frames, like the reference (video_process_patch.py:106)
+        texts = self.processor.apply_chat_template(conversation, tokenize=False, add_generation_prompt=True)
+        if past_ids is not None:
+            texts = "<|im_end|>\n" + texts[self.system_prompt_offset:]
+        inputs = self.processor(text=texts, images=None, videos=video_inputs or None, return_tensors="pt",
+                                return_attention_mask=False)
+        inputs.to(self.model.device)
+        if past_ids is not None:
+            inputs["input_ids"] = torch.cat([past_ids, inputs.input_ids], dim=1)
+        outputs = self.model.generate(
+            **inputs, past_key_values=state.get("past_key_values", None),
+            return_dict_in_generate=True, do_sample=do_sample,
+            repetition_penalty=repetition_penalty,
+            max_new_tokens=max_new_tokens,
+            pad_token_id=self.model.config.eos_token_id,
+        )
+        state["past_key_values"] = outputs.past_key_values if not hf_spaces else None
+        state["past_ids"] = outputs.sequences[:, :-1] if not hf_spaces else None
+        response = self.processor.decode(outputs.sequences[0, inputs.input_ids.size(1):], skip_special_tokens=True)
+        return response, state
+
+    @torch.inference_mode()
+    def live_cc_once_for_evaluation(
+        self,
+        query: str,
+        video: str,
+        video_start: float = 0,
+        video_end: float = None,
+        remote_loader: callable = None,
+        max_new_tokens: int = 32,
+        repetition_penalty: float = 1.05,
+    ):
+        """REF/demo/infer.py:245-310: offline variant of live_cc (clip read once, same 6+2+2... chunking).
+        Difference from the reference, on purpose: `return_attention_mask=False` like the demo path — the
+        reference passes a new-tokens-only mask next to full-history ids here, which transformers 5.x would
+        mis-slice."""
+        clip, _ = _read_video_decord_plus({"video": video, "video_start": video_start, "video_end": video_end,
+                                           "remote_loader": remote_loader})
+        clip = _spatial_resize_video(clip)
+        interleave_clips = [clip[: self.initial_fps_frames]]
+        clip = clip[self.initial_fps_frames:]
+        if len(clip) > 0:
+            interleave_clips.extend(list(clip.split(self.streaming_fps_frames)))
+        past_key_values = None
+        past_ids = None
+        responses = []
+        start_timestamp = stop_timestamp = 0
+        for i, clip in enumerate(interleave_clips):
+            if i == 0:
+                start_timestamp, stop_timestamp = 0, self.initial_time_interval
+            else:
+                start_timestamp, stop_timestamp = stop_timestamp, stop_timestamp + self.streaming_time_interval
+            message = {
+                "role": "user",
+                "content": [
+                    {"type": "text", "text": f"Time={start_timestamp:.1f}-{stop_timestamp:.1f}s"},
+                    {"type": "video", "video": clip},
+                ],
+            }
+            if not past_key_values:
+                message["content"].append({"type": "text", "text": query})
+            texts = self.processor.apply_chat_template([message], tokenize=False, add_generation_prompt=True)
+            if past_key_values:
+                texts = "<|im_end|>\n" + texts[self.system_prompt_offset:]
+            inputs = self.processor(text=texts, images=None, videos=[clip], return_tensors="pt",
+                                    return_attention_mask=False)
+            inputs.to(self.model.device)
+            if past_key_values:
+                inputs["input_ids"] = torch.cat([past_ids, inputs.input_ids], dim=1)
+            outputs = self.model.generate(
+                **inputs, past_key_values=past_key_values,
+                return_dict_in_generate=True,
+                max_new_tokens=max_new_tokens, repetition_penalty=repetition_penalty,
+                pad_token_id=self.model.config.eos_token_id,
+            )
+            past_key_values = outputs.past_key_values
+            past_ids = outputs.sequences[:, :-1]
+            responses.append([
+                video_start + start_timestamp,
+                video_start + stop_timestamp,
+                self.processor.decode(outputs.sequences[0, inputs.input_ids.size(1):], skip_special_tokens=True),
+            ])
+        return responses

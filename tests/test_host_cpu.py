@@ -63,8 +63,10 @@ class MockModel:
     def generate(self, input_ids=None, pixel_values_videos=None, video_grid_thw=None, past_key_values=None,
                  max_new_tokens=16, **kw):
         cache = past_key_values or MockCache()
-        self.calls.append(dict(L=input_ids.shape[1], past=cache.n, grid=video_grid_thw.tolist(),
-                               rows=pixel_values_videos.shape[0], kw=kw, new=input_ids[0, cache.n:].tolist()))
+        self.calls.append(dict(L=input_ids.shape[1], past=cache.n,
+                               grid=video_grid_thw.tolist() if video_grid_thw is not None else [],
+                               rows=pixel_values_videos.shape[0] if pixel_values_videos is not None else 0, kw=kw,
+                               new=input_ids[0, cache.n:].tolist()))
         gen = torch.tensor([[1234, 1235, self.config.eos_token_id]])
         seq = torch.cat([input_ids, gen], 1)
         cache.n = seq.shape[1] - 1
@@ -109,6 +111,32 @@ def test_live_cc_chunk_schedule_and_state_contract():
     assert "logits_processor" in first["kw"] and first["kw"]["logits_processor"][0].token_id == infer.streaming_eos_token_id
     assert state["past_ids"].shape[1] == state["past_key_values"].get_seq_length()
     assert len(infer.timings) == len(model.calls)
+
+
+def test_video_qa_and_offline_eval_variants():
+    """REF/demo/infer.py:183-242 (video_qa) and :245-310 (live_cc_once_for_evaluation) on the mock model."""
+    from livecc_b200.streaming import LiveCCDemoInfer
+
+    cfg = LiveCCConfig.small()
+    model = MockModel(cfg)
+    infer = LiveCCDemoInfer(model=model, processor=StubProcessor(cfg))
+    state = {"video_path": "synthetic://240x56x84@30?seed=5"}  # 8 s
+    resp, state = infer.video_qa("What happens?", [], state)
+    first = model.calls[-1]
+    assert first["past"] == 0 and first["grid"][0][0] >= 2 and first["kw"]["do_sample"] is False
+    n_video = first["new"].count(cfg.video_token_id)
+    assert n_video == first["rows"] // 4 and "max_new_tokens" not in first["kw"]
+    resp2, state = infer.video_qa("And then?", [], state)
+    second = model.calls[-1]
+    assert second["past"] == first["L"] + 2 and second["new"].count(cfg.video_token_id) == 0  # video only once
+    assert state["past_ids"].shape[1] == state["past_key_values"].get_seq_length()
+
+    model2 = MockModel(cfg)
+    infer2 = LiveCCDemoInfer(model=model2, processor=StubProcessor(cfg))
+    out = infer2.live_cc_once_for_evaluation("Describe.", "synthetic://300x56x84@30?seed=6", video_start=0, video_end=None)
+    frames = [c["grid"][0][0] * 2 for c in model2.calls]
+    assert frames[0] == 6 and all(f == 2 for f in frames[1:]) and len(out) == len(frames)
+    assert out[0][:2] == [0, 3.0] and out[1][:2] == [3.0, 4.0]
 
 
 def test_livecc_utils_surface():
