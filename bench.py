@@ -178,8 +178,7 @@ def run_stream_e2e(infer, path, seconds, max_new):
         lat.append((rec["generate_s"] + rec["preprocess_s"] + rec["ingest_s"]) / rec["frames"])
     v = infer.model.config.vision_config
     for rec in infer.timings[n0:]:
-        n_patches = rec["frames"] // 2 * (infer._last_hw[0] // 14) * (infer._last_hw[1] // 14)
-        h2d += n_patches * v.patch_dim * 4 + 8 * 64
+        h2d += rec["frames"] * 3 * infer._last_hw[0] * infer._last_hw[1] + 8 * 64  # uint8 frames + new ids
         d2h += 8 * (rec["new_tokens"] + 1) + 32
     kv = state["past_key_values"].get_seq_length()
     state["past_key_values"].release()
@@ -310,7 +309,9 @@ def main():
     chunks, path = build_chunks(cfg, args.seconds, args.size, seed=rank)
     chunks_dev = [dict(input_ids=c.input_ids.to(dev), pixel_values_videos=c.pixel_values_videos.to(dev),
                        video_grid_thw=c.video_grid_thw, frames=int(c.video_grid_thw[0, 0]) * 2) for c in chunks]
-    infer = LiveCCDemoInfer(model=eng)
+    from livecc_b200.processing import StubProcessor
+
+    infer = LiveCCDemoInfer(model=eng, processor=StubProcessor(cfg, emit_frames=True))  # uint8 frames, GPU ingest
     infer._last_hw = (args.size, args.size)
 
     def barrier():
@@ -417,7 +418,7 @@ def main():
         line["e2e"] = {"value": tot_e_tok / max_e_sec, "unit": "tokens/s", "frames_per_s": tot_e_frames / max_e_sec,
                        "p50_frame_latency_ms": el[len(el) // 2] * 1e3, "h2d_bytes_per_step": int(e2e["h2d"]),
                        "d2h_bytes_per_step": int(e2e["d2h"]),
-                       "api": "LiveCCDemoInfer.live_cc (host uint8 frames -> host patchify -> pinned H2D -> generate -> D2H ids)"}
+                       "api": "LiveCCDemoInfer.live_cc (host uint8 frames -> H2D -> fused normalize+patchify -> generate -> D2H ids)"}
     # decode-step roofline inside the timed region: every generated token after the first of a chunk is one
     # CUDA-graph replay streaming all decoder weights + the stream's KV
     kv_bytes_tok = 2 * t.num_hidden_layers * t.num_key_value_heads * 128 * 2

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define LCC_ABI_VERSION 4
+#define LCC_ABI_VERSION 5
 #define LCC_PAGE_SIZE 64
 
 typedef struct lcc_ctx lcc_ctx;
@@ -215,6 +215,13 @@ int lcc_model_bind_workspace(lcc_model* m, void* ws, size_t ws_bytes, int max_pa
  * pixel_values f32 [t*h*w, patch_dim] -> out bf16 [t*h*w/merge^2, vit_out]. */
 int lcc_vit_forward(lcc_model* m, const float* pixel_values, int t, int h, int w, void* out,
                     lcc_stream_t stream);
+
+/* Same, starting from the resized uint8 frames [T,3,H,W] on the device (H, W multiples of 28): the
+ * rescale/normalize/patchify of Qwen2VLVideoProcessor._preprocess (video_processing_qwen2_vl.py:240-272) and the
+ * bf16 cast of PatchEmbed (mq2vl.py:309) are fused into one kernel; bit-identical to the f32 path.
+ * mean255/std255: HOST float[3] = fp32(image_mean)*255, fp32(image_std)*255 (image_processing_backends.py:301-304). */
+int lcc_vit_forward_frames(lcc_model* m, const uint8_t* frames, int T, int H, int W, const float* mean255,
+                           const float* std255, void* out, lcc_stream_t stream);
 
 /* Prefill of S new tokens (Qwen2VLModel.forward + lm_head on the last token, mq2vl.py:1230-1300,
  * 828-910, 1437) followed by the first token selection. ids: device int64[S] (the new tokens);

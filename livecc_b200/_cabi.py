@@ -13,7 +13,7 @@ PKG_DIR = Path(__file__).resolve().parent
 LIB_PATH = PKG_DIR / "liblivecc_sm100a.so"
 HEADER_PATH = PKG_DIR.parent / "include" / "livecc_b200.h"
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 PAGE_SIZE = 64
 
 # epilogue codes (LCC_EPI_*)
@@ -328,6 +328,12 @@ class NativeModel:
 
     def vit_forward(self, pixel_values, t, h, w, out):
         self._call("lcc_vit_forward", _ptr(pixel_values), _i(t), _i(h), _i(w), _ptr(out), Context.stream_ptr())
+
+    def vit_forward_frames(self, frames_u8, mean255, std255, out):
+        T, _, H, W = frames_u8.shape
+        m = (C.c_float * 3)(*mean255)
+        sd = (C.c_float * 3)(*std255)
+        self._call("lcc_vit_forward_frames", _ptr(frames_u8), _i(T), _i(H), _i(W), m, sd, _ptr(out), Context.stream_ptr())
 
     def prefill(self, st: StreamState, ids, pos3, S, past, video_embeds, sampling: Sampling):
         self._call("lcc_prefill", C.byref(st), _ptr(ids), _ptr(pos3), _i(S), _i(past), _ptr(video_embeds),

@@ -37,6 +37,51 @@ int cast_f32_bf16(const float* in, bf16* out, int64_t n, int num_sms, cudaStream
 }
 
 // ------------------------------------------------------------------------------------------
+// GPU frame ingest: uint8 frames [T,3,H,W] -> bf16 patch rows [N, 3*2*14*14] in one pass,
+// replacing the host-side rescale/normalize/patchify of Qwen2VLVideoProcessor._preprocess
+// (video_processing_qwen2_vl.py:240-272; fused mean/std: image_processing_backends.py:301-304,327) plus the
+// f32 H2D copy and the bf16 cast (mq2vl.py:309). Bit-identical to cast_bf16(host patchify): the value is
+// bf16( (float(u8) - mean255[c]) / std255[c] ) with IEEE fp32 subtract and divide; odd T repeats the last frame.
+// Row order (t, h/2, w/2, 2, 2), column order (c, tp, 14, 14).
+// ------------------------------------------------------------------------------------------
+__global__ void patchify_u8_kernel(const uint8_t* __restrict__ frames, int T, int H, int W,
+                                   bf16* __restrict__ out, float m0, float m1, float m2, float s0, float s1,
+                                   float s2) {
+    constexpr int P = 14, TP = 2, MS = 2, COLS = 3 * TP * P * P;
+    const int gh = H / P, gw = W / P;
+    const int grid_t = (T + TP - 1) / TP;
+    const int64_t total = (int64_t)grid_t * gh * gw * (COLS / 2);  // two adjacent px per thread
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int col = (int)(idx % (COLS / 2)) * 2;
+    const int row = (int)(idx / (COLS / 2));
+    // row -> (t, hb, wb, hi, wi)
+    const int in_win = row % (MS * MS);
+    const int win = row / (MS * MS);
+    const int wbn = gw / MS, hbn = gh / MS;
+    const int wb = win % wbn, hb = (win / wbn) % hbn, t = win / (wbn * hbn);
+    const int ph = hb * MS + in_win / MS, pw = wb * MS + in_win % MS;
+    // col -> (c, tp, py, px)
+    const int px = col % P, py = (col / P) % P, tp = (col / (P * P)) % TP, c = col / (P * P * TP);
+    const int tf = min(t * TP + tp, T - 1);
+    const uint8_t* src = frames + (((size_t)tf * 3 + c) * H + (size_t)ph * P + py) * W + (size_t)pw * P + px;
+    const float mean = c == 0 ? m0 : (c == 1 ? m1 : m2);
+    const float sd = c == 0 ? s0 : (c == 1 ? s1 : s2);
+    const float a = __fdiv_rn(__fsub_rn((float)src[0], mean), sd);
+    const float b = __fdiv_rn(__fsub_rn((float)src[1], mean), sd);  // px is even, px+1 < 14: same patch row
+    *reinterpret_cast<uint32_t*>(out + (size_t)row * COLS + col) = pack_bf16x2(a, b);
+}
+
+int patchify_u8(const uint8_t* frames, int T, int H, int W, bf16* out, const float* mean255, const float* std255,
+                cudaStream_t s) {
+    if (T <= 0 || H % 28 || W % 28) return -1;
+    const int64_t total = (int64_t)((T + 1) / 2) * (H / 14) * (W / 14) * (1176 / 2);
+    patchify_u8_kernel<<<(int)((total + 255) / 256), 256, 0, s>>>(frames, T, H, W, out, mean255[0], mean255[1],
+                                                                  mean255[2], std255[0], std255[1], std255[2]);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
 // LayerNorm over rows (nn.LayerNorm eps=1e-6, mq2vl.py:464-465,317): fp32 two-pass statistics,
 // y = bf16((x - mean) * rstd * w + b). One warp per row, dim % 8 == 0.
 // ------------------------------------------------------------------------------------------

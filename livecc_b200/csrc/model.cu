@@ -166,8 +166,10 @@ size_t lcc_ws_offset(const lcc_model* m, int which) {
     return 0;
 }
 
-int lcc_vit_forward(lcc_model* m, const float* pixel_values, int t, int h, int w, void* out,
-                    lcc_stream_t stream) {
+// Shared body of the two ViT entry points: `pixel_values` (f32 patch rows from the HF processor) or
+// `frames` (uint8 [T,3,H,W] on the device: fused normalize + patchify, no f32 round trip).
+static int vit_forward_impl(lcc_model* m, const float* pixel_values, const uint8_t* frames, int T_frames, int t,
+                            int h, int w, const float* mean255, const float* std255, void* out, lcc_stream_t stream) {
     if (!m) return -1;
     const lcc_model_config& c = m->cfg;
     cudaStream_t s = (cudaStream_t)stream;
@@ -182,7 +184,12 @@ int lcc_vit_forward(lcc_model* m, const float* pixel_values, int t, int h, int w
     int* vcu = (int*)(ws + L.vcu);
     const int dim = c.vit_dim, hd = dim / c.vit_heads;
 
-    STEP(lcc::cast_f32_bf16(pixel_values, vx, (int64_t)N * c.patch_dim, m->ctx->num_sms, s), "vit cast");
+    if (frames) {
+        if (c.patch_dim != 1176) LCC_FAIL(m->ctx, -4, "frame ingest is specialised for 3x2x14x14 patches");
+        STEP(lcc::patchify_u8(frames, T_frames, h * 14, w * 14, vx, mean255, std255, s), "vit frame ingest");
+    } else {
+        STEP(lcc::cast_f32_bf16(pixel_values, vx, (int64_t)N * c.patch_dim, m->ctx->num_sms, s), "vit cast");
+    }
     STEP(gemm(m, vx, c.patch_dim, m->w.patch_w, c.patch_dim, vh, dim, N, dim, c.patch_dim, nullptr, nullptr, 0,
               lcc::EPI_NONE, s), "vit patch_embed");
     STEP(lcc::vit_rope_table(vcos, vsin, t, h, w, c.merge, hd, m->w.vit_inv_freq, s), "vit rope table");
@@ -205,6 +212,19 @@ int lcc_vit_forward(lcc_model* m, const float* pixel_values, int t, int h, int w
     STEP(gemm(m, vmlp, md, m->w.merger_fc2_w, md, out, c.vit_out, NM, c.vit_out, md, m->w.merger_fc2_b, nullptr, 0, lcc::EPI_BIAS, s), "merger fc2");
     LCC_CHECK_LAUNCH(m->ctx, "lcc_vit_forward");
     return 0;
+}
+
+int lcc_vit_forward(lcc_model* m, const float* pixel_values, int t, int h, int w, void* out,
+                    lcc_stream_t stream) {
+    return vit_forward_impl(m, pixel_values, nullptr, 0, t, h, w, nullptr, nullptr, out, stream);
+}
+
+int lcc_vit_forward_frames(lcc_model* m, const uint8_t* frames, int T, int H, int W, const float* mean255,
+                           const float* std255, void* out, lcc_stream_t stream) {
+    if (!m) return -1;
+    if (!frames || T <= 0 || H % 28 || W % 28 || !mean255 || !std255)
+        LCC_FAIL(m->ctx, -2, "lcc_vit_forward_frames: frames must be uint8 [T,3,H,W] with H,W multiples of 28");
+    return vit_forward_impl(m, nullptr, frames, T, (T + 1) / 2, H / 14, W / 14, mean255, std255, out, stream);
 }
 
 int lcc_prefill(lcc_model* m, const lcc_stream_state* st, const int64_t* ids, const int32_t* pos3, int S,

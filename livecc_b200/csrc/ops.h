@@ -11,6 +11,8 @@ typedef __nv_bfloat16 bf16;
 
 // elementwise.cu
 int cast_f32_bf16(const float* in, bf16* out, int64_t n, int num_sms, cudaStream_t s);
+int patchify_u8(const uint8_t* frames, int T, int H, int W, bf16* out, const float* mean255, const float* std255,
+                cudaStream_t s);
 int layernorm(const bf16* x, int ldx, const bf16* w, const bf16* b, bf16* y, int ldy, int rows, int dim,
               float eps, cudaStream_t s);
 int rmsnorm(const bf16* x, int ldx, const bf16* w, bf16* y, int ldy, int rows, int dim, float eps,

@@ -214,13 +214,36 @@ class LiveCCB200ForConditionalGeneration:
         return out
 
     @torch.inference_mode()
+    def get_video_features_from_frames(self, frames: torch.Tensor) -> torch.Tensor:
+        """GPU frame ingest: uint8 [T,3,H,W] (H, W multiples of 28) -> [n_tok, H] bf16; the processor's
+        rescale/normalize/patchify and the bf16 cast run fused in front of the patch-embed GEMM. Bit-identical to
+        get_video_features(patchify_video(frames))."""
+        from .processing import OPENAI_CLIP_MEAN, OPENAI_CLIP_STD
+
+        if frames.dtype != torch.uint8 or frames.dim() != 4 or frames.shape[1] != 3:
+            raise ValueError("video_frames must be a uint8 tensor [T,3,H,W]")
+        T, _, H, W = frames.shape
+        if H % 28 or W % 28:
+            raise ValueError("frame size must be a multiple of 28 (apply smart_resize first)")
+        v = self.config.vision_config
+        fr = frames.to(device=self.device, non_blocking=True).contiguous()
+        t, h, w = (T + 1) // 2, H // 14, W // 14
+        self._ensure_workspace(t * h * w, 0)
+        # the processor's fused constants (image_processing_backends.py:301-304): fp32(mean) * (1 / (1/255))
+        mean255 = (torch.tensor(OPENAI_CLIP_MEAN) * (1.0 / (1 / 255))).tolist()
+        std255 = (torch.tensor(OPENAI_CLIP_STD) * (1.0 / (1 / 255))).tolist()
+        out = torch.empty((t * h * w // v.spatial_merge_size ** 2, v.hidden_size), dtype=torch.bfloat16, device=self.device)
+        self._native.vit_forward_frames(fr, mean255, std255, out)
+        return out
+
+    @torch.inference_mode()
     def generate(self, input_ids: torch.Tensor = None, pixel_values_videos: Optional[torch.Tensor] = None,
                  video_grid_thw: Optional[torch.Tensor] = None, past_key_values: Optional[PagedKVCache] = None,
                  return_dict_in_generate: bool = True, do_sample: Optional[bool] = None,
                  repetition_penalty: float = 1.0, logits_processor=None, max_new_tokens: int = 16,
                  pad_token_id: Optional[int] = None, attention_mask=None, mm_token_type_ids=None,
                  pixel_values=None, image_grid_thw=None, output_logits: bool = False,
-                 _forced_ids: Optional[List[int]] = None, **unsupported):
+                 video_frames: Optional[torch.Tensor] = None, _forced_ids: Optional[List[int]] = None, **unsupported):
         """The subset of GenerationMixin.generate that LiveCC's streaming loop uses (see module docstring).
         input_ids: [1, L] int64 = full id history (REF/demo/infer.py:159-160); the cache decides how many
         trailing ids are new (gen/utils.py:3747-3758). Greedy decoding (do_sample=True is accepted only with
@@ -248,6 +271,9 @@ class LiveCCB200ForConditionalGeneration:
         if S <= 0:
             raise ValueError(f"input_ids has {L} ids but the cache already holds {past}")
 
+        if video_frames is not None and video_grid_thw is None:
+            _T, _, _H, _W = video_frames.shape
+            video_grid_thw = torch.tensor([[(_T + 1) // 2, _H // 14, _W // 14]])
         # ---- positions (host integers; first turn only needs the ids on the host) ----
         if past == 0 or cache.rope_delta is None:
             ids_host = ids_dev[0].tolist()
@@ -264,11 +290,19 @@ class LiveCCB200ForConditionalGeneration:
         self._ev[0].record()
         video_embeds = None
         n_video_expected = -1
+        if pixel_values_videos is not None and video_frames is not None:
+            raise ValueError("pass either pixel_values_videos (HF processor rows) or video_frames (uint8 frames)")
         if pixel_values_videos is not None:
             if video_grid_thw is None:
                 raise ValueError("video_grid_thw is required with pixel_values_videos")
             video_embeds = self.get_video_features(pixel_values_videos, video_grid_thw)
             n_video_expected = video_embeds.shape[0]
+        elif video_frames is not None:
+            video_embeds = self.get_video_features_from_frames(video_frames)
+            n_video_expected = video_embeds.shape[0]
+            if video_grid_thw is None:
+                T, _, H, W = video_frames.shape
+                video_grid_thw = torch.tensor([[(T + 1) // 2, H // 14, W // 14]])
 
         self._ev[1].record()
         # ---- capacity, buffers, device scalars ----

@@ -142,8 +142,12 @@ class StubProcessor:
 
     DEFAULT_SYSTEM = "You are a helpful assistant."
 
-    def __init__(self, config=None, merge_size: int = 2, patch_size: int = 14, temporal_patch_size: int = 2):
-        """`config`: optional LiveCCConfig supplying (possibly relocated) special ids and vocab size."""
+    def __init__(self, config=None, merge_size: int = 2, patch_size: int = 14, temporal_patch_size: int = 2,
+                 emit_frames: bool = False):
+        """`config`: optional LiveCCConfig supplying (possibly relocated) special ids and vocab size.
+        `emit_frames=True` (GPU frame ingest): uint8 clips are passed through as `video_frames`
+        (4x fewer H2D bytes than f32 patch rows) and the engine normalises + patchifies them on the device."""
+        self.emit_frames = emit_frames
         if config is not None:
             self.tokenizer = StubTokenizer(config.special_token_ids(), config.newline_token_id,
                                            config.text_config.vocab_size)
@@ -195,13 +199,23 @@ class StubProcessor:
             text = text[0]
         data = {}
         if videos:
-            flats, grids = [], []
-            for clip in videos:
-                f, g = patchify_video(clip, self.patch_size, self.temporal_patch_size, self.merge_size)
-                flats.append(f)
-                grids.append(g)
-            data["pixel_values_videos"] = torch.cat(flats, dim=0)
-            data["video_grid_thw"] = torch.cat(grids, dim=0)
+            use_frames = self.emit_frames and len(videos) == 1 and videos[0].dtype == torch.uint8
+            if use_frames:
+                clip = videos[0]
+                T, _, H, W = clip.shape
+                if H % (self.patch_size * self.merge_size) or W % (self.patch_size * self.merge_size):
+                    raise ValueError("frame size must be a multiple of 28 (apply smart_resize first)")
+                data["video_frames"] = clip.contiguous()
+                data["video_grid_thw"] = torch.tensor([[(T + self.temporal_patch_size - 1) // self.temporal_patch_size,
+                                                        H // self.patch_size, W // self.patch_size]], dtype=torch.int64)
+            else:
+                flats, grids = [], []
+                for clip in videos:
+                    f, g = patchify_video(clip, self.patch_size, self.temporal_patch_size, self.merge_size)
+                    flats.append(f)
+                    grids.append(g)
+                data["pixel_values_videos"] = torch.cat(flats, dim=0)
+                data["video_grid_thw"] = torch.cat(grids, dim=0)
             # processing_qwen2_vl.py:111-119: one <|video_pad|> per merged token
             idx = 0
             merge_len = self.merge_size ** 2

@@ -192,3 +192,28 @@ def test_long_cache_split_kv_prefill(small):
     worst = max((a.float().flatten() - b.float().flatten()).abs().max().item() for a, b in zip(logits_o, out.logits))
     assert worst < LOGIT_ATOL, worst
     assert out.sequences[0, ids_o.shape[1]:].tolist() == gen
+
+
+def test_gpu_frame_ingest_is_bit_identical(small):
+    """§8(f) rank 1: uint8 frames -> fused normalize+patchify kernel == host patchify + f32 rows, bit for bit
+    (video features and therefore logits), including an odd frame count (last frame repeated)."""
+    cfg, sd, eng, rs = small
+    from livecc_b200.processing import patchify_video
+
+    for T, hw in [(2, (112, 112)), (6, (56, 84)), (3, (84, 56))]:
+        g = torch.Generator().manual_seed(T)
+        clip = torch.randint(0, 256, (T, 3, hw[0], hw[1]), generator=g, dtype=torch.uint8)
+        px, grid = patchify_video(clip)
+        a = eng.get_video_features(px.to(DEV), grid)
+        b = eng.get_video_features_from_frames(clip.to(DEV))
+        torch.cuda.synchronize()
+        assert torch.equal(a, b)
+    proc_f = StubProcessor(cfg, emit_frames=True)
+    inp = make_turn_inputs(StubProcessor(cfg), 0, 2, (112, 112), 5).to(DEV)
+    inp_f = make_turn_inputs(proc_f, 0, 2, (112, 112), 5).to(DEV)
+    assert "video_frames" in inp_f and "pixel_values_videos" not in inp_f
+    assert torch.equal(inp.input_ids, inp_f.input_ids) and torch.equal(inp.video_grid_thw, inp_f.video_grid_thw)
+    o1 = eng.generate(**inp, max_new_tokens=4, repetition_penalty=1.05, output_logits=True)
+    o2 = eng.generate(**inp_f, max_new_tokens=4, repetition_penalty=1.05, output_logits=True)
+    assert torch.equal(o1.sequences, o2.sequences)
+    assert all(torch.equal(x, y) for x, y in zip(o1.logits, o2.logits))

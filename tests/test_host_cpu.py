@@ -139,6 +139,20 @@ def test_video_qa_and_offline_eval_variants():
     assert out[0][:2] == [0, 3.0] and out[1][:2] == [3.0, 4.0]
 
 
+def test_processor_frame_passthrough():
+    cfg = LiveCCConfig.small()
+    clip = torch.randint(0, 256, (3, 3, 56, 84), dtype=torch.uint8)
+    text = StubProcessor(cfg).apply_chat_template([{"role": "user", "content": [{"type": "video", "video": clip}]}],
+                                                  tokenize=False, add_generation_prompt=True)
+    a = StubProcessor(cfg)(text=text, videos=[clip], return_attention_mask=False)
+    b = StubProcessor(cfg, emit_frames=True)(text=text, videos=[clip], return_attention_mask=False)
+    assert torch.equal(a.input_ids, b.input_ids) and torch.equal(a.video_grid_thw, b.video_grid_thw)
+    assert b.video_frames.dtype == torch.uint8 and b.video_frames.shape == (3, 3, 56, 84) and "pixel_values_videos" not in b
+    # float frames (video_qa path) fall back to host patch rows
+    c = StubProcessor(cfg, emit_frames=True)(text=text, videos=[clip.float()], return_attention_mask=False)
+    assert "pixel_values_videos" in c and torch.equal(c.pixel_values_videos, a.pixel_values_videos)
+
+
 def test_livecc_utils_surface():
     import livecc_b200.livecc_utils as U
 
