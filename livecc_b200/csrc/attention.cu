@@ -450,6 +450,16 @@ struct DecodeAttnParams {
     int* counters;      // [Hkv] arrival counters, zero between launches (last CTA of a group merges the splits)
     bf16* out;          // [Hq * 128]
     float scale_log2;
+    int* done_groups;   // optional: incremented once per KV group when its merged output is in `out`
+};
+
+// o_proj role of the fused attention + o_proj kernel (see attn_oproj_kernel)
+struct OprojParams {
+    const bf16* W;      // [N, K] o_proj weight
+    int ldw, N, K;
+    bf16* h;            // residual stream, updated in place
+    int* sync;          // [0] = KV groups done (producer flag), [1] = o_proj CTAs finished (for the reset)
+    int n_cta;          // number of o_proj CTAs
 };
 
 __device__ __forceinline__ void rope1d_row(const bf16* src, bf16* dst, int lane_dim /*0..63*/, float pos,
@@ -462,16 +472,15 @@ __device__ __forceinline__ void rope1d_row(const bf16* src, bf16* dst, int lane_
     dst[lane_dim + 64] = f2bf(rbf(rbf(x2 * c) + rbf(x1 * s)));
 }
 
-__global__ void __launch_bounds__(128) attn_decode_kernel(const DecodeAttnParams p) {
+__device__ __forceinline__ void attn_decode_role(const DecodeAttnParams& p, const int g, const int split,
+                                                 uint8_t* smem_attn) {
     constexpr int D = 128, LDS = D + 8, BN = 64;
     pdl_wait();  // qkv of this token comes from the previous kernel
     if (p.finished && *p.finished) return;
-    extern __shared__ __align__(16) uint8_t smem_attn[];
     bf16* sq = reinterpret_cast<bf16*>(smem_attn);  // [16][LDS]
     bf16* sk = sq + 16 * LDS;                        // [2][64][LDS]
     bf16* sv = sk + 2 * BN * LDS;                    // [2][64][LDS]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int g = blockIdx.x, split = blockIdx.y;
     const int G = p.Hq / p.Hkv;
     const int kv_old = *p.kv_len;
     const int T = kv_old + 1;
@@ -648,6 +657,127 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const DecodeAttnParams
         o.y = pack_bf16x2(acc.z * inv, acc.w * inv);
         *reinterpret_cast<uint2*>(p.out + (size_t)(g * G + r) * D + lane * 4) = o;
     }
+    if (p.done_groups) {  // publish this group's slice of `out` to the o_proj CTAs of the fused kernel
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) atomicAdd(p.done_groups, 1);
+    }
+}
+
+__global__ void __launch_bounds__(128) attn_decode_kernel(const DecodeAttnParams p) {
+    extern __shared__ __align__(16) uint8_t smem_attn[];
+    attn_decode_role(p, blockIdx.x, blockIdx.y, smem_attn);
+}
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused decode attention + o_proj (+ residual). One launch, two CTA roles:
+//   CTAs [0, Hkv*nsplit)        : attention (as above); the last CTA of each KV group bumps sync[0]
+//   CTAs [Hkv*nsplit, +n_cta)   : o_proj rows. They are resident from the start, issue the first 16
+//                                 weight loads per lane, then wait (bounded spin) until sync[0] == Hkv,
+//                                 stage the attention output and finish their dot products.
+// This removes one kernel boundary per layer and hides o_proj's launch + first-load latency behind the
+// attention. Attention CTAs have the lower block indices, so they are always dispatched first and never
+// wait on anything: the o_proj CTAs cannot starve them.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float dot8_attn(const uint4& w, const uint4& x) {
+    const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+    const uint32_t xw[4] = {x.x, x.y, x.z, x.w};
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float2 a = unpack_bf16x2(ww[j]), b = unpack_bf16x2(xw[j]);
+        acc = fmaf(a.x, b.x, acc);
+        acc = fmaf(a.y, b.y, acc);
+    }
+    return acc;
+}
+
+__device__ __forceinline__ void oproj_role(const DecodeAttnParams& p, const OprojParams& o, const int cta,
+                                           uint8_t* smem) {
+    constexpr int ROWS = 4, UNROLL = 4;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row0 = cta * 16 + warp * ROWS;
+    const int K = o.K;
+    int rows[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) rows[r] = min(row0 + r, o.N - 1);
+    uint4 w[ROWS][UNROLL];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const int cc = lane * 8 + u * 256;
+            w[r][u] = (cc < K) ? ld_stream16(o.W + (size_t)rows[r] * o.ldw + cc) : make_uint4(0, 0, 0, 0);
+        }
+    if (p.finished && *p.finished) return;
+    // ---- wait for the merged attention output (bounded: a lost signal degrades the result, never hangs) ----
+    if (threadIdx.x == 0) {
+        int spins = 0;
+        while (ld_acquire_gpu(o.sync) < p.Hkv && ++spins < (1 << 20)) __nanosleep(400);
+    }
+    __syncthreads();
+    bf16* xs = reinterpret_cast<bf16*>(smem);
+    for (int c = threadIdx.x * 8; c < K; c += blockDim.x * 8)
+        *reinterpret_cast<uint4*>(xs + c) = __ldcg(reinterpret_cast<const uint4*>(p.out + c));
+    __syncthreads();
+    float acc[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) acc[r] = 0.f;
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+        const int cc = min(lane * 8 + u * 256, K - 8);
+        const uint4 xv = *reinterpret_cast<const uint4*>(xs + cc);
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) acc[r] += dot8_attn(w[r][u], xv);
+    }
+    for (int c = lane * 8 + UNROLL * 256; (c - lane * 8) < K; c += UNROLL * 256) {
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const int cc = c + u * 256;
+                w[r][u] = (cc < K) ? ld_stream16(o.W + (size_t)rows[r] * o.ldw + cc) : make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const int cc = min(c + u * 256, K - 8);
+            const uint4 xv = *reinterpret_cast<const uint4*>(xs + cc);
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) acc[r] += dot8_attn(w[r][u], xv);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) acc[r] = warp_sum(acc[r]);
+    if (lane == 0) {
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+            const int n = row0 + r;
+            if (n < o.N) o.h[n] = f2bf(rbf(acc[r]) + bf2f(o.h[n]));  // o_proj + residual (mq2vl.py:593,645)
+        }
+    }
+    // ---- the last o_proj CTA re-arms the flags for the next launch ----
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int c = atomicAdd(o.sync + 1, 1);
+        if (c == o.n_cta - 1) {
+            o.sync[0] = 0;
+            o.sync[1] = 0;
+            __threadfence();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) attn_oproj_kernel(const DecodeAttnParams p, const OprojParams o) {
+    extern __shared__ __align__(16) uint8_t smem_attn[];
+    const int n_attn = p.Hkv * p.nsplit;
+    if ((int)blockIdx.x < n_attn) attn_decode_role(p, blockIdx.x % p.Hkv, blockIdx.x / p.Hkv, smem_attn);
+    else oproj_role(p, o, blockIdx.x - n_attn, smem_attn);
 }
 
 int attn_decode(bf16* qkv, bf16* kc, bf16* vc, const int* page_table, int page_size, const int* kv_len,
@@ -667,6 +797,32 @@ int attn_decode(bf16* qkv, bf16* kc, bf16* vc, const int* page_table, int page_s
     p.part_o = part_o; p.part_ml = part_ml; p.counters = counters; p.out = out;
     p.scale_log2 = 1.4426950408889634f / sqrtf(128.f);
     if (launch_kernel(attn_decode_kernel, dim3(Hkv, nsplit), dim3(128), (size_t)smem, s, pdl, p) != cudaSuccess) return -3;
+    return 0;
+}
+
+// Fused attention + o_proj launch (see attn_oproj_kernel). sync: device int[2], zero-initialised once.
+int attn_oproj_decode(bf16* qkv, bf16* kc, bf16* vc, const int* page_table, int page_size, const int* kv_len,
+                      const int* rope_pos, const int* finished, const float* inv_freq, int Hq, int Hkv, int nsplit,
+                      float* part_o, float* part_ml, int* counters, bf16* attn_out, const bf16* o_w, int o_ldw,
+                      int o_N, bf16* h, int* sync, cudaStream_t s) {
+    if (page_size != 64 || Hq % Hkv || Hq / Hkv > 8) return -1;
+    constexpr int smem = (16 + 4 * 64) * 136 * 2;
+    if (Hq * 128 * 2 > smem) return -4;
+    static bool set = false;
+    if (!set) {
+        if (cudaFuncSetAttribute(attn_oproj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+            return -2;
+        set = true;
+    }
+    DecodeAttnParams p{};
+    p.qkv = qkv; p.kc = kc; p.vc = vc; p.page_table = page_table; p.kv_len = kv_len; p.rope_pos = rope_pos;
+    p.finished = finished; p.inv_freq = inv_freq; p.Hq = Hq; p.Hkv = Hkv; p.nsplit = nsplit;
+    p.part_o = part_o; p.part_ml = part_ml; p.counters = counters; p.out = attn_out;
+    p.scale_log2 = 1.4426950408889634f / sqrtf(128.f);
+    p.done_groups = sync;
+    OprojParams o{};
+    o.W = o_w; o.ldw = o_ldw; o.N = o_N; o.K = Hq * 128; o.h = h; o.sync = sync; o.n_cta = (o_N + 15) / 16;
+    attn_oproj_kernel<<<Hkv * nsplit + o.n_cta, 128, smem, s>>>(p, o);
     return 0;
 }
 

@@ -13,6 +13,8 @@
 //   gemv_splitk_kernel: large K (down_proj, K = 18944). A CTA owns ROWS rows; its 8 warps split K.
 // (A persistent one-CTA-per-SM variant was measured slower — 3.87 vs 3.29 ms/step — because it gives up the
 //  thread-level parallelism that hides the load->use latency; see DESIGN.md.)
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "launch.h"
 #include "ops.h"
@@ -213,14 +215,13 @@ __global__ void __launch_bounds__(256) gemv_rows_kernel(const GemvParams p) {
 // staged in shared memory: a 16-byte x chunk is loaded once per lane (read-only path, L1-resident after the
 // first touch on an SM) and reused for all ROWS rows, so a CTA starts streaming weights immediately and the
 // 717 CTAs do not each copy 37 KB of x through L2.
-template <int ROWS>
+template <int ROWS, int UNROLL>
 __global__ void __launch_bounds__(256) gemv_splitk_kernel(const GemvParams p) {
     static_assert(ROWS <= 8, "part[] is sized for <= 8 rows");
     __shared__ float part[8][ROWS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row0 = blockIdx.x * ROWS;
     const int K = p.K;
-    constexpr int UNROLL = 2;
     int c = (warp * 32 + lane) * 8;
     uint4 w[ROWS][UNROLL];
     const bool full_first = (c + (UNROLL - 1) * 2048) < K;
@@ -302,22 +303,6 @@ static int check_common(const GemvParams& p) {
     } while (0)
 #define LCC_LAUNCH(kern, grid, smem) LCC_LAUNCH_B(kern, grid, 256, smem)
 
-// Rows per CTA for a one-wave grid: all CTAs of these small kernels are resident at once, so the SM that
-// receives ceil(ctas/num_sms) CTAs finishes last. Pick the candidate with the best (max load / mean load);
-// ties go to the larger CTA (fewer copies of x staged).
-static int pick_rows_per_cta(int N, int num_sms, const int* cand, int ncand) {
-    int best = cand[0];
-    double best_ratio = 1e9;
-    for (int i = 0; i < ncand; ++i) {
-        const int r = cand[i];
-        const int ctas = (N + r - 1) / r;
-        const double mean = (double)ctas / num_sms;
-        const double ratio = (double)((ctas + num_sms - 1) / num_sms) / mean;
-        if (ratio < best_ratio - 1e-9 || (ratio < best_ratio + 1e-9 && r > best)) { best_ratio = ratio; best = r; }
-    }
-    return best;
-}
-
 // qkv = W_qkv * rmsnorm(h) + b          (mq2vl.py:631, 559-565)
 int gemv_norm_bias(const bf16* W, int ldw, const bf16* x, const bf16* norm_w, float eps, const bf16* bias,
                    bf16* out, int N, int K, const int* finished, const void* pf_ptr, size_t pf_bytes, int num_sms, bool pdl,
@@ -325,7 +310,17 @@ int gemv_norm_bias(const bf16* W, int ldw, const bf16* x, const bf16* norm_w, fl
     GemvParams p{}; p.W = W; p.ldw = ldw; p.x = x; p.norm_w = norm_w; p.eps = eps; p.N = N; p.K = K;
     p.bias = bias; p.out = out; p.finished = finished; p.pf_ptr = (const uint8_t*)pf_ptr; p.pf_bytes = (unsigned)pf_bytes;
     if (int r = check_common(p)) return r;
-    LCC_LAUNCH((gemv_rows_kernel<2, true, GV_BIAS, 8>), (N + 15) / 16, K * 2);
+    // measured on B200 (tools/bench_kernel.py sweep): 2 rows/warp x 4 loads x 4 warps = 12.8 us at N=4608,K=3584;
+    // every shape tried lands in 12.8-17 us: the kernel is bound by launch + first-load + epilogue latency
+    int rpw = 2, unroll = 4, warps = 4;  // tuning hooks: rows per warp, loads in flight per row, warps per CTA
+    if (const char* e = getenv("LIVECC_SMALL_RPW")) rpw = atoi(e);
+    if (const char* e = getenv("LIVECC_SMALL_UNROLL")) unroll = atoi(e);
+    if (const char* e = getenv("LIVECC_SMALL_WARPS")) warps = atoi(e);
+    const int rows_cta = rpw * warps;
+    if (rpw == 1 && unroll == 4) LCC_LAUNCH_B((gemv_rows_kernel<1, true, GV_BIAS, 4>), (N + rows_cta - 1) / rows_cta, warps * 32, K * 2);
+    else if (rpw == 1) LCC_LAUNCH_B((gemv_rows_kernel<1, true, GV_BIAS, 8>), (N + rows_cta - 1) / rows_cta, warps * 32, K * 2);
+    else if (unroll == 4) LCC_LAUNCH_B((gemv_rows_kernel<2, true, GV_BIAS, 4>), (N + rows_cta - 1) / rows_cta, warps * 32, K * 2);
+    else LCC_LAUNCH_B((gemv_rows_kernel<2, true, GV_BIAS, 8>), (N + rows_cta - 1) / rows_cta, warps * 32, K * 2);
     return 0;
 }
 
@@ -336,18 +331,23 @@ int gemv_residual(const bf16* W, int ldw, const bf16* x, bf16* h_inout, int N, i
     p.pf_ptr = (const uint8_t*)pf_ptr; p.pf_bytes = (unsigned)pf_bytes;
     if (int r = check_common(p)) return r;
     if (K > 8192) {
-        static const int cand[] = {4, 5, 6, 8};
-        switch (pick_rows_per_cta(N, num_sms, cand, 4)) {
-            case 4: LCC_LAUNCH((gemv_splitk_kernel<4>), (N + 3) / 4, 0); break;
-            case 5: LCC_LAUNCH((gemv_splitk_kernel<5>), (N + 4) / 5, 0); break;
-            case 6: LCC_LAUNCH((gemv_splitk_kernel<6>), (N + 5) / 6, 0); break;
-            default: LCC_LAUNCH((gemv_splitk_kernel<8>), (N + 7) / 8, 0); break;
-        }
+        // 4 rows per CTA measured best on B200 (25.9 us vs 26.7-27.1 for 5/6/8 rows at N=3584, K=18944)
+        int unroll = 2;
+        if (const char* e = getenv("LIVECC_SPLITK_UNROLL")) unroll = atoi(e);  // tuning hook
+        if (unroll == 4) LCC_LAUNCH((gemv_splitk_kernel<4, 4>), (N + 3) / 4, 0);
+        else if (unroll == 3) LCC_LAUNCH((gemv_splitk_kernel<4, 3>), (N + 3) / 4, 0);
+        else LCC_LAUNCH((gemv_splitk_kernel<4, 2>), (N + 3) / 4, 0);
     } else {
-        static const int cand[] = {5, 6, 7, 8, 10, 12, 14, 16};  // warps x rows-per-warp
-        const int r = pick_rows_per_cta(N, num_sms, cand, 8);
-        if (r <= 8) LCC_LAUNCH_B((gemv_rows_kernel<1, false, GV_RESIDUAL, 8>), (N + r - 1) / r, r * 32, K * 2);
-        else LCC_LAUNCH_B((gemv_rows_kernel<2, false, GV_RESIDUAL, 8>), (N + r - 1) / r, (r / 2) * 32, K * 2);
+        int rpw = 0, unroll = 8, warps = 8;
+        if (const char* e = getenv("LIVECC_SMALL_RPW")) rpw = atoi(e);
+        if (const char* e = getenv("LIVECC_SMALL_UNROLL")) unroll = atoi(e);
+        if (const char* e = getenv("LIVECC_SMALL_WARPS")) warps = atoi(e);
+        if (rpw == 0) { rpw = 1; unroll = 8; warps = 8; }  // measured best (11.1 us at N=K=3584; sweep range 11-15 us)
+        const int rows_cta = rpw * warps;
+        if (rpw == 1 && unroll == 4) LCC_LAUNCH_B((gemv_rows_kernel<1, false, GV_RESIDUAL, 4>), (N + rows_cta - 1) / rows_cta, warps * 32, K * 2);
+        else if (rpw == 1) LCC_LAUNCH_B((gemv_rows_kernel<1, false, GV_RESIDUAL, 8>), (N + rows_cta - 1) / rows_cta, warps * 32, K * 2);
+        else if (unroll == 4) LCC_LAUNCH_B((gemv_rows_kernel<2, false, GV_RESIDUAL, 4>), (N + rows_cta - 1) / rows_cta, warps * 32, K * 2);
+        else LCC_LAUNCH_B((gemv_rows_kernel<2, false, GV_RESIDUAL, 8>), (N + rows_cta - 1) / rows_cta, warps * 32, K * 2);
     }
     return 0;
 }

@@ -24,6 +24,7 @@ struct lcc_model {
     uint8_t* ws = nullptr;
     size_t ws_bytes = 0;
     int cap_patches = 0, cap_tokens = 0;
+    bool fuse_attn_oproj = false;  // LIVECC_B200_FUSE=1: one launch for decode attention + o_proj (flag-synchronised roles)
     bool use_pdl = false;  // programmatic dependent launch between the decode-step kernels (LIVECC_B200_PDL=1 enables)
 };
 
@@ -141,6 +142,8 @@ lcc_model* lcc_model_create(lcc_ctx* ctx, const lcc_model_config* cfg, const lcc
     m->layers.assign(w->layers, w->layers + cfg->layers);
     m->w.vit_blocks = m->vit_blocks.data();
     m->w.layers = m->layers.data();
+    const char* fuse_env = getenv("LIVECC_B200_FUSE");
+    m->fuse_attn_oproj = fuse_env && fuse_env[0] == '1';
 #ifdef LCC_ENABLE_PDL
     const char* pdl_env = getenv("LIVECC_B200_PDL");
     m->use_pdl = pdl_env && pdl_env[0] == '1';
@@ -297,11 +300,18 @@ int lcc_decode_steps(lcc_model* m, const lcc_stream_state* st, int n_steps, int 
             const size_t next_qkv_bytes = (i + 1 < c.layers) ? qkv_bytes : kPf;
             STEP(lcc::gemv_norm_bias((const bf16*)lw.qkv_w, H, h, (const bf16*)lw.ln1_w, c.rms_eps, (const bf16*)lw.qkv_b,
                                      qkv, qkv_dim, H, fin, lw.o_w, cap(o_bytes), m->ctx->num_sms, pdl, s), "decode qkv");
-            STEP(lcc::attn_decode(qkv, kc, vc, st->page_table, LCC_PAGE_SIZE, st->scalars + LCC_SC_KV_LEN,
-                                  st->scalars + LCC_SC_ROPE_POS, fin, m->w.text_inv_freq, Hq, Hkv, nsplit, part_o,
-                                  part_ml, attn_cnt, attn, pdl, s), "decode attention");
-            STEP(lcc::gemv_residual((const bf16*)lw.o_w, Hq * 128, attn, h, H, Hq * 128, fin, lw.gate_up_w, cap(gu_bytes),
-                                    m->ctx->num_sms, pdl, s), "decode o_proj");
+            if (m->fuse_attn_oproj) {
+                STEP(lcc::attn_oproj_decode(qkv, kc, vc, st->page_table, LCC_PAGE_SIZE, st->scalars + LCC_SC_KV_LEN,
+                                            st->scalars + LCC_SC_ROPE_POS, fin, m->w.text_inv_freq, Hq, Hkv, nsplit,
+                                            part_o, part_ml, attn_cnt, attn, (const bf16*)lw.o_w, Hq * 128, H, h,
+                                            attn_cnt + 32, s), "decode attention + o_proj");
+            } else {
+                STEP(lcc::attn_decode(qkv, kc, vc, st->page_table, LCC_PAGE_SIZE, st->scalars + LCC_SC_KV_LEN,
+                                      st->scalars + LCC_SC_ROPE_POS, fin, m->w.text_inv_freq, Hq, Hkv, nsplit, part_o,
+                                      part_ml, attn_cnt, attn, pdl, s), "decode attention");
+                STEP(lcc::gemv_residual((const bf16*)lw.o_w, Hq * 128, attn, h, H, Hq * 128, fin, lw.gate_up_w,
+                                        cap(gu_bytes), m->ctx->num_sms, pdl, s), "decode o_proj");
+            }
             STEP(lcc::gemv_norm_swiglu((const bf16*)lw.gate_up_w, H, h, (const bf16*)lw.ln2_w, c.rms_eps, act,
                                        2 * c.inter, H, fin, lw.down_w, cap(down_bytes), m->ctx->num_sms, pdl, s), "decode gate_up");
             STEP(lcc::gemv_residual((const bf16*)lw.down_w, c.inter, act, h, H, c.inter, fin, next_qkv, cap(next_qkv_bytes),

@@ -37,6 +37,11 @@ int attn_decode(bf16* qkv, bf16* kc, bf16* vc, const int* page_table, int page_s
                 const int* rope_pos, const int* finished, const float* inv_freq, int Hq, int Hkv, int nsplit,
                 float* part_o, float* part_ml, int* counters, bf16* out, bool pdl, cudaStream_t s);
 
+int attn_oproj_decode(bf16* qkv, bf16* kc, bf16* vc, const int* page_table, int page_size, const int* kv_len,
+                      const int* rope_pos, const int* finished, const float* inv_freq, int Hq, int Hkv, int nsplit,
+                      float* part_o, float* part_ml, int* counters, bf16* attn_out, const bf16* o_w, int o_ldw,
+                      int o_N, bf16* h, int* sync, cudaStream_t s);
+
 // gemv.cu
 int gemv_norm_bias(const bf16* W, int ldw, const bf16* x, const bf16* norm_w, float eps, const bf16* bias,
                    bf16* out, int N, int K, const int* finished, const void* pf_ptr, size_t pf_bytes, int num_sms, bool pdl,
