@@ -111,7 +111,6 @@ def build_chunks(cfg, seconds, size, seed):
     pts = torch.from_numpy(reader._frame_pts[:, 1])
     ts_all = torch.arange(0.0, seconds, 0.5)
     clip, ts, idxs = get_smart_resized_clip(reader, H, W, ts_all, pts, 0)
-    path = path  # NB: LiveCCDemoInfer caches readers per path (REF/demo/infer.py:91-96): one path per stream
     chunks = [clip[:6]] + list(clip[6:].split(2))
     tss = [ts[:6]] + list(ts[6:].split(2))
     out = []

@@ -11,7 +11,7 @@ Parameter names follow transformers 5.5.0 `Qwen2VLForConditionalGeneration.state
 from __future__ import annotations
 
 from dataclasses import dataclass, field
-from typing import Callable, Dict, Iterator, List, Tuple
+from typing import Dict, Iterator, List, Tuple
 
 import torch
 

@@ -16,7 +16,6 @@ construction fails.
 """
 from __future__ import annotations
 
-import ctypes as C
 import os
 from dataclasses import dataclass
 from typing import List, Optional

@@ -12,7 +12,6 @@ from __future__ import annotations
 
 import functools
 import time
-from typing import Optional
 
 import torch
 

@@ -12,7 +12,7 @@ M-RoPE of t>1 grids differs from the 4.5x stack LiveCC shipped with; SURVEY.md Â
 """
 from __future__ import annotations
 
-from typing import Dict, Iterable, List, Optional, Tuple
+from typing import Dict, Iterable, Optional, Tuple
 
 import torch
 
