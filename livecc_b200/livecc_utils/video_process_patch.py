@@ -195,100 +195,113 @@ def _resize_bicubic_antialias(video: torch.Tensor, size):
 
 
 # ---- the four public functions ------------------------------------------------------------------
+def _first_frame_at_or_after(pts: np.ndarray, stamps: np.ndarray, start: int = 0) -> np.ndarray:
+    """For every (ascending) timestamp the index of the first frame, at or after `start`, whose pts is >= the
+    timestamp; indices past the end are len(pts). This is the forward scan of video_process_patch.py:137-142
+    (the cursor never moves backwards and may stay on a frame for several timestamps) done with one
+    searchsorted."""
+    pts = np.asarray(pts, dtype=np.float64)
+    idx = np.searchsorted(pts, np.asarray(stamps, dtype=np.float64), side="left")
+    return np.maximum(idx, start)
+
+
+def _open_for_element(ele: dict):
+    path = ele["video"]
+    if isinstance(path, str) and (path.startswith("synthetic://") or os.path.exists(path)):
+        return _open_reader(path, num_threads=2)
+    if ele.get("remote_loader") is not None:
+        return _open_reader(ele["remote_loader"](path), num_threads=2)
+    raise ValueError(f"video_path {path} not found")
+
+
 def _read_video_decord_plus(ele: dict, strict_fps: bool = False, drop_last: bool = True, return_pts: bool = False):
-    """video_process_patch.py:24-83."""
-    video_path = ele["video"]
-    if isinstance(video_path, str) and (video_path.startswith("synthetic://") or os.path.exists(video_path)):
-        vr = _open_reader(video_path, num_threads=2)
-    elif ele.get("remote_loader") is not None:
-        vr = _open_reader(ele["remote_loader"](video_path), num_threads=2)
-    else:
-        raise ValueError(f"video_path {video_path} not found")
-    video_start = ele.get("video_start", None)
-    video_end = ele.get("video_end", None)
-    video_fps = vr.get_avg_fps()
-    clip_idxs, clip_pts = None, None
-    if video_start is not None or video_end is not None:
+    """Reads (a window of) a video as uint8 TCHW (video_process_patch.py:24-83).
+    ele: {"video": path, optional "video_start"/"video_end" seconds, "remote_loader", nframes/fps hints}.
+    Default: `smart_nframes` frames, evenly spread over the window. strict_fps: one frame per 1/FPS s (first
+    frame whose pts reaches the tick), capped at FPS_MAX_FRAMES, padded to a multiple of FRAME_FACTOR by
+    repeating the last frame. Returns (clip, sample_fps[, pts])."""
+    vr = _open_for_element(ele)
+    start, end = ele.get("video_start"), ele.get("video_end")
+    native_fps = vr.get_avg_fps()
+    window_idx = window_pts = None
+    if start is not None or end is not None:
         vr.get_frame_timestamp(0)
-        video_pts = vr._frame_pts[:, 1]
-        video_start = video_pts[0] if not video_start else video_start
-        video_end = video_pts[-1] if not video_end else video_end
-        clip_idxs = ((video_start <= video_pts) & (video_pts <= video_end)).nonzero()[0]
-        clip_pts = video_pts[clip_idxs]
-        total_frames = len(clip_idxs)
+        all_pts = vr._frame_pts[:, 1]
+        lo = all_pts[0] if not start else start
+        hi = all_pts[-1] if not end else end
+        window_idx = np.flatnonzero((lo <= all_pts) & (all_pts <= hi))
+        window_pts = all_pts[window_idx]
+        n_available = len(window_idx)
     else:
-        total_frames = len(vr)
-    if not strict_fps:
-        nframes = smart_nframes(ele, total_frames=total_frames, video_fps=video_fps)
-        nframes_idxs = np.linspace(0, total_frames - 1, nframes).round().astype(int)
-        clip_idxs = nframes_idxs if clip_idxs is None else clip_idxs[nframes_idxs]
-    else:
-        if clip_pts is None:
+        n_available = len(vr)
+    if strict_fps:
+        if window_pts is None:
             vr.get_frame_timestamp(0)
-            clip_pts = vr._frame_pts[:, 1]
-            clip_idxs = np.arange(len(clip_pts))
-        expected_timestamps = np.arange(clip_pts[0], clip_pts[-1] + 1e-6, 1 / FPS)
-        if len(expected_timestamps) > FPS_MAX_FRAMES:
-            if drop_last:
-                expected_timestamps = expected_timestamps[:FPS_MAX_FRAMES]
-            else:
-                expected_timestamps = expected_timestamps[
-                    np.linspace(0, len(expected_timestamps) - 1, FPS_MAX_FRAMES).round().astype(int)]
-        expected_idxs_for_clip_pts = (expected_timestamps[:, None] <= clip_pts).argmax(axis=1)
-        clip_pts = clip_pts[expected_idxs_for_clip_pts].tolist()
-        clip_idxs = clip_idxs[expected_idxs_for_clip_pts].tolist()
-        while len(clip_idxs) % FRAME_FACTOR != 0:
-            clip_idxs.append(clip_idxs[-1])
-            clip_pts.append(clip_pts[-1])
-    clip = torch.from_numpy(vr.get_batch(list(clip_idxs)).asnumpy()).permute(0, 3, 1, 2)
-    sample_fps = len(clip_idxs) / max(total_frames, 1e-6) * video_fps
-    if return_pts:
-        return clip, sample_fps, clip_pts
-    return clip, sample_fps
+            window_pts = vr._frame_pts[:, 1]
+            window_idx = np.arange(len(window_pts))
+        ticks = np.arange(window_pts[0], window_pts[-1] + 1e-6, 1 / FPS)
+        if len(ticks) > FPS_MAX_FRAMES:
+            ticks = ticks[:FPS_MAX_FRAMES] if drop_last else \
+                ticks[np.linspace(0, len(ticks) - 1, FPS_MAX_FRAMES).round().astype(int)]
+        pick = np.minimum(_first_frame_at_or_after(window_pts, ticks), len(window_pts) - 1)
+        chosen_idx, chosen_pts = window_idx[pick].tolist(), window_pts[pick].tolist()
+        pad = -len(chosen_idx) % FRAME_FACTOR
+        chosen_idx += chosen_idx[-1:] * pad
+        chosen_pts += chosen_pts[-1:] * pad
+    else:
+        n_wanted = smart_nframes(ele, total_frames=n_available, video_fps=native_fps)
+        spread = np.linspace(0, n_available - 1, n_wanted).round().astype(int)
+        chosen_idx = spread if window_idx is None else window_idx[spread]
+        chosen_pts = window_pts
+    clip = torch.from_numpy(vr.get_batch(list(chosen_idx)).asnumpy()).permute(0, 3, 1, 2)  # THWC -> TCHW
+    sample_fps = len(chosen_idx) / max(n_available, 1e-6) * native_fps
+    return (clip, sample_fps, chosen_pts) if return_pts else (clip, sample_fps)
+
+
+def _budgeted_max_pixels(nframes: int) -> float:
+    """Per-frame pixel budget: total budget spread over frame pairs, clamped (video_process_patch.py:93,115)."""
+    return max(min(VIDEO_MAX_PIXELS, VIDEO_TOTAL_PIXELS / nframes * FRAME_FACTOR), int(VIDEO_MIN_PIXELS * 1.05))
 
 
 def _spatial_resize_video(video: torch.Tensor, nframes: int = None):
-    """video_process_patch.py:88-107."""
-    if not nframes:
-        nframes, _, height, width = video.shape
-    else:
-        height, width = video.shape[2:]
-    max_pixels = max(min(VIDEO_MAX_PIXELS, VIDEO_TOTAL_PIXELS / nframes * FRAME_FACTOR), int(VIDEO_MIN_PIXELS * 1.05))
-    resized_height, resized_width = smart_resize(height, width, factor=IMAGE_FACTOR, min_pixels=VIDEO_MIN_PIXELS,
-                                                 max_pixels=max_pixels)
-    return _resize_bicubic_antialias(video, (resized_height, resized_width)).float()
+    """Bicubic antialiased resize of a TCHW clip to the smart-resized size under the per-frame pixel budget;
+    returns float frames like the reference (video_process_patch.py:88-107)."""
+    height, width = video.shape[2:]
+    target = smart_resize(height, width, factor=IMAGE_FACTOR, min_pixels=VIDEO_MIN_PIXELS,
+                          max_pixels=_budgeted_max_pixels(nframes or video.shape[0]))
+    return _resize_bicubic_antialias(video, target).float()
 
 
 def get_smart_resized_video_reader(video_path: str, max_pixels: int = None):
-    """video_process_patch.py:109-124."""
-    video_reader = _open_reader(video_path)
-    nframes = min(len(video_reader), FPS_MAX_FRAMES)
-    height, width, _ = video_reader.next().shape
+    """Opens a reader and fixes the streaming frame size once from the first frame
+    (video_process_patch.py:109-124). Returns (reader, resized_height, resized_width)."""
+    probe = _open_reader(video_path)
+    height, width, _ = probe.next().shape
     if max_pixels is None:
-        max_pixels = max(min(VIDEO_MAX_PIXELS, VIDEO_TOTAL_PIXELS / nframes * FRAME_FACTOR), int(VIDEO_MIN_PIXELS * 1.05))
-    resized_height, resized_width = smart_resize(height, width, factor=IMAGE_FACTOR, min_pixels=VIDEO_MIN_PIXELS,
-                                                 max_pixels=max_pixels)
-    video_reader = _open_reader(video_path, num_threads=2)
-    return video_reader, resized_height, resized_width
+        max_pixels = _budgeted_max_pixels(min(len(probe), FPS_MAX_FRAMES))
+    target = smart_resize(height, width, factor=IMAGE_FACTOR, min_pixels=VIDEO_MIN_PIXELS, max_pixels=max_pixels)
+    return _open_reader(video_path, num_threads=2), target[0], target[1]
 
 
 def get_smart_resized_clip(video_reader, resized_height: int, resized_width: int, timestamps: torch.Tensor,
                            video_pts: np.ndarray, video_pts_index_from: int = 0):
-    """video_process_patch.py:126-156."""
-    while len(timestamps) % FRAME_FACTOR != 0:
-        timestamps = torch.cat([timestamps, timestamps[-1:] + 1 / FPS])
-    clip_idxs = []
-    for timestamp in timestamps:
-        while video_pts_index_from < len(video_pts) and video_pts[video_pts_index_from] < timestamp:
-            video_pts_index_from += 1
-        if video_pts_index_from >= len(video_pts):
-            break
-        clip_idxs.append(video_pts_index_from)
-    while len(clip_idxs) % FRAME_FACTOR != 0:
-        clip_idxs = clip_idxs[:-1]
-        timestamps = timestamps[:-1]
-    clip = torch.from_numpy(video_reader.get_batch(clip_idxs).asnumpy()).permute(0, 3, 1, 2)
-    if (clip.shape[0] == 3) and (clip.shape[1] == len(clip_idxs)):
+    """Frames for the given timestamps (video_process_patch.py:126-156): timestamps are padded to a multiple of
+    FRAME_FACTOR by extrapolation, each maps to the first not-yet-passed frame whose pts reaches it, timestamps
+    beyond the last frame are dropped and the result is trimmed back to a multiple of FRAME_FACTOR.
+    Returns (uint8 TCHW clip resized to (resized_height, resized_width), timestamps, frame indices)."""
+    extra = -len(timestamps) % FRAME_FACTOR
+    if extra:
+        tail = timestamps[-1] + torch.arange(1, extra + 1, dtype=timestamps.dtype) / FPS
+        timestamps = torch.cat([timestamps, tail])
+    pts = video_pts.numpy() if isinstance(video_pts, torch.Tensor) else np.asarray(video_pts)
+    idx = _first_frame_at_or_after(pts, timestamps.numpy(), video_pts_index_from)
+    overrun = idx >= len(pts)
+    n_found = int(np.argmax(overrun)) if overrun.any() else len(idx)  # the scan stops at the first overrun
+    odd = n_found % FRAME_FACTOR
+    clip_idxs = idx[: n_found - odd].tolist()
+    if odd:  # the reference trims the timestamps only by the frames dropped for evenness (not to the clip length)
+        timestamps = timestamps[:-odd]
+    clip = torch.from_numpy(video_reader.get_batch(clip_idxs).asnumpy()).permute(0, 3, 1, 2)  # THWC -> TCHW
+    if clip.shape[0] == 3 and clip.shape[1] == len(clip_idxs):  # a reader that returns channel-first batches
         clip = clip.transpose(0, 1)
-    clip = _resize_bicubic_antialias(clip, (resized_height, resized_width))
-    return clip, timestamps, clip_idxs
+    return _resize_bicubic_antialias(clip, (resized_height, resized_width)), timestamps, clip_idxs

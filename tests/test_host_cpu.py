@@ -241,3 +241,42 @@ def test_bench_reference_arm_contract_small():
     assert d["impl"] == "reference" and d["unit"] == "tokens/s" and d["value"] > 0 and d["higher_is_better"] is True
     assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in d["config"]
+
+
+def test_frame_selection_matches_the_reference_scan():
+    """get_smart_resized_clip's vectorised frame selection == the forward scan specified at
+    REF/livecc-utils/src/livecc_utils/video_process_patch.py:134-145 (spelled out here as the test's oracle),
+    including the end-of-video and odd-count quirks."""
+    import livecc_b200.livecc_utils.video_process_patch as V
+
+    def scan(timestamps, pts, start):
+        ts = timestamps.clone()
+        while len(ts) % 2 != 0:
+            ts = torch.cat([ts, ts[-1:] + 1 / 2.0])
+        out, cur = [], start
+        for t in ts:
+            while cur < len(pts) and pts[cur] < t:
+                cur += 1
+            if cur >= len(pts):
+                break
+            out.append(cur)
+        while len(out) % 2 != 0:
+            out, ts = out[:-1], ts[:-1]
+        return out, ts
+
+    class FakeReader:
+        def get_batch(self, idxs):
+            return V._Batch(np.zeros((len(idxs), 28, 28, 3), np.uint8))
+
+    rng = np.random.default_rng(0)
+    for trial in range(200):
+        n = int(rng.integers(1, 60))
+        pts = np.sort(rng.uniform(0, 10, n)) if trial % 3 else np.arange(1, n + 1) / 29.97
+        t0 = float(rng.uniform(-0.5, 9))
+        k = int(rng.integers(1, 9))
+        stamps = torch.arange(t0, t0 + 0.5 * k - 1e-9, 0.5)
+        start = int(rng.integers(0, n + 2))
+        want_idx, want_ts = scan(stamps, pts, start)
+        clip, got_ts, got_idx = V.get_smart_resized_clip(FakeReader(), 28, 28, stamps, torch.from_numpy(pts), start)
+        assert got_idx == want_idx, (trial, got_idx, want_idx)
+        assert torch.allclose(got_ts.double(), want_ts.double()) and clip.shape[0] == len(want_idx)
