@@ -384,6 +384,152 @@ static int launch_flash(const FlashParams& p, dim3 grid, cudaStream_t s) {
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// ViT attention with MT (= 2) row tiles per warp: CTA = 4 warps = 128 query rows. Every K/V fragment loaded
+// with ldmatrix feeds MT MMAs, which halves the shared-memory traffic per FLOP of the 64-row kernel above
+// (the limiter of the mma.sync path at head_dim 80). Non-causal, K/V read from the fused qkv buffer, one
+// cu_seqlens segment per blockIdx.z (VisionAttention, mq2vl.py:392-454).
+// ---------------------------------------------------------------------------------------------
+template <int MT>
+__global__ void __launch_bounds__(128) vit_flash_kernel(const FlashParams p) {
+    constexpr int D = 80, LDS = D + 8, BN = 64, BM = 64 * MT;
+    extern __shared__ __align__(16) uint8_t smem_attn[];
+    bf16* sq = reinterpret_cast<bf16*>(smem_attn);  // [BM][LDS]
+    bf16* sk = sq + BM * LDS;                        // [2][64][LDS]
+    bf16* sv = sk + 2 * BN * LDS;                    // [2][64][LDS]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int head = blockIdx.y;
+    const int seg_start = p.cu_seqlens[blockIdx.z];
+    const int seg_len = p.cu_seqlens[blockIdx.z + 1] - seg_start;
+    const int row0 = blockIdx.x * BM;
+    if (row0 >= seg_len) return;
+
+    for (int i = threadIdx.x; i < BM * (D / 8); i += 128) {
+        const int r = i / (D / 8), c = i % (D / 8);
+        const bool ok = (row0 + r) < seg_len;
+        cp_async16(sq + r * LDS + c * 8, p.q + (size_t)(seg_start + (ok ? row0 + r : 0)) * p.q_ld + (size_t)head * D + c * 8, ok);
+    }
+    cp_async_commit();
+    const int n_tiles = (seg_len + BN - 1) / BN;
+    auto load_kv = [&](int tile, int buf) {
+        bf16* dk = sk + buf * BN * LDS;
+        bf16* dv = sv + buf * BN * LDS;
+        const int t0 = tile * BN;
+        const bf16* gk = p.k + (size_t)(seg_start + t0) * p.kv_ld + (size_t)head * D;
+        const bf16* gv = p.v + (size_t)(seg_start + t0) * p.kv_ld + (size_t)head * D;
+        for (int i = threadIdx.x; i < BN * (D / 8); i += 128) {
+            const int r = i / (D / 8), c = i % (D / 8);
+            const bool ok = (t0 + r) < seg_len;
+            cp_async16(dk + r * LDS + c * 8, gk + (size_t)(ok ? r : 0) * p.kv_ld + c * 8, ok);
+            cp_async16(dv + r * LDS + c * 8, gv + (size_t)(ok ? r : 0) * p.kv_ld + c * 8, ok);
+        }
+    };
+    load_kv(0, 0);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+
+    uint32_t qf[MT][D / 16][4];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+            const int mat = lane >> 3, r = lane & 7;
+            const bf16* ptr = sq + (size_t)((warp * MT + mt) * 16 + (mat & 1) * 8 + r) * LDS + kk * 16 + (mat >> 1) * 8;
+            ldmatrix_x4(qf[mt][kk][0], qf[mt][kk][1], qf[mt][kk][2], qf[mt][kk][3], ptr);
+        }
+    float o[MT][D / 8][4];
+    float m[MT][2], l[MT][2];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+        m[mt][0] = m[mt][1] = -INFINITY;
+        l[mt][0] = l[mt][1] = 0.f;
+#pragma unroll
+        for (int d = 0; d < D / 8; ++d)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[mt][d][j] = 0.f;
+    }
+
+    for (int t = 0; t < n_tiles; ++t) {
+        const int buf = t & 1;
+        if (t + 1 < n_tiles) load_kv(t + 1, buf ^ 1);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        const bf16* ks = sk + buf * BN * LDS;
+        const bf16* vs = sv + buf * BN * LDS;
+        float s[MT][8][4];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int n = 0; n < 8; ++n)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) s[mt][n][j] = 0.f;
+        // S = Q K^T : each K fragment feeds MT row tiles
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                const int mat = lane >> 3, r = lane & 7;
+                const bf16* ptr = ks + (size_t)(nt * 16 + (mat >> 1) * 8 + r) * LDS + kk * 16 + (mat & 1) * 8;
+                uint32_t b0, b1, b2, b3;
+                ldmatrix_x4(b0, b1, b2, b3, ptr);
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                    mma_bf16_16816(s[mt][nt * 2], qf[mt][kk], b0, b1);
+                    mma_bf16_16816(s[mt][nt * 2 + 1], qf[mt][kk], b2, b3);
+                }
+            }
+        }
+        if ((t + 1) * BN > seg_len) {  // ragged last tile
+            const int kbase = t * BN + 2 * (lane & 3);
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                for (int n = 0; n < 8; ++n) {
+                    const int kidx = kbase + n * 8;
+                    if (kidx >= seg_len) { s[mt][n][0] = -INFINITY; s[mt][n][2] = -INFINITY; }
+                    if (kidx + 1 >= seg_len) { s[mt][n][1] = -INFINITY; s[mt][n][3] = -INFINITY; }
+                }
+        }
+        uint32_t pf[MT][4][4];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) softmax_step<D, 4>(s[mt], p.scale_log2, m[mt], l[mt], o[mt], pf[mt]);
+        // O += P V : each V fragment feeds MT row tiles
+#pragma unroll
+        for (int kt = 0; kt < 4; ++kt) {
+#pragma unroll
+            for (int dn = 0; dn < D / 16; ++dn) {
+                const int mat = lane >> 3, r = lane & 7;
+                const bf16* ptr = vs + (size_t)(kt * 16 + (mat & 1) * 8 + r) * LDS + dn * 16 + (mat >> 1) * 8;
+                uint32_t b0, b1, b2, b3;
+                ldmatrix_x4_trans(b0, b1, b2, b3, ptr);
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                    mma_bf16_16816(o[mt][dn * 2], pf[mt][kt], b0, b1);
+                    mma_bf16_16816(o[mt][dn * 2 + 1], pf[mt][kt], b2, b3);
+                }
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            float lr = l[mt][r];
+            lr += __shfl_xor_sync(0xffffffffu, lr, 1);
+            lr += __shfl_xor_sync(0xffffffffu, lr, 2);
+            const int rr = row0 + (warp * MT + mt) * 16 + (lane >> 2) + r * 8;
+            if (rr >= seg_len) continue;
+            const float inv = lr > 0.f ? 1.f / lr : 0.f;
+            bf16* dst = p.out + (size_t)(seg_start + rr) * p.o_ld + (size_t)head * D + 2 * (lane & 3);
+#pragma unroll
+            for (int d = 0; d < D / 8; ++d)
+                *reinterpret_cast<uint32_t*>(dst + d * 8) = pack_bf16x2(o[mt][d][2 * r] * inv, o[mt][d][2 * r + 1] * inv);
+        }
+}
+
 // ViT: qkv [N, 3*heads*80]; segments from cu_seqlens (device int32, nseg+1 entries); max_seg_len bounds the grid.
 int vit_attention(const bf16* qkv, int ld, bf16* out, int o_ld, const int* cu_seqlens, int nseg,
                   int max_seg_len, int heads, int head_dim, cudaStream_t s) {
@@ -395,6 +541,21 @@ int vit_attention(const bf16* qkv, int ld, bf16* out, int o_ld, const int* cu_se
     p.out = out; p.o_ld = o_ld; p.cu_seqlens = cu_seqlens; p.S = max_seg_len; p.past = 0; p.G = 1;
     p.Hkv = heads;
     p.scale_log2 = 1.4426950408889634f / sqrtf((float)head_dim);
+    // 128-row CTAs (two row tiles per warp) once they still give every SM >= 2 CTAs; else the 64-row kernel
+    int dev_sms = 148;
+    cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, 0);
+    const int ctas128 = ((max_seg_len + 127) / 128) * heads * nseg;
+    if (cu_seqlens && ctas128 >= 2 * dev_sms) {
+        constexpr int smem = (128 + 4 * 64) * 88 * 2;
+        static bool set = false;
+        if (!set) {
+            if (cudaFuncSetAttribute(vit_flash_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+                return -2;
+            set = true;
+        }
+        vit_flash_kernel<2><<<dim3((max_seg_len + 127) / 128, heads, nseg), 128, smem, s>>>(p);
+        return 0;
+    }
     dim3 grid((max_seg_len + 63) / 64, heads, nseg);
     return launch_flash<80, false, false>(p, grid, s);
 }

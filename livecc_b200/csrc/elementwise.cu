@@ -223,28 +223,47 @@ int vit_rope_table(float* cos_t, float* sin_t, int t, int h, int w, int merge, i
 // out[i] = x[i]*cos[i] + rot(x)[i]*sin[i], rot(x) = cat(-x[hd/2:], x[:hd/2]); cos[i] = table[i mod hd/2].
 __global__ void vit_rope_apply_kernel(bf16* __restrict__ qkv, int ld, const float* __restrict__ cos_t,
                                       const float* __restrict__ sin_t, int N, int heads, int hd) {
+    // one thread = 8 consecutive rotation pairs (x[j..j+8), x[j+half..j+half+8)): two 16-byte loads/stores of
+    // bf16 and four float4 loads of cos/sin; requires half % 8 == 0 (hd = 80 -> half = 40)
     const int half = hd / 2;
-    const int pairs_per_row = 2 * heads * half;  // q and k
+    const int chunks = half / 8;
+    const int per_row = 2 * heads * chunks;  // q and k
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (int64_t)N * pairs_per_row) return;
-    const int row = (int)(idx / pairs_per_row);
-    const int r = (int)(idx % pairs_per_row);
-    const int which = r / (heads * half);  // 0 = q, 1 = k
-    const int hh = (r / half) % heads;
-    const int j = r % half;
-    bf16* base = qkv + (size_t)row * ld + (size_t)which * heads * hd + (size_t)hh * hd;
-    const float x1 = bf2f(base[j]), x2 = bf2f(base[j + half]);
-    const float c = cos_t[(size_t)row * half + j], s = sin_t[(size_t)row * half + j];
-    // (q * cos) + (rotate_half(q) * sin) with separately rounded products (no FMA contraction)
-    const float o1 = __fadd_rn(__fmul_rn(x1, c), __fmul_rn(-x2, s));
-    const float o2 = __fadd_rn(__fmul_rn(x2, c), __fmul_rn(x1, s));
-    base[j] = f2bf(o1);
-    base[j + half] = f2bf(o2);
+    if (idx >= (int64_t)N * per_row) return;
+    const int row = (int)(idx / per_row);
+    const int r = (int)(idx % per_row);
+    const int which = r / (heads * chunks);  // 0 = q, 1 = k
+    const int hh = (r / chunks) % heads;
+    const int j0 = (r % chunks) * 8;
+    bf16* base = qkv + (size_t)row * ld + (size_t)which * heads * hd + (size_t)hh * hd + j0;
+    const uint4 u1 = *reinterpret_cast<const uint4*>(base);
+    const uint4 u2 = *reinterpret_cast<const uint4*>(base + half);
+    const float4* cp = reinterpret_cast<const float4*>(cos_t + (size_t)row * half + j0);
+    const float4* sp = reinterpret_cast<const float4*>(sin_t + (size_t)row * half + j0);
+    const float4 c0 = cp[0], c1 = cp[1], s0 = sp[0], s1 = sp[1];
+    const float c[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+    const float sn[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    const uint32_t w1[4] = {u1.x, u1.y, u1.z, u1.w}, w2[4] = {u2.x, u2.y, u2.z, u2.w};
+    uint32_t o1[4], o2[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float2 a = unpack_bf16x2(w1[k]), b = unpack_bf16x2(w2[k]);
+        // (q * cos) + (rotate_half(q) * sin) with separately rounded products (no FMA contraction)
+        const float p0 = __fadd_rn(__fmul_rn(a.x, c[2 * k]), __fmul_rn(-b.x, sn[2 * k]));
+        const float p1 = __fadd_rn(__fmul_rn(a.y, c[2 * k + 1]), __fmul_rn(-b.y, sn[2 * k + 1]));
+        const float q0 = __fadd_rn(__fmul_rn(b.x, c[2 * k]), __fmul_rn(a.x, sn[2 * k]));
+        const float q1 = __fadd_rn(__fmul_rn(b.y, c[2 * k + 1]), __fmul_rn(a.y, sn[2 * k + 1]));
+        o1[k] = pack_bf16x2(p0, p1);
+        o2[k] = pack_bf16x2(q0, q1);
+    }
+    *reinterpret_cast<uint4*>(base) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
+    *reinterpret_cast<uint4*>(base + half) = make_uint4(o2[0], o2[1], o2[2], o2[3]);
 }
 
 int vit_rope_apply(bf16* qkv, int ld, const float* cos_t, const float* sin_t, int N, int heads, int hd,
                    cudaStream_t s) {
-    const int64_t total = (int64_t)N * 2 * heads * (hd / 2);
+    if ((hd / 2) % 8 || ld % 8) return -1;
+    const int64_t total = (int64_t)N * 2 * heads * (hd / 16);
     if (total <= 0) return 0;
     vit_rope_apply_kernel<<<(int)((total + 255) / 256), 256, 0, s>>>(qkv, ld, cos_t, sin_t, N, heads, hd);
     return 0;

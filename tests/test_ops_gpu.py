@@ -88,9 +88,11 @@ def test_vit_rope(ctx, grid):
     assert torch.equal(out[:, 2], v)
 
 
-@pytest.mark.parametrize("seglens", [[1024], [256, 256, 256], [1196, 1196], [64, 80]])
-def test_vit_attention(ctx, seglens):
-    heads, hd = 4, 80
+@pytest.mark.parametrize("seglens,heads", [([1024], 4), ([256, 256, 256], 4), ([1196, 1196], 4), ([64, 80], 4),
+                                           ([1024] * 5, 16), ([1196] * 4, 16), ([200, 1024, 328], 16)])
+def test_vit_attention(ctx, seglens, heads):
+    """the last three cases are large enough to take the 128-row (two row tiles per warp) kernel"""
+    hd = 80
     N = sum(seglens)
     qkv = _rand((N, 3 * heads * hd), 4)
     cu = [0]
