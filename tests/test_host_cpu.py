@@ -280,3 +280,23 @@ def test_frame_selection_matches_the_reference_scan():
         clip, got_ts, got_idx = V.get_smart_resized_clip(FakeReader(), 28, 28, stamps, torch.from_numpy(pts), start)
         assert got_idx == want_idx, (trial, got_idx, want_idx)
         assert torch.allclose(got_ts.double(), want_ts.double()) and clip.shape[0] == len(want_idx)
+
+
+def test_cv2_reader_on_a_real_demo_video():
+    """The decord stand-in on a real 1080p clip of the reference repo (only where /root/reference is mounted):
+    pts table, smart-resized streaming size for max_pixels = 384*28*28, and a 6-frame opening clip."""
+    path = "/root/reference/demo/sources/howto_fix_laptop_mute_1080p.mp4"
+    if not os.path.exists(path):
+        pytest.skip("reference demo media not mounted on this box")
+    import livecc_b200.livecc_utils as U
+
+    reader, H, W = U.get_smart_resized_video_reader(path, 384 * 28 * 28)
+    assert (H, W) == (392, 728) and H % 28 == 0 and W % 28 == 0 and H * W <= 384 * 28 * 28
+    reader.get_frame_timestamp(0)
+    pts = torch.from_numpy(reader._frame_pts[:, 1])
+    assert len(reader) == len(pts) > 200 and 20 < float(pts[-1]) < 60 and bool((pts[1:] > pts[:-1]).all())
+    clip, ts, idxs = U.get_smart_resized_clip(reader, H, W, torch.arange(0.0, 3.0, 0.5), pts, 0)
+    assert clip.shape == (6, 3, 392, 728) and clip.dtype == torch.uint8 and len(idxs) == 6
+    assert idxs == sorted(idxs) and float(clip.float().std()) > 5.0  # real picture content
+    px, grid = __import__("livecc_b200.processing", fromlist=["patchify_video"]).patchify_video(clip)
+    assert grid.tolist() == [[3, 28, 52]] and px.shape == (3 * 28 * 52, 1176)
