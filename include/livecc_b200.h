@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define LCC_ABI_VERSION 5
+#define LCC_ABI_VERSION 6
 #define LCC_PAGE_SIZE 64
 
 typedef struct lcc_ctx lcc_ctx;
@@ -98,9 +98,14 @@ int lcc_vit_rope_apply(lcc_ctx* ctx, void* qkv, int ld, const float* cos_t, cons
                        int heads, int head_dim, lcc_stream_t stream);
 
 /* VisionAttention core (mq2vl.py:392-454): non-causal attention inside each cu_seqlens segment,
- * q/k/v read from qkv [N, 3*heads*80] (already rotated), out [N, heads*80]. cu_seqlens: device int32[nseg+1]. */
-int lcc_vit_attention(lcc_ctx* ctx, const void* qkv, int ld, void* out, int o_ld, const int32_t* cu_seqlens,
-                      int nseg, int max_seg_len, int heads, int head_dim, lcc_stream_t stream);
+ * q/k/v read from qkv [n_rows, 3*heads*80] (already rotated), out [n_rows, heads*80]. cu_seqlens: device
+ * int32[nseg+1] with cu_seqlens[nseg] == n_rows. impl: LCC_VIT_ATTN_DEFAULT, or force one kernel family. */
+#define LCC_VIT_ATTN_DEFAULT 0
+#define LCC_VIT_ATTN_MMA 1 /* mma.sync flash kernels */
+#define LCC_VIT_ATTN_TC 2  /* tcgen05 + TMEM kernel */
+int lcc_vit_attention(lcc_ctx* ctx, const void* qkv, int ld, int64_t n_rows, void* out, int o_ld,
+                      const int32_t* cu_seqlens, int nseg, int max_seg_len, int heads, int head_dim, int impl,
+                      lcc_stream_t stream);
 
 /* embed_tokens gather + masked_scatter of the video features (mq2vl.py:1255-1272).
  * ids: device int64[S]; rank_ws: device int32[S+1] scratch (last entry receives the video-token count). */

@@ -13,7 +13,7 @@ PKG_DIR = Path(__file__).resolve().parent
 LIB_PATH = PKG_DIR / "liblivecc_sm100a.so"
 HEADER_PATH = PKG_DIR.parent / "include" / "livecc_b200.h"
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 PAGE_SIZE = 64
 
 # epilogue codes (LCC_EPI_*)
@@ -206,12 +206,14 @@ class Context:
                   _i(heads), _i(head_dim), self.stream_ptr())
         return qkv
 
-    def vit_attention(self, qkv, cu_seqlens, max_seg_len, heads, head_dim):
+    def vit_attention(self, qkv, cu_seqlens, max_seg_len, heads, head_dim, impl=0):
+        """impl: 0 default, 1 mma.sync kernels, 2 tcgen05 kernel (LCC_VIT_ATTN_*)"""
         import torch
 
         out = torch.empty((qkv.shape[0], heads * head_dim), dtype=torch.bfloat16, device=qkv.device)
-        self.call("lcc_vit_attention", _ptr(qkv), _i(qkv.stride(0)), _ptr(out), _i(out.stride(0)), _ptr(cu_seqlens),
-                  _i(cu_seqlens.numel() - 1), _i(max_seg_len), _i(heads), _i(head_dim), self.stream_ptr())
+        self.call("lcc_vit_attention", _ptr(qkv), _i(qkv.stride(0)), C.c_int64(qkv.shape[0]), _ptr(out),
+                  _i(out.stride(0)), _ptr(cu_seqlens), _i(cu_seqlens.numel() - 1), _i(max_seg_len), _i(heads),
+                  _i(head_dim), _i(impl), self.stream_ptr())
         return out
 
     def embed_gather(self, ids, table, video_embeds, video_token_id):

@@ -11,6 +11,8 @@
 //    group form one 16-row MMA tile; fuses the 1-D RoPE of q, the RoPE + append of the new k/v.
 //    The last CTA of a KV group to finish merges the split-KV partials (no separate combine launch).
 // Softmax statistics are fp32; P is rounded to bf16 before P·V (as the reference does, :370).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "launch.h"
 #include "ops.h"
@@ -531,10 +533,15 @@ __global__ void __launch_bounds__(128) vit_flash_kernel(const FlashParams p) {
 }
 
 // ViT: qkv [N, 3*heads*80]; segments from cu_seqlens (device int32, nseg+1 entries); max_seg_len bounds the grid.
-int vit_attention(const bf16* qkv, int ld, bf16* out, int o_ld, const int* cu_seqlens, int nseg,
-                  int max_seg_len, int heads, int head_dim, cudaStream_t s) {
+int vit_attention(const bf16* qkv, int ld, int64_t n_rows, bf16* out, int o_ld, const int* cu_seqlens, int nseg,
+                  int max_seg_len, int heads, int head_dim, int impl, cudaStream_t s) {
     if (head_dim != 80) return -1;
     if (nseg <= 0 || max_seg_len <= 0) return 0;
+    if (impl == 0) {
+        const char* e = getenv("LIVECC_B200_VIT_ATTN");  // "mma" forces the mma.sync kernels
+        impl = (e && e[0] == 'm') ? 1 : 2;
+    }
+    if (impl == 2 && cu_seqlens) return vit_attention_tc(qkv, ld, n_rows, out, o_ld, cu_seqlens, nseg, max_seg_len, heads, s);
     FlashParams p{};
     p.q = qkv; p.q_ld = ld;
     p.k = qkv + (size_t)heads * head_dim; p.v = qkv + (size_t)2 * heads * head_dim; p.kv_ld = ld;

@@ -84,10 +84,10 @@ int lcc_vit_rope_apply(lcc_ctx* ctx, void* qkv, int ld, const float* cos_t, cons
            "lcc_vit_rope_apply");
 }
 
-int lcc_vit_attention(lcc_ctx* ctx, const void* qkv, int ld, void* out, int o_ld, const int32_t* cu_seqlens,
-                      int nseg, int max_seg_len, int heads, int head_dim, lcc_stream_t stream) {
-    OP_RET(ctx, lcc::vit_attention((const bf16*)qkv, ld, (bf16*)out, o_ld, cu_seqlens, nseg, max_seg_len, heads,
-                                   head_dim, (cudaStream_t)stream), "lcc_vit_attention");
+int lcc_vit_attention(lcc_ctx* ctx, const void* qkv, int ld, int64_t n_rows, void* out, int o_ld, const int32_t* cu_seqlens,
+                      int nseg, int max_seg_len, int heads, int head_dim, int impl, lcc_stream_t stream) {
+    OP_RET(ctx, lcc::vit_attention((const bf16*)qkv, ld, n_rows, (bf16*)out, o_ld, cu_seqlens, nseg, max_seg_len, heads,
+                                   head_dim, impl, (cudaStream_t)stream), "lcc_vit_attention");
 }
 
 int lcc_embed_gather(lcc_ctx* ctx, const int64_t* ids, const void* table, const void* video_embeds,

@@ -1,5 +1,6 @@
 // Internal interface of the tcgen05 GEMM core (see gemm_tcgen05.cu).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -30,5 +31,11 @@ struct GemmArgs {
 };
 
 int gemm_bf16_tn(const GemmArgs& a, int num_sms, cudaStream_t stream);
+
+// TMA descriptor of a row-major bf16 matrix [rows, cols] (row stride ld elements) with box [box_rows, box_cols];
+// box_cols*2 bytes must equal the swizzle span: 128 (SWIZZLE_128B) or 32 (swizzle32 = SWIZZLE_32B).
+// Out-of-range rows/cols are zero-filled.
+int make_tmap_bf16_2d_box(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_cols,
+                          int box_rows, bool swizzle32);
 
 }  // namespace lcc

@@ -270,19 +270,25 @@ static PFN_encodeTiled get_encode_fn() {
     return fn;
 }
 
-// 2-D bf16 row-major [rows, cols] with row stride ld (elements); box = [box_rows, 64 cols], SW128.
-int make_tmap_bf16_2d(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t cols, int64_t ld,
-                      int box_rows) {
+int make_tmap_bf16_2d_box(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_cols,
+                          int box_rows, bool swizzle32) {
     PFN_encodeTiled fn = get_encode_fn();
     if (!fn) return -1;
     cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride,
-                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    swizzle32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : -2;
+}
+
+// 2-D bf16 row-major [rows, cols] with row stride ld (elements); box = [box_rows, 64 cols], SW128.
+int make_tmap_bf16_2d(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t cols, int64_t ld,
+                      int box_rows) {
+    return make_tmap_bf16_2d_box(tm, ptr, rows, cols, ld, BLOCK_K, box_rows, false);
 }
 
 template <int BLOCK_N, int EPI>

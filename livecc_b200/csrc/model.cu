@@ -202,7 +202,7 @@ static int vit_forward_impl(lcc_model* m, const float* pixel_values, const uint8
         STEP(lcc::layernorm(vh, dim, (const bf16*)b.norm1_w, (const bf16*)b.norm1_b, vn, dim, N, dim, 1e-6f, s), "vit norm1");
         STEP(gemm(m, vn, dim, b.qkv_w, dim, vqkv, 3 * dim, N, 3 * dim, dim, b.qkv_b, nullptr, 0, lcc::EPI_BIAS, s), "vit qkv");
         STEP(lcc::vit_rope_apply(vqkv, 3 * dim, vcos, vsin, N, c.vit_heads, hd, s), "vit rope");
-        STEP(lcc::vit_attention(vqkv, 3 * dim, vattn, dim, vcu, t, h * w, c.vit_heads, hd, s), "vit attention");
+        STEP(lcc::vit_attention(vqkv, 3 * dim, N, vattn, dim, vcu, t, h * w, c.vit_heads, hd, 0, s), "vit attention");
         STEP(gemm(m, vattn, dim, b.proj_w, dim, vh, dim, N, dim, dim, b.proj_b, vh, dim, lcc::EPI_BIAS_RESIDUAL, s), "vit proj");
         STEP(lcc::layernorm(vh, dim, (const bf16*)b.norm2_w, (const bf16*)b.norm2_b, vn, dim, N, dim, 1e-6f, s), "vit norm2");
         STEP(gemm(m, vn, dim, b.fc1_w, dim, vmlp, c.vit_mlp, N, c.vit_mlp, dim, b.fc1_b, nullptr, 0, lcc::EPI_BIAS_QUICKGELU, s), "vit fc1");

@@ -28,8 +28,12 @@ int mrope_kv_write(bf16* qkv, int ld, const int* pos3, int S, const float* inv_f
                    cudaStream_t s);
 
 // attention.cu
-int vit_attention(const bf16* qkv, int ld, bf16* out, int o_ld, const int* cu_seqlens, int nseg,
-                  int max_seg_len, int heads, int head_dim, cudaStream_t s);
+// n_rows = rows of qkv/out (= cu_seqlens[nseg]); impl: 0 = default, 1 = mma.sync kernels, 2 = tcgen05 kernel
+int vit_attention(const bf16* qkv, int ld, int64_t n_rows, bf16* out, int o_ld, const int* cu_seqlens, int nseg,
+                  int max_seg_len, int heads, int head_dim, int impl, cudaStream_t s);
+// attention_tc.cu
+int vit_attention_tc(const bf16* qkv, int ld, int64_t n_rows, bf16* out, int o_ld, const int* cu_seqlens, int nseg,
+                     int max_seg_len, int heads, cudaStream_t s);
 int attn_prefill_paged(const bf16* q, int q_ld, const bf16* kc, const bf16* vc, const int* page_table,
                        int page_size, int Hq, int Hkv, int S, int past, bf16* out, int o_ld, float* part_o,
                        float* part_ml, size_t part_capacity_rows, int num_sms, cudaStream_t s);

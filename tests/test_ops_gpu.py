@@ -90,8 +90,10 @@ def test_vit_rope(ctx, grid):
 
 @pytest.mark.parametrize("seglens,heads", [([1024], 4), ([256, 256, 256], 4), ([1196, 1196], 4), ([64, 80], 4),
                                            ([1024] * 5, 16), ([1196] * 4, 16), ([200, 1024, 328], 16)])
-def test_vit_attention(ctx, seglens, heads):
-    """the last three cases are large enough to take the 128-row (two row tiles per warp) kernel"""
+@pytest.mark.parametrize("impl", [2, 1])
+def test_vit_attention(ctx, seglens, heads, impl):
+    """impl 2 = tcgen05/TMEM kernel (default; 128-key tiles up to one wave of CTAs, 64-key tiles beyond),
+    impl 1 = mma.sync kernels (the last three cases are large enough to take their 128-row variant)"""
     hd = 80
     N = sum(seglens)
     qkv = _rand((N, 3 * heads * hd), 4)
@@ -99,7 +101,7 @@ def test_vit_attention(ctx, seglens, heads):
     for n in seglens:
         cu.append(cu[-1] + n)
     # reference: eager attention per segment (no rotary here: identity cos/sin)
-    out = ctx.vit_attention(qkv, torch.tensor(cu, dtype=torch.int32, device=DEV), max(seglens), heads, hd)
+    out = ctx.vit_attention(qkv, torch.tensor(cu, dtype=torch.int32, device=DEV), max(seglens), heads, hd, impl=impl)
     q, k, v = qkv.reshape(N, 3, heads, hd).permute(1, 2, 0, 3).unbind(0)  # [heads, N, hd]
     refs = [_attn_ref_fp32(q[:, s:e], k[:, s:e], v[:, s:e], None, hd ** -0.5) for s, e in zip(cu[:-1], cu[1:])]
     ref = torch.cat(refs, dim=1).transpose(0, 1).reshape(N, heads * hd)
