@@ -121,10 +121,16 @@ int lcc_mrope_kv_write(lcc_ctx* ctx, void* qkv, int ld, const int32_t* pos3, int
                        const int32_t* page_table, int kv_start, lcc_stream_t stream);
 
 /* Causal GQA attention of S new tokens over past+S cached tokens (Qwen2VLAttention core,
- * mq2vl.py:572-594; eager_attention_forward :353-375). q: rotated rows of qkv; out [S, Hq*128]. */
+ * mq2vl.py:572-594; eager_attention_forward :353-375). q: rotated rows of qkv; out [S, Hq*128].
+ * part_o / part_ml: optional split-KV scratch, f32[part_rows,128] and f32[part_rows,2] with
+ * part_rows >= nsplit*S*Hq (nsplit <= 8); NULL => no KV split. impl: LCC_ATTN_DEFAULT | LCC_ATTN_MMA | LCC_ATTN_TC.
+ * The V slots of the last page behind token past+S-1 must hold finite values (lcc_mrope_kv_write zeroes them). */
+#define LCC_ATTN_DEFAULT 0
+#define LCC_ATTN_MMA 1 /* mma.sync flash kernel */
+#define LCC_ATTN_TC 2  /* tcgen05 + TMEM kernel */
 int lcc_attn_prefill(lcc_ctx* ctx, const void* q, int q_ld, const void* k_cache, const void* v_cache,
                      const int32_t* page_table, int Hq, int Hkv, int S, int past, void* out, int o_ld,
-                     lcc_stream_t stream);
+                     float* part_o, float* part_ml, int64_t part_rows, int impl, lcc_stream_t stream);
 
 /* One-token attention: RoPE of q, RoPE + append of the new k/v at slot scalars[LCC_SC_KV_LEN],
  * split-KV attention over the paged cache and merge. qkv: raw projections(+bias) of the new token.

@@ -231,13 +231,18 @@ class Context:
                   _i(sec_t), _i(sec_h), _i(Hq), _i(Hkv), _ptr(k_cache), _ptr(v_cache), _ptr(page_table), _i(kv_start),
                   self.stream_ptr())
 
-    def attn_prefill(self, q, k_cache, v_cache, page_table, Hq, Hkv, past):
+    def attn_prefill(self, q, k_cache, v_cache, page_table, Hq, Hkv, past, impl=0, split=False):
+        """impl: 0 default, 1 mma.sync kernel, 2 tcgen05 kernel (LCC_ATTN_*); split: provide split-KV scratch"""
         import torch
 
         S = q.shape[0]
         out = torch.empty((S, Hq * 128), dtype=torch.bfloat16, device=q.device)
+        part_rows = 8 * S * Hq if split else 0
+        part_o = torch.empty((max(part_rows, 1), 128), dtype=torch.float32, device=q.device)
+        part_ml = torch.empty((max(part_rows, 1), 2), dtype=torch.float32, device=q.device)
         self.call("lcc_attn_prefill", _ptr(q), _i(q.stride(0)), _ptr(k_cache), _ptr(v_cache), _ptr(page_table), _i(Hq),
-                  _i(Hkv), _i(S), _i(past), _ptr(out), _i(out.stride(0)), self.stream_ptr())
+                  _i(Hkv), _i(S), _i(past), _ptr(out), _i(out.stride(0)), _ptr(part_o) if split else None,
+                  _ptr(part_ml) if split else None, C.c_int64(part_rows), _i(impl), self.stream_ptr())
         return out
 
     def attn_decode(self, qkv, k_cache, v_cache, page_table, scalars, inv_freq, Hq, Hkv, nsplit):

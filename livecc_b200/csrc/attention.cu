@@ -571,9 +571,25 @@ int vit_attention(const bf16* qkv, int ld, int64_t n_rows, bf16* out, int o_ld, 
 // (already containing the S new tokens at positions past..past+S-1).
 int attn_prefill_paged(const bf16* q, int q_ld, const bf16* kc, const bf16* vc, const int* page_table,
                        int page_size, int Hq, int Hkv, int S, int past, bf16* out, int o_ld, float* part_o,
-                       float* part_ml, size_t part_capacity_rows, int num_sms, cudaStream_t s) {
+                       float* part_ml, size_t part_capacity_rows, int num_sms, int impl, cudaStream_t s) {
     if (page_size != 64) return -1;
     if (S <= 0) return 0;
+    if (impl == 0) {
+        const char* e = getenv("LIVECC_B200_PREFILL_ATTN");  // "mma" forces the mma.sync kernel
+        impl = (e && e[0] == 'm') ? 1 : 2;
+    }
+    if (impl == 2) {
+        int ns = 1;
+        if (int r = attn_prefill_tc(q, q_ld, kc, vc, page_table, Hq, Hkv, S, past, out, o_ld, part_o, part_ml,
+                                    part_capacity_rows, num_sms, &ns, s))
+            return r;
+        if (ns > 1) {
+            const int G = Hq / Hkv;
+            flash_merge_kernel<<<dim3(S * G, Hkv), 128, 0, s>>>(part_o, part_ml, ns, Hkv, S * G, G,
+                                                                1.4426950408889634f / sqrtf(128.f), out, o_ld);
+        }
+        return 0;
+    }
     FlashParams p{};
     p.q = q; p.q_ld = q_ld; p.kc = kc; p.vc = vc; p.page_table = page_table; p.Hkv = Hkv;
     p.out = out; p.o_ld = o_ld; p.cu_seqlens = nullptr; p.S = S; p.past = past; p.G = Hq / Hkv;

@@ -107,10 +107,10 @@ int lcc_mrope_kv_write(lcc_ctx* ctx, void* qkv, int ld, const int32_t* pos3, int
 
 int lcc_attn_prefill(lcc_ctx* ctx, const void* q, int q_ld, const void* k_cache, const void* v_cache,
                      const int32_t* page_table, int Hq, int Hkv, int S, int past, void* out, int o_ld,
-                     lcc_stream_t stream) {
+                     float* part_o, float* part_ml, int64_t part_rows, int impl, lcc_stream_t stream) {
     OP_RET(ctx, lcc::attn_prefill_paged((const bf16*)q, q_ld, (const bf16*)k_cache, (const bf16*)v_cache, page_table,
-                                        LCC_PAGE_SIZE, Hq, Hkv, S, past, (bf16*)out, o_ld, nullptr, nullptr, 0,
-                                        ctx->num_sms, (cudaStream_t)stream),
+                                        LCC_PAGE_SIZE, Hq, Hkv, S, past, (bf16*)out, o_ld, part_o, part_ml,
+                                        (size_t)(part_rows > 0 ? part_rows : 0), ctx->num_sms, impl, (cudaStream_t)stream),
            "lcc_attn_prefill");
 }
 

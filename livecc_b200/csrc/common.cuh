@@ -119,6 +119,16 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
         : "memory");
 }
 
+// 3-D tiled TMA load (coordinates innermost first).
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1,
+                                            int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
 // ----------------------------------------------------------------------------
 // tcgen05 / TMEM
 // ----------------------------------------------------------------------------
@@ -171,6 +181,18 @@ __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
     d |= (uint64_t)(1024 >> 4) << 32;                     // SBO = 1024 B   [32,46)
     d |= (uint64_t)1 << 46;                               // version = 1    [46,48)
     d |= (uint64_t)2 << 61;                               // SWIZZLE_128B   [61,64)
+    return d;
+}
+
+// MN-major operand staged as SWIZZLE_128B atoms [k rows][64 bf16] (cute: ((T,8,m),(8,k)):((1,T,LBO),(8T,SBO))):
+// 64 contiguous MN elements per 128-byte row, next k row +128 B, next 8 k rows +SBO (1024), next 64 MN elements +LBO.
+__device__ __forceinline__ uint64_t make_sw128_mnmajor_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
     return d;
 }
 

@@ -373,6 +373,11 @@ __global__ void mrope_kv_write_kernel(bf16* __restrict__ qkv, int ld, const int*
         const int kvh = hh - Hq - Hkv;
         bf16* dst = vc + (((size_t)page * Hkv + kvh) * page_size + slot) * 128;
         if (lane < 16) *reinterpret_cast<uint4*>(dst + lane * 8) = *reinterpret_cast<const uint4*>(row + lane * 8);
+        // The V slots of the last page behind the newest token are zeroed: the tensor-core prefill kernel multiplies
+        // them by P = 0 (masked keys), which must not meet NaN/Inf bit patterns of a recycled page.
+        if (s_idx == S - 1)
+            for (int i = lane; i < (page_size - 1 - slot) * 16; i += 32)
+                *reinterpret_cast<uint4*>(dst + 128 + i * 8) = make_uint4(0u, 0u, 0u, 0u);
         return;
     }
     const int pt = pos3[s_idx], ph = pos3[S + s_idx], pw = pos3[2 * S + s_idx];

@@ -35,6 +35,9 @@ int gemm_bf16_tn(const GemmArgs& a, int num_sms, cudaStream_t stream);
 // TMA descriptor of a row-major bf16 matrix [rows, cols] (row stride ld elements) with box [box_rows, box_cols];
 // box_cols*2 bytes must equal the swizzle span: 128 (SWIZZLE_128B) or 32 (swizzle32 = SWIZZLE_32B).
 // Out-of-range rows/cols are zero-filled.
+// 3-D variant (SWIZZLE_128B, inner box 64 elements): dims/box innermost first, strides in elements for dims 1 and 2.
+int make_tmap_bf16_3d_sw128(CUtensorMap* tm, const void* ptr, int64_t d0, int64_t d1, int64_t d2, int64_t stride1,
+                            int64_t stride2, int box1, int box2);
 int make_tmap_bf16_2d_box(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_cols,
                           int box_rows, bool swizzle32);
 

@@ -285,6 +285,20 @@ int make_tmap_bf16_2d_box(CUtensorMap* tm, const void* ptr, int64_t rows, int64_
     return r == CUDA_SUCCESS ? 0 : -2;
 }
 
+int make_tmap_bf16_3d_sw128(CUtensorMap* tm, const void* ptr, int64_t d0, int64_t d1, int64_t d2, int64_t stride1,
+                            int64_t stride2, int box1, int box2) {
+    PFN_encodeTiled fn = get_encode_fn();
+    if (!fn) return -1;
+    cuuint64_t gdim[3] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2};
+    cuuint64_t gstride[2] = {(cuuint64_t)stride1 * 2, (cuuint64_t)stride2 * 2};
+    cuuint32_t box[3] = {64u, (cuuint32_t)box1, (cuuint32_t)box2};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : -2;
+}
+
 // 2-D bf16 row-major [rows, cols] with row stride ld (elements); box = [box_rows, 64 cols], SW128.
 int make_tmap_bf16_2d(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t cols, int64_t ld,
                       int box_rows) {

@@ -255,7 +255,7 @@ int lcc_prefill(lcc_model* m, const lcc_stream_state* st, const int64_t* ids, co
                                  st->page_table, LCC_PAGE_SIZE, past, s), "mrope + kv write");
         STEP(lcc::attn_prefill_paged(qkv, qkv_dim, kc, vc, st->page_table, LCC_PAGE_SIZE, Hq, Hkv, S, past, attn,
                                      Hq * 128, (float*)(ws + L.pf_part_o), (float*)(ws + L.pf_part_ml),
-                                     kPrefillSplitRows * (size_t)Hq, m->ctx->num_sms, s), "prefill attention");
+                                     kPrefillSplitRows * (size_t)Hq, m->ctx->num_sms, 0, s), "prefill attention");
         STEP(gemm(m, attn, Hq * 128, lw.o_w, Hq * 128, hid, H, S, H, Hq * 128, nullptr, hid, H, lcc::EPI_RESIDUAL, s), "o_proj");
         STEP(lcc::rmsnorm(hid, H, (const bf16*)lw.ln2_w, normed, H, S, H, c.rms_eps, s), "post_attention_layernorm");
         STEP(gemm(m, normed, H, lw.gate_up_w, H, act, c.inter, S, 2 * c.inter, H, nullptr, nullptr, 0, lcc::EPI_SWIGLU, s), "gate_up");

@@ -34,9 +34,14 @@ int vit_attention(const bf16* qkv, int ld, int64_t n_rows, bf16* out, int o_ld, 
 // attention_tc.cu
 int vit_attention_tc(const bf16* qkv, int ld, int64_t n_rows, bf16* out, int o_ld, const int* cu_seqlens, int nseg,
                      int max_seg_len, int heads, cudaStream_t s);
+// impl: 0 = default, 1 = mma.sync kernel, 2 = tcgen05 kernel (LCC_ATTN_*)
 int attn_prefill_paged(const bf16* q, int q_ld, const bf16* kc, const bf16* vc, const int* page_table,
                        int page_size, int Hq, int Hkv, int S, int past, bf16* out, int o_ld, float* part_o,
-                       float* part_ml, size_t part_capacity_rows, int num_sms, cudaStream_t s);
+                       float* part_ml, size_t part_capacity_rows, int num_sms, int impl, cudaStream_t s);
+// attention_prefill_tc.cu
+int attn_prefill_tc(const bf16* q, int q_ld, const bf16* kc, const bf16* vc, const int* page_table, int Hq, int Hkv,
+                    int S, int past, bf16* out, int o_ld, float* part_o, float* part_ml, size_t part_capacity_rows,
+                    int num_sms, int* nsplit_out, cudaStream_t s);
 int attn_decode(bf16* qkv, bf16* kc, bf16* vc, const int* page_table, int page_size, const int* kv_len,
                 const int* rope_pos, const int* finished, const float* inv_freq, int Hq, int Hkv, int nsplit,
                 float* part_o, float* part_ml, int* counters, bf16* out, bool pdl, cudaStream_t s);

@@ -151,10 +151,16 @@ def _text_inv_freq():
     return (1.0 / (1e6 ** (torch.arange(0, 128, 2, dtype=torch.int64).to(torch.float) / 128))).to(DEV)
 
 
-@pytest.mark.parametrize("S,past", [(281, 0), (300, 1000), (1, 64), (70, 3)])
-def test_mrope_kv_write_and_prefill_attention(ctx, S, past):
+@pytest.mark.parametrize("impl,split", [(2, False), (2, True), (1, False), (1, True)])
+@pytest.mark.parametrize("S,past", [(281, 0), (300, 1000), (1, 64), (70, 3), (281, 4100)])
+def test_mrope_kv_write_and_prefill_attention(ctx, S, past, impl, split):
+    """impl 2 = tcgen05/TMEM kernel (default), impl 1 = mma.sync kernel; split = with split-KV scratch (the split
+    count is the kernel's choice: > 1 only for the long-past cases). The cache pages start as NaN bit patterns, as a
+    recycled pool page may: nothing behind the newest token may leak into the result."""
     Hq, Hkv = 14, 2
     cache = PagedCache(1, Hkv, past + S)
+    cache.k.fill_(float("nan"))
+    cache.v.fill_(float("nan"))
     inv = _text_inv_freq()
     # pre-fill the past part of the cache with random (already rotated) keys/values
     if past:
@@ -185,7 +191,7 @@ def test_mrope_kv_write_and_prefill_attention(ctx, S, past):
     if past:
         assert torch.equal(kc[:, :past], pk) and torch.equal(vc[:, :past], pv)
     # attention of the S new rows over past+S
-    out = ctx.attn_prefill(work, cache.k[0], cache.v[0], cache.page_table, Hq, Hkv, past)
+    out = ctx.attn_prefill(work, cache.k[0], cache.v[0], cache.page_table, Hq, Hkv, past, impl=impl, split=split)
     T = past + S
     rep = Hq // Hkv
     kr = kc[:, None].expand(Hkv, rep, T, 128).reshape(Hq, T, 128)
