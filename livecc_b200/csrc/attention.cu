@@ -1,5 +1,7 @@
-// Attention kernels of the LiveCC path (round-1 implementation: mma.sync.m16n8k16 bf16 flash-style
-// kernels with cp.async-staged K/V tiles; the tcgen05 version is the next step).
+// Attention kernels of the LiveCC path, mma.sync.m16n8k16 bf16 flash-style with cp.async-staged K/V tiles.
+// The ViT and prefill kernels here were the round's first implementation and are now the fallback / cross-check of
+// the tcgen05 + TMEM kernels (attention_tc.cu, attention_prefill_tc.cu), which the launchers below dispatch to by
+// default; the one-token decode attention (HBM-bound) lives only here.
 //
 //  * flash_fwd_kernel<D, CAUSAL, PAGED>: multi-row attention.
 //      - ViT (D=80, non-causal, K/V read from the fused qkv buffer, one cu_seqlens segment per
