@@ -552,7 +552,9 @@ int vit_attention(const bf16* qkv, int ld, int64_t n_rows, bf16* out, int o_ld, 
     p.scale_log2 = 1.4426950408889634f / sqrtf((float)head_dim);
     // 128-row CTAs (two row tiles per warp) once they still give every SM >= 2 CTAs; else the 64-row kernel
     int dev_sms = 148;
-    cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, 0);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, dev);
     const int ctas128 = ((max_seg_len + 127) / 128) * heads * nseg;
     if (cu_seqlens && ctas128 >= 2 * dev_sms) {
         constexpr int smem = (128 + 4 * 64) * 88 * 2;

@@ -353,7 +353,9 @@ int vit_attention_tc(const bf16* qkv, int ld, int64_t n_rows, bf16* out, int o_l
     // <= one wave of CTAs: 128-key tiles, one CTA per SM; more: 64-key tiles so that two CTAs share an SM and one
     // CTA's softmax runs under the other's waits (measured: 103 -> 77 us at 8x1024 patches, 16 heads)
     int dev_sms = 148;
-    cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, 0);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, dev);
     const char* e = getenv("LIVECC_B200_VIT_TC_BN");  // tuning hook: force keys per tile (64 | 128)
     const int variant = e ? atoi(e) : ((int)(grid.x * grid.y * grid.z) <= dev_sms ? 128 : 64);
     if (variant == 128) return launch_tc<Cfg<128, 3>>(qkv, ld, n_rows, p, grid, s);
