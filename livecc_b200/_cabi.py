@@ -152,8 +152,9 @@ class Context:
         return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
     # ---- op level ----------------------------------------------------------------------------
-    def gemm(self, a, b, out=None, bias=None, residual=None, epilogue=EPI_NONE, block_n=0):
-        """out[M,N] = epilogue(a[M,K] @ b[N,K]^T); 2-D bf16 CUDA tensors, last dim contiguous."""
+    def gemm(self, a, b, out=None, bias=None, residual=None, epilogue=EPI_NONE, block_n=0, splitk_ws=None):
+        """out[M,N] = epilogue(a[M,K] @ b[N,K]^T); 2-D bf16 CUDA tensors, last dim contiguous.
+        splitk_ws: optional fp32 scratch tensor (experimental split-K, LIVECC_B200_GEMM_SPLITK=1)."""
         import torch
 
         M, K = a.shape
@@ -165,7 +166,9 @@ class Context:
         assert out.stride(1) == 1 and out.shape == (M, n_out)
         ldr = residual.stride(0) if residual is not None else 0
         self.call("lcc_gemm_bf16", _ptr(a), _i(a.stride(0)), _ptr(b), _i(b.stride(0)), _ptr(out), _i(out.stride(0)),
-                  _i(M), _i(N), _i(K), _ptr(bias), _ptr(residual), _i(ldr), _i(epilogue), _i(block_n), self.stream_ptr())
+                  _i(M), _i(N), _i(K), _ptr(bias), _ptr(residual), _i(ldr), _i(epilogue), _i(block_n), _ptr(splitk_ws),
+                  C.c_int64(splitk_ws.numel() * splitk_ws.element_size() if splitk_ws is not None else 0),
+                  self.stream_ptr())
         return out
 
     def cast_f32_bf16(self, x):

@@ -33,9 +33,11 @@ int lcc_num_sms(lcc_ctx* ctx) { return ctx ? ctx->num_sms : -1; }
 
 int lcc_gemm_bf16(lcc_ctx* ctx, const void* A, int lda, const void* B, int ldb, void* C, int ldc,
                   int M, int N, int K, const void* bias, const void* residual, int ldr, int epilogue,
-                  int block_n, lcc_stream_t stream) {
+                  int block_n, void* splitk_ws, int64_t splitk_ws_bytes, lcc_stream_t stream) {
     if (!ctx) return -1;
     lcc::GemmArgs a;
+    a.splitk_ws = splitk_ws;
+    a.splitk_ws_bytes = splitk_ws_bytes > 0 ? (size_t)splitk_ws_bytes : 0;
     a.A = A; a.B = B; a.C = C;
     a.M = M; a.N = N; a.K = K;
     a.lda = lda; a.ldb = ldb; a.ldc = ldc;

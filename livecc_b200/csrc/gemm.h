@@ -15,6 +15,7 @@ enum GemmEpilogue {
     EPI_RESIDUAL = 4,        // C = bf16(bf16(acc) + residual)            (o_proj/down_proj, mq2vl.py:645-660)
     EPI_BIAS_RESIDUAL = 5,   // C = bf16(bf16(acc + bias) + residual)     (ViT proj/fc2, mq2vl.py:479-487)
     EPI_SWIGLU = 6,          // C[:, j] = bf16(silu(bf16 gate_j) * bf16 up_j), gate/up rows interleaved by 16
+    EPI_PARTIAL_F32 = 7,     // internal (split-K): fp32 partial tiles, reduced by splitk_reduce_kernel
 };
 
 struct GemmArgs {
@@ -28,6 +29,10 @@ struct GemmArgs {
     int ldr;
     int epi;
     int block_n;  // 0 = heuristic, else 64 / 128 / 256
+    // optional split-K scratch (fp32, >= splits*M*N*4 bytes); null = never split. `splits` is set internally.
+    void* splitk_ws = nullptr;
+    size_t splitk_ws_bytes = 0;
+    int splits = 1;
 };
 
 int gemm_bf16_tn(const GemmArgs& a, int num_sms, cudaStream_t stream);

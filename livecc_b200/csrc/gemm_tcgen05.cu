@@ -16,6 +16,8 @@
 // overlaps the main loop of tile i+1.
 //
 // The fused epilogues reproduce the reference's bf16 rounding points (one torch op = one rounding).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "gemm.h"
 
@@ -52,8 +54,11 @@ __global__ void __launch_bounds__(384, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     const __grid_constant__ CUtensorMap tmap_b, bf16* C, int M, int N,
                     int K, int ldc, const bf16* __restrict__ bias,
-                    const bf16* residual /* may alias C */, int ldr) {
+                    const bf16* residual /* may alias C */, int ldr, int splits_arg /* >= 1 */) {
     using Cfg = GemmCfg<BLOCK_N>;
+    // split-K exists only in the EPI_PARTIAL_F32 instantiations; everywhere else splits is the constant 1 and the
+    // unit arithmetic below folds back to the plain (m tile, n tile) loop.
+    const int splits = (EPI == EPI_PARTIAL_F32) ? splits_arg : 1;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte alignment.
@@ -70,8 +75,12 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
 
     const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
     const int n_tiles = (N + BLOCK_N - 1) / BLOCK_N;
-    const int num_tiles = m_tiles * n_tiles;
     const int num_k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
+    // Work unit = (m tile, k split, n tile), m fastest so that the CTAs that share a weight tile run together.
+    // splits == 1: a unit is a whole output tile. splits > 1 (EPI_PARTIAL_F32): a unit covers kbps k-blocks and
+    // writes an fp32 partial tile; splitk_reduce_kernel sums the partials and applies the epilogue.
+    const int num_tiles = m_tiles * n_tiles * splits;
+    const int kbps = (num_k_blocks + splits - 1) / splits;
 
     if (warp == 0 && lane == 0) {
         prefetch_tensormap(&tmap_a);
@@ -103,8 +112,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m_blk = tile % m_tiles, n_blk = tile / m_tiles;
-                for (int kb = 0; kb < num_k_blocks; ++kb) {
+                const int m_blk = tile % m_tiles, ks = (tile / m_tiles) % splits, n_blk = tile / (m_tiles * splits);
+                const int kb0 = ks * kbps, kb1 = min(kb0 + kbps, num_k_blocks);
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
                     uint8_t* sb = sa + Cfg::A_BYTES;
@@ -126,7 +136,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
             mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
-            for (int kb = 0; kb < num_k_blocks; ++kb) {
+            const int ks = (tile / m_tiles) % splits;
+            const int kb0 = ks * kbps, kb1 = min(kb0 + kbps, num_k_blocks);
+            for (int kb = kb0; kb < kb1; ++kb) {
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
                 if (lane == 0) {
@@ -138,10 +150,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
                         // advance start address by k*32 bytes (>>4 => +2k) inside the swizzle atom
                         umma_bf16_ss(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
-                                     (kb | k) != 0 ? 1u : 0u);
+                                     ((kb - kb0) | k) != 0 ? 1u : 0u);
                     }
                     umma_commit(&empty_bar[stage]);  // frees the smem slot when the MMAs retire
-                    if (kb == num_k_blocks - 1) umma_commit(&tmem_full[acc]);
+                    if (kb == kb1 - 1) umma_commit(&tmem_full[acc]);
                 }
                 __syncwarp();
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -156,7 +168,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int m_blk = tile % m_tiles, n_blk = tile / m_tiles;
+            const int m_blk = tile % m_tiles, ks = (tile / m_tiles) % splits, n_blk = tile / (m_tiles * splits);
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const int row = m_blk * BLOCK_M + q * 32 + lane;
@@ -169,7 +181,17 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 tmem_ld_32x32b_x32(taddr, v);
                 tmem_ld_wait();
                 const int col0 = n_blk * BLOCK_N + c * 32;
-                if (EPI == EPI_SWIGLU) {
+                if (EPI == EPI_PARTIAL_F32) {
+                    // fp32 partial tile of split ks: P[ks][row][col] (C is the partial buffer, ldc == N)
+                    if (row_ok) {
+                        float* dst = reinterpret_cast<float*>(C) + ((size_t)ks * M + row) * (size_t)ldc + col0;
+#pragma unroll
+                        for (int g = 0; g < 8; ++g)
+                            if (col0 + g * 4 < N)
+                                *reinterpret_cast<uint4*>(dst + g * 4) =
+                                    make_uint4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+                    }
+                } else if (EPI == EPI_SWIGLU) {
                     // Weight rows are interleaved in 32-row groups: 16 gate rows then the 16
                     // matching up rows. out[j] = bf16(silu_bf16(bf16 gate) * bf16 up)  (mq2vl.py:503)
                     if (row_ok && col0 < N) {
@@ -320,11 +342,12 @@ static int launch_cfg(const GemmArgs& a, int num_sms, cudaStream_t stream) {
         attr_set = true;
     }
     const int m_tiles = (a.M + BLOCK_M - 1) / BLOCK_M, n_tiles = (a.N + BLOCK_N - 1) / BLOCK_N;
-    const int tiles = m_tiles * n_tiles;
+    const int splits = (EPI == EPI_PARTIAL_F32 && a.splits > 1) ? a.splits : 1;
+    const int tiles = m_tiles * n_tiles * splits;
     const int grid = tiles < num_sms ? tiles : num_sms;
     kern<<<grid, 384, Cfg::SMEM_BYTES, stream>>>(ta, tb, (bf16*)a.C, a.M, a.N, a.K, a.ldc,
                                                  (const bf16*)a.bias, (const bf16*)a.residual,
-                                                 a.ldr);
+                                                 a.ldr, splits);
     return cudaGetLastError() == cudaSuccess ? 0 : -13;
 }
 
@@ -342,6 +365,95 @@ static int launch_epi(const GemmArgs& a, int num_sms, cudaStream_t stream) {
     return -14;
 }
 
+// Sum of the split-K partials + the fused epilogue (same rounding points as the in-kernel epilogues):
+// C = bf16(sum [+ bias]) [then bf16(. + residual)].  One thread per 8 columns; residual may alias C.
+__global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits, int M, int N,
+                                     const bf16* __restrict__ bias, const bf16* residual, int ldr, bf16* C, int ldc,
+                                     int epi) {
+    const int groups = N / 8;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)M * groups) return;
+    const int row = (int)(idx / groups), col = (int)(idx % groups) * 8;
+    float x[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int ks = 0; ks < splits; ++ks) {
+        const float4* src = reinterpret_cast<const float4*>(part + ((size_t)ks * M + row) * (size_t)N + col);
+        const float4 a = src[0], b = src[1];
+        x[0] += a.x; x[1] += a.y; x[2] += a.z; x[3] += a.w;
+        x[4] += b.x; x[5] += b.y; x[6] += b.z; x[7] += b.w;
+    }
+    if (epi == EPI_BIAS || epi == EPI_BIAS_RESIDUAL) {
+        const uint4 bb = *reinterpret_cast<const uint4*>(bias + col);
+        const uint32_t bw[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 f = unpack_bf16x2(bw[j]);
+            x[2 * j] += f.x;
+            x[2 * j + 1] += f.y;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = rbf(x[j]);
+    if (epi == EPI_RESIDUAL || epi == EPI_BIAS_RESIDUAL) {
+        const uint4 rr = *reinterpret_cast<const uint4*>(residual + (size_t)row * ldr + col);
+        const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 f = unpack_bf16x2(rw[j]);
+            x[2 * j] += f.x;
+            x[2 * j + 1] += f.y;
+        }
+    }
+    uint4 o;
+    o.x = pack_bf16x2(x[0], x[1]);
+    o.y = pack_bf16x2(x[2], x[3]);
+    o.z = pack_bf16x2(x[4], x[5]);
+    o.w = pack_bf16x2(x[6], x[7]);
+    *reinterpret_cast<uint4*>(C + (size_t)row * ldc + col) = o;
+}
+
+// Split-K for small-M GEMMs whose tile count cannot occupy the SMs (prefill o_proj / down_proj / qkv at M ~ 281).
+// Returns 1 if it handled the GEMM, 0 if the caller should run the plain path, < 0 on error.
+// UNVALIDATED ON HARDWARE (written at the end of round 1 without GPU time): opt-in through LIVECC_B200_GEMM_SPLITK=1.
+static int try_splitk(const GemmArgs& a, int num_sms, cudaStream_t stream) {
+    static int enabled = -1;
+    if (enabled < 0) {
+        const char* e = getenv("LIVECC_B200_GEMM_SPLITK");
+        enabled = (e && e[0] == '1') ? 1 : 0;
+    }
+    if (!enabled || !a.splitk_ws || a.M > 384) return 0;
+    if (a.epi != EPI_NONE && a.epi != EPI_BIAS && a.epi != EPI_RESIDUAL && a.epi != EPI_BIAS_RESIDUAL) return 0;
+    const int block_n = a.N >= 256 ? 256 : (a.N >= 128 ? 128 : 64);
+    const int m_tiles = (a.M + BLOCK_M - 1) / BLOCK_M, n_tiles = (a.N + block_n - 1) / block_n;
+    const int tiles = m_tiles * n_tiles;
+    const int nkb = (a.K + BLOCK_K - 1) / BLOCK_K;
+    if (tiles * 2 > num_sms) return 0;
+    int splits = (2 * num_sms + tiles / 2) / tiles;  // about two work units per CTA
+    if (splits > 8) splits = 8;
+    if (splits > nkb / 4) splits = nkb / 4;  // >= 4 k-blocks per unit
+    while (splits > 1 && (splits - 1) * ((nkb + splits - 1) / splits) >= nkb) --splits;  // no empty split
+    while (splits > 1 && (size_t)splits * a.M * a.N * 4 > a.splitk_ws_bytes) --splits;
+    if (splits < 2) return 0;
+    GemmArgs p = a;
+    p.C = a.splitk_ws;
+    p.ldc = a.N;
+    p.epi = EPI_PARTIAL_F32;
+    p.splits = splits;
+    p.bias = nullptr;
+    p.residual = nullptr;
+    int r;
+    switch (block_n) {
+        case 256: r = launch_cfg<256, EPI_PARTIAL_F32>(p, num_sms, stream); break;
+        case 128: r = launch_cfg<128, EPI_PARTIAL_F32>(p, num_sms, stream); break;
+        default: r = launch_cfg<64, EPI_PARTIAL_F32>(p, num_sms, stream); break;
+    }
+    if (r) return r;
+    const int64_t threads = (int64_t)a.M * (a.N / 8);
+    splitk_reduce_kernel<<<(int)((threads + 255) / 256), 256, 0, stream>>>(
+        (const float*)a.splitk_ws, splits, a.M, a.N, (const bf16*)a.bias, (const bf16*)a.residual, a.ldr, (bf16*)a.C,
+        a.ldc, a.epi);
+    return cudaGetLastError() == cudaSuccess ? 1 : -13;
+}
+
 int gemm_bf16_tn(const GemmArgs& a, int num_sms, cudaStream_t stream) {
     if (a.M <= 0 || a.N <= 0 || a.K <= 0) return -1;
     if ((a.K % 8) || (a.lda % 8) || (a.ldb % 8) || (a.N % 8) || (a.ldc % 8)) return -2;
@@ -349,6 +461,7 @@ int gemm_bf16_tn(const GemmArgs& a, int num_sms, cudaStream_t stream) {
     if ((a.epi == EPI_RESIDUAL || a.epi == EPI_BIAS_RESIDUAL) && (!a.residual || (a.ldr % 8))) return -4;
     if ((a.epi == EPI_BIAS || a.epi == EPI_BIAS_QUICKGELU || a.epi == EPI_BIAS_GELU ||
          a.epi == EPI_BIAS_RESIDUAL) && !a.bias) return -5;
+    if (int r = try_splitk(a, num_sms, stream)) return r < 0 ? r : 0;
     // Tile-shape heuristic. Narrow tiles re-read the A tile from L2 once per N tile and are L2->SM
     // bandwidth bound (128x64 tiles need ~190 B/clk/SM; the L2 delivers ~40), so prefer the widest
     // tile that still occupies at least half of the SMs.

@@ -38,12 +38,13 @@ int get_layout(const lcc_model* m, int need_patches, int need_tokens, WsLayout* 
 
 struct WsLayout {
     size_t vx, vh, vn, vqkv, vattn, vmlp, vcos, vsin, vcu;  // ViT
-    size_t hid, normed, qkv, attn, act, rank, pf_part_o, pf_part_ml;  // prefill
+    size_t hid, normed, qkv, attn, act, rank, pf_part_o, pf_part_ml, pf_splitk;  // prefill
     size_t h1, qkv1, attn1, act1, logits_raw, logits_proc, part_o, part_ml, attn_cnt;  // decode
     size_t total;
 };
 
 constexpr int kMaxSplit = 64;
+constexpr size_t kSplitKRows = 8 * 384;  // split-K GEMM partials: splits (<= 8) x M (<= 384) fp32 rows of the widest projection
 constexpr size_t kPrefillSplitRows = 8 * 1024;  // split-KV prefill partials: nsplit * S <= this many positions
 
 WsLayout make_layout(const lcc_model_config& c, int NP, int NT) {
@@ -69,6 +70,7 @@ WsLayout make_layout(const lcc_model_config& c, int NP, int NT) {
     L.rank = take((nt + 2) * 4);
     L.pf_part_o = take(kPrefillSplitRows * (size_t)c.q_heads * 128 * 4);
     L.pf_part_ml = take(kPrefillSplitRows * (size_t)c.q_heads * 2 * 4);
+    L.pf_splitk = take(kSplitKRows * (qkv_dim > (size_t)c.hidden ? qkv_dim : (size_t)c.hidden) * 4);
     L.h1 = take((size_t)c.hidden * 2);
     L.qkv1 = take(qkv_dim * 2);
     L.attn1 = take((size_t)c.q_heads * 128 * 2);
@@ -88,10 +90,12 @@ __global__ void fill_cu_seqlens_kernel(int* cu, int t, int hw) {
 }
 
 int gemm(lcc_model* m, const void* A, int lda, const void* B, int ldb, void* C, int ldc, int M, int N, int K,
-         const void* bias, const void* res, int ldr, int epi, cudaStream_t s) {
+         const void* bias, const void* res, int ldr, int epi, cudaStream_t s, void* splitk_ws = nullptr,
+         size_t splitk_ws_bytes = 0) {
     lcc::GemmArgs a;
     a.A = A; a.B = B; a.C = C; a.M = M; a.N = N; a.K = K; a.lda = lda; a.ldb = ldb; a.ldc = ldc;
     a.bias = bias; a.residual = res; a.ldr = ldr; a.epi = epi; a.block_n = 0;
+    a.splitk_ws = splitk_ws; a.splitk_ws_bytes = splitk_ws_bytes;  // used only with LIVECC_B200_GEMM_SPLITK=1
     return lcc::gemm_bf16_tn(a, m->ctx->num_sms, s);
 }
 
@@ -242,6 +246,8 @@ int lcc_prefill(lcc_model* m, const lcc_stream_state* st, const int64_t* ids, co
     bf16* hid = (bf16*)(ws + L.hid); bf16* normed = (bf16*)(ws + L.normed); bf16* qkv = (bf16*)(ws + L.qkv);
     bf16* attn = (bf16*)(ws + L.attn); bf16* act = (bf16*)(ws + L.act); int* rank = (int*)(ws + L.rank);
     const int H = c.hidden, Hq = c.q_heads, Hkv = c.kv_heads, qkv_dim = (Hq + 2 * Hkv) * 128;
+    void* skw = ws + L.pf_splitk;  // split-K scratch of the small-N projections (opt-in, see gemm_tcgen05.cu::try_splitk)
+    const size_t skb = kSplitKRows * (size_t)(qkv_dim > H ? qkv_dim : H) * 4;
 
     STEP(lcc::embed_gather(ids, (const bf16*)m->w.embed, (const bf16*)video_embeds, c.video_token_id, hid, rank,
                            st->scalars + LCC_SC_VIDEO_TOKENS, S, H, c.vocab, s), "embed gather");
@@ -250,16 +256,16 @@ int lcc_prefill(lcc_model* m, const lcc_stream_state* st, const int64_t* ids, co
         bf16* kc = (bf16*)st->k_pool + (size_t)i * st->layer_stride;
         bf16* vc = (bf16*)st->v_pool + (size_t)i * st->layer_stride;
         STEP(lcc::rmsnorm(hid, H, (const bf16*)lw.ln1_w, normed, H, S, H, c.rms_eps, s), "input_layernorm");
-        STEP(gemm(m, normed, H, lw.qkv_w, H, qkv, qkv_dim, S, qkv_dim, H, lw.qkv_b, nullptr, 0, lcc::EPI_BIAS, s), "qkv proj");
+        STEP(gemm(m, normed, H, lw.qkv_w, H, qkv, qkv_dim, S, qkv_dim, H, lw.qkv_b, nullptr, 0, lcc::EPI_BIAS, s, skw, skb), "qkv proj");
         STEP(lcc::mrope_kv_write(qkv, qkv_dim, pos3, S, m->w.text_inv_freq, c.mrope_t, c.mrope_h, Hq, Hkv, kc, vc,
                                  st->page_table, LCC_PAGE_SIZE, past, s), "mrope + kv write");
         STEP(lcc::attn_prefill_paged(qkv, qkv_dim, kc, vc, st->page_table, LCC_PAGE_SIZE, Hq, Hkv, S, past, attn,
                                      Hq * 128, (float*)(ws + L.pf_part_o), (float*)(ws + L.pf_part_ml),
                                      kPrefillSplitRows * (size_t)Hq, m->ctx->num_sms, 0, s), "prefill attention");
-        STEP(gemm(m, attn, Hq * 128, lw.o_w, Hq * 128, hid, H, S, H, Hq * 128, nullptr, hid, H, lcc::EPI_RESIDUAL, s), "o_proj");
+        STEP(gemm(m, attn, Hq * 128, lw.o_w, Hq * 128, hid, H, S, H, Hq * 128, nullptr, hid, H, lcc::EPI_RESIDUAL, s, skw, skb), "o_proj");
         STEP(lcc::rmsnorm(hid, H, (const bf16*)lw.ln2_w, normed, H, S, H, c.rms_eps, s), "post_attention_layernorm");
         STEP(gemm(m, normed, H, lw.gate_up_w, H, act, c.inter, S, 2 * c.inter, H, nullptr, nullptr, 0, lcc::EPI_SWIGLU, s), "gate_up");
-        STEP(gemm(m, act, c.inter, lw.down_w, c.inter, hid, H, S, H, c.inter, nullptr, hid, H, lcc::EPI_RESIDUAL, s), "down_proj");
+        STEP(gemm(m, act, c.inter, lw.down_w, c.inter, hid, H, S, H, c.inter, nullptr, hid, H, lcc::EPI_RESIDUAL, s, skw, skb), "down_proj");
     }
     // final norm + lm_head on the last position only (logits_to_keep = 1, gen/utils.py:2487-2491)
     STEP(lcc::gemv_norm_logits((const bf16*)m->w.lm_head, H, hid + (size_t)(S - 1) * H, (const bf16*)m->w.final_norm_w,

@@ -101,3 +101,24 @@ def test_gemm_strided_views(ctx):
     ref = (a.float() @ b.float().T).to(torch.bfloat16)
     assert torch.equal(big_c[:, 64:64 + N], ref)
     assert big_c[:, :64].abs().sum().item() == 0 and big_c[:, 64 + N:].abs().sum().item() == 0
+
+
+@pytest.mark.skipif(__import__("os").environ.get("LIVECC_B200_GEMM_SPLITK") != "1",
+                    reason="experimental split-K path: run with LIVECC_B200_GEMM_SPLITK=1 (not yet validated on hardware)")
+@pytest.mark.parametrize("M,N,K", [(281, 3584, 18944), (281, 3584, 3584), (281, 4608, 3584), (64, 256, 2048), (384, 136, 4096)])
+def test_gemm_splitk_exact_integer_operands(ctx, M, N, K):
+    """split-K (fp32 partial tiles + reduce kernel with the fused epilogue): integer operands keep every partial sum
+    exact, so the result must be bit-identical to the unsplit reference for all four supported epilogues."""
+    a = _ints((M, K), -2, 2, 11)
+    b = _ints((N, K), -1, 1, 12)
+    bias = _ints((N,), -8, 8, 13)
+    res = _ints((M, N), -8, 8, 14)
+    ws = torch.empty((8 * M * N,), dtype=torch.float32, device="cuda")
+    acc = a.float() @ b.float().T
+    assert torch.equal(ctx.gemm(a, b, splitk_ws=ws), acc.to(torch.bfloat16))
+    assert torch.equal(ctx.gemm(a, b, bias=bias, epilogue=A.EPI_BIAS, splitk_ws=ws), (acc + bias.float()).to(torch.bfloat16))
+    out = res.clone()  # in place: residual aliases the output, as in the decoder
+    ctx.gemm(a, b, out=out, residual=out, epilogue=A.EPI_RESIDUAL, splitk_ws=ws)
+    assert torch.equal(out, (acc.to(torch.bfloat16).float() + res.float()).to(torch.bfloat16))
+    out = ctx.gemm(a, b, bias=bias, residual=res, epilogue=A.EPI_BIAS_RESIDUAL, splitk_ws=ws)
+    assert torch.equal(out, ((acc + bias.float()).to(torch.bfloat16).float() + res.float()).to(torch.bfloat16))
