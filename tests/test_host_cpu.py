@@ -300,3 +300,39 @@ def test_cv2_reader_on_a_real_demo_video():
     assert idxs == sorted(idxs) and float(clip.float().std()) > 5.0  # real picture content
     px, grid = __import__("livecc_b200.processing", fromlist=["patchify_video"]).patchify_video(clip)
     assert grid.tolist() == [[3, 28, 52]] and px.shape == (3 * 28 * 52, 1176)
+
+
+def test_op_wrappers_pass_as_many_arguments_as_the_header_declares():
+    """ctypes does no arity checking: a wrapper that drifts from include/livecc_b200.h would corrupt the call
+    silently. Drive the wrappers with a recording `call` and CPU tensors and compare with the prototypes."""
+    import ctypes as C
+    import re
+    from pathlib import Path
+
+    import torch
+
+    from livecc_b200 import _cabi
+
+    header = (Path(__file__).resolve().parents[1] / "include" / "livecc_b200.h").read_text()
+
+    def declared(fn):
+        return len(re.search(fn + r"\((.*?)\);", header, re.S).group(1).split(","))
+
+    ctx = object.__new__(_cabi.Context)
+    calls = []
+    ctx.call = lambda name, *args: calls.append((name, len(args)))
+    ctx.stream_ptr = lambda: C.c_void_p(0)
+    bf = torch.bfloat16
+    a, b = torch.zeros((4, 8), dtype=bf), torch.zeros((16, 8), dtype=bf)
+    ctx.gemm(a, b)
+    ctx.gemm(a, b, splitk_ws=torch.zeros(64))
+    qkv, cu = torch.zeros((8, 3 * 2 * 80), dtype=bf), torch.tensor([0, 8], dtype=torch.int32)
+    ctx.vit_attention(qkv, cu, 8, 2, 80)
+    ctx.vit_attention(qkv, cu, 8, 2, 80, impl=1)
+    q, kv = torch.zeros((3, 8 * 128), dtype=bf), torch.zeros((2, 2, 64, 128), dtype=bf)
+    pt = torch.zeros(2, dtype=torch.int32)
+    ctx.attn_prefill(q, kv, kv, pt, 4, 2, 0)
+    ctx.attn_prefill(q, kv, kv, pt, 4, 2, 0, impl=1, split=True)
+    assert len(calls) == 6
+    for name, nargs in calls:
+        assert nargs + 1 == declared(name), (name, nargs + 1, declared(name))  # + the ctx argument added by call()
