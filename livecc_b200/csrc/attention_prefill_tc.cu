@@ -34,7 +34,7 @@ constexpr int OFF_V = OFF_K + STAGES * KV_BYTES;
 constexpr int OFF_P = OFF_V + STAGES * KV_BYTES;
 constexpr int OFF_BAR = OFF_P + P_BYTES;
 constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
-constexpr int COL_S = 0, COL_O = 2 * BN, TMEM_COLS = 256;
+constexpr int COL_S = 0, COL_O = 2 * BN, COL_P = 256;  // P (32 columns of packed bf16x2) only in the PTMEM variant
 constexpr float RESCALE_THRESHOLD = 8.f;
 }  // namespace ptc
 
@@ -55,10 +55,14 @@ __device__ __forceinline__ float ex2_ftz_p(float x) {
     return y;
 }
 
+// PTMEM: P goes to TMEM (tcgen05.st) and P.V reads its A operand from TMEM instead of staging P in shared memory
+// (experimental, LIVECC_B200_ATTN_PTMEM=1: written without GPU time at the end of round 1, not validated yet).
+template <bool PTMEM>
 __global__ void __launch_bounds__(192, 1)
 attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                        const __grid_constant__ CUtensorMap tmap_v, PrefillTcParams p) {
     using namespace ptc;
+    constexpr int TMEM_COLS = PTMEM ? 512 : 256;
     const int kvh = blockIdx.y, split = blockIdx.z;
     const int pos0 = blockIdx.x * p.PT;
     if (pos0 >= p.S) return;
@@ -183,10 +187,13 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
                 const uint32_t v_addr = smem_u32(smem + OFF_V + st * KV_BYTES);
                 const uint64_t dp = make_sw128_kmajor_desc(p_addr);
 #pragma unroll
-                for (int ks = 0; ks < BN / 16; ++ks)  // 16 tokens per MMA: +32 B in P rows, +16 token rows in V
-                    umma_bf16_ss(tmem_base + COL_O, dp + (uint64_t)(2 * ks),
-                                 make_sw128_mnmajor_desc(v_addr + ks * (16 * 128), KV_ATOM_BYTES), idesc_pv,
-                                 (i | ks) ? 1u : 0u);
+                for (int ks = 0; ks < BN / 16; ++ks) {  // 16 tokens per MMA: +32 B in P rows, +16 token rows in V
+                    const uint64_t dv = make_sw128_mnmajor_desc(v_addr + ks * (16 * 128), KV_ATOM_BYTES);
+                    if constexpr (PTMEM)
+                        umma_bf16_ts(tmem_base + COL_O, tmem_base + COL_P + ks * 8, dv, idesc_pv, (i | ks) ? 1u : 0u);
+                    else
+                        umma_bf16_ss(tmem_base + COL_O, dp + (uint64_t)(2 * ks), dv, idesc_pv, (i | ks) ? 1u : 0u);
+                }
                 umma_commit(&kv_empty[st]);
                 umma_commit(pv_done);
             }
@@ -271,12 +278,18 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
                     tmem_st_wait();
                 }
             }
-            // P row (64 keys = one 128-byte swizzled row: 16-byte chunk index XOR (row & 7))
+            if constexpr (PTMEM) {
+                // P row -> TMEM: word j = keys (2j, 2j+1), lane = row (the A-operand layout of kind::f16)
+                tmem_st_32x32b_x32(tmem_base + COL_P + lane_off, pk);
+                tmem_st_wait();
+            } else {
+                // P row (64 keys = one 128-byte swizzled row: 16-byte chunk index XOR (row & 7))
 #pragma unroll
-            for (int c = 0; c < 8; ++c)
-                *reinterpret_cast<uint4*>(p_row + ((c ^ sw) << 4)) =
-                    make_uint4(pk[c * 4], pk[c * 4 + 1], pk[c * 4 + 2], pk[c * 4 + 3]);
-            fence_proxy_async_smem();
+                for (int c = 0; c < 8; ++c)
+                    *reinterpret_cast<uint4*>(p_row + ((c ^ sw) << 4)) =
+                        make_uint4(pk[c * 4], pk[c * 4 + 1], pk[c * 4 + 2], pk[c * 4 + 3]);
+                fence_proxy_async_smem();
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(p_full);
@@ -329,7 +342,7 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, ptc::TMEM_COLS);
+        tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
 
@@ -357,15 +370,23 @@ int attn_prefill_tc(const bf16* q, int q_ld, const bf16* kc, const bf16* vc, con
     const int64_t pool_rows = (int64_t)1 << 31;  // page ids come from the page table; no meaningful row bound here
     if (make_tmap_bf16_2d_box(&tk, kc, pool_rows, D, D, 64, BN, false)) return -11;
     if (make_tmap_bf16_2d_box(&tv, vc, pool_rows, D, D, 64, BN, false)) return -11;
-    static bool set = false;
-    if (!set) {
-        if (cudaFuncSetAttribute(attn_prefill_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) !=
-            cudaSuccess)
+    static int ptmem = -1;
+    if (ptmem < 0) {
+        const char* pe = getenv("LIVECC_B200_ATTN_PTMEM");
+        ptmem = (pe && pe[0] == '1') ? 1 : 0;
+        if (cudaFuncSetAttribute(attn_prefill_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) !=
+                cudaSuccess ||
+            cudaFuncSetAttribute(attn_prefill_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) !=
+                cudaSuccess) {
+            ptmem = -1;
             return -12;
-        set = true;
+        }
     }
     PrefillTcParams p{out, o_ld, page_table, Hkv, G, PT, S, past, 1.4426950408889634f / sqrtf((float)D), nsplit, part_o, part_ml};
-    attn_prefill_tc_kernel<<<dim3(q_tiles, Hkv, nsplit), 192, SMEM_BYTES, s>>>(tq, tk, tv, p);
+    if (ptmem)
+        attn_prefill_tc_kernel<true><<<dim3(q_tiles, Hkv, nsplit), 192, SMEM_BYTES, s>>>(tq, tk, tv, p);
+    else
+        attn_prefill_tc_kernel<false><<<dim3(q_tiles, Hkv, nsplit), 192, SMEM_BYTES, s>>>(tq, tk, tv, p);
     *nsplit_out = nsplit;
     return 0;
 }

@@ -30,9 +30,12 @@ constexpr int Q_SLAB_BYTES = BM * 32;
 constexpr int Q_BYTES = DSLABS * Q_SLAB_BYTES;
 constexpr float RESCALE_THRESHOLD = 8.f;  // log2 units: P stays <= 2^8 between rescales
 // BN = keys per tile. BN=128: one CTA per SM (512 TMEM columns); BN=64: two CTAs per SM (256 columns, <= 113 KB smem)
-template <int BN_, int STAGES_>
+// PTMEM: P goes to TMEM (tcgen05.st) and P.V reads its A operand from TMEM instead of staging P in shared memory
+// (experimental, LIVECC_B200_ATTN_PTMEM=1: written without GPU time at the end of round 1, not validated yet).
+template <int BN_, int STAGES_, bool PTMEM_ = false>
 struct Cfg {
     static constexpr int BN = BN_, STAGES = STAGES_;
+    static constexpr bool PTMEM = PTMEM_;
     static constexpr int KV_SLAB_BYTES = BN * 32;                // [BN keys][16 bf16]
     static constexpr int KV_BYTES = DSLABS * KV_SLAB_BYTES;      // one K or V tile
     static constexpr int PSLABS = BN / SLAB_COLS;                // P: PSLABS slabs of [128 rows][16 keys]
@@ -44,6 +47,7 @@ struct Cfg {
     static constexpr int OFF_BAR = OFF_P + PSLABS * P_SLAB_BYTES;
     static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;  // + barriers + alignment slack
     static constexpr int COL_S = 0, COL_O = 2 * BN;
+    static constexpr int COL_P = COL_O + 96;  // BN/2 columns of packed bf16x2 (PTMEM only); 2*BN + 96 + BN/2 <= TMEM_COLS
     static constexpr int TMEM_COLS = (2 * BN + D) > 256 ? 512 : 256;
     static constexpr int MIN_CTAS = TMEM_COLS == 256 ? 2 : 1;
 };
@@ -173,10 +177,14 @@ vit_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
                 const int st = t % STAGES;
                 const uint32_t v_addr = smem_u32(smem + OFF_V + st * KV_BYTES);
 #pragma unroll
-                for (int ks = 0; ks < PSLABS; ++ks)
-                    umma_bf16_ss(tmem_base + COL_O, make_sw32_desc(p_addr + ks * P_SLAB_BYTES, 16, 256),
-                                 make_sw32_desc(v_addr + ks * (SLAB_COLS * 32), KV_SLAB_BYTES, 256), idesc_pv,
-                                 (t | ks) ? 1u : 0u);
+                for (int ks = 0; ks < PSLABS; ++ks) {
+                    const uint64_t dv = make_sw32_desc(v_addr + ks * (SLAB_COLS * 32), KV_SLAB_BYTES, 256);
+                    if constexpr (C::PTMEM)  // A = P from TMEM: 16 keys = 8 columns of packed bf16x2 per MMA
+                        umma_bf16_ts(tmem_base + COL_O, tmem_base + C::COL_P + ks * 8, dv, idesc_pv, (t | ks) ? 1u : 0u);
+                    else
+                        umma_bf16_ss(tmem_base + COL_O, make_sw32_desc(p_addr + ks * P_SLAB_BYTES, 16, 256), dv, idesc_pv,
+                                     (t | ks) ? 1u : 0u);
+                }
                 umma_commit(&kv_empty[st]);
                 umma_commit(pv_done);
             }
@@ -265,16 +273,28 @@ vit_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
                     tmem_st_wait();
                 }
             }
-            // P row -> smem slabs (16 keys per slab; 16-byte chunk index XOR address bit 7)
+            if constexpr (C::PTMEM) {
+                // P row -> TMEM: word j of the row = keys (2j, 2j+1), lane = row (the A-operand layout of kind::f16)
 #pragma unroll
-            for (int ks = 0; ks < PSLABS; ++ks)
+                for (int c = 0; c < BN / 64; ++c) {
+                    uint32_t w32[32];
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    const int w = ks * 8 + c * 4;
-                    *reinterpret_cast<uint4*>(p_row + ks * P_SLAB_BYTES + ((c ^ sw) << 4)) =
-                        make_uint4(pk[w], pk[w + 1], pk[w + 2], pk[w + 3]);
+                    for (int j = 0; j < 32; ++j) w32[j] = pk[c * 32 + j];
+                    tmem_st_32x32b_x32(tmem_base + C::COL_P + c * 32 + lane_off, w32);
                 }
-            fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the MMA (async proxy)
+                tmem_st_wait();
+            } else {
+                // P row -> smem slabs (16 keys per slab; 16-byte chunk index XOR address bit 7)
+#pragma unroll
+                for (int ks = 0; ks < PSLABS; ++ks)
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const int w = ks * 8 + c * 4;
+                        *reinterpret_cast<uint4*>(p_row + ks * P_SLAB_BYTES + ((c ^ sw) << 4)) =
+                            make_uint4(pk[w], pk[w + 1], pk[w + 2], pk[w + 3]);
+                    }
+                fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the MMA (async proxy)
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(p_full);
@@ -358,6 +378,15 @@ int vit_attention_tc(const bf16* qkv, int ld, int64_t n_rows, bf16* out, int o_l
     cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, dev);
     const char* e = getenv("LIVECC_B200_VIT_TC_BN");  // tuning hook: force keys per tile (64 | 128)
     const int variant = e ? atoi(e) : ((int)(grid.x * grid.y * grid.z) <= dev_sms ? 128 : 64);
+    static int ptmem = -1;
+    if (ptmem < 0) {
+        const char* pe = getenv("LIVECC_B200_ATTN_PTMEM");
+        ptmem = (pe && pe[0] == '1') ? 1 : 0;
+    }
+    if (ptmem) {
+        if (variant == 128) return launch_tc<Cfg<128, 3, true>>(qkv, ld, n_rows, p, grid, s);
+        return launch_tc<Cfg<64, 3, true>>(qkv, ld, n_rows, p, grid, s);
+    }
     if (variant == 128) return launch_tc<Cfg<128, 3>>(qkv, ld, n_rows, p, grid, s);
     return launch_tc<Cfg<64, 3>>(qkv, ld, n_rows, p, grid, s);
 }
