@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define LCC_ABI_VERSION 6
+#define LCC_ABI_VERSION 7
 #define LCC_PAGE_SIZE 64
 
 typedef struct lcc_ctx lcc_ctx;
@@ -110,9 +110,12 @@ int lcc_vit_attention(lcc_ctx* ctx, const void* qkv, int ld, int64_t n_rows, voi
                       lcc_stream_t stream);
 
 /* embed_tokens gather + masked_scatter of the video features (mq2vl.py:1255-1272).
- * ids: device int64[S]; rank_ws: device int32[S+1] scratch (last entry receives the video-token count). */
+ * ids: device int64[S]; video_embeds: bf16 [n_video_rows, H] or NULL (then placeholders keep their text embedding,
+ * as in the reference when no pixel values are passed); placeholders beyond n_video_rows also keep their text
+ * embedding (nothing is read out of bounds; the caller compares the count and raises like mq2vl.py:1169-1175).
+ * rank_ws: device int32[S+1] scratch (last entry receives the video-token count). */
 int lcc_embed_gather(lcc_ctx* ctx, const int64_t* ids, const void* table, const void* video_embeds,
-                     int64_t video_token_id, void* out, int32_t* rank_ws, int S, int H, int64_t vocab,
+                     int n_video_rows, int64_t video_token_id, void* out, int32_t* rank_ws, int S, int H, int64_t vocab,
                      lcc_stream_t stream);
 
 /* M-RoPE (mq2vl.py:188-201,212-254) on the q and k parts of qkv [S, (Hq+2Hkv)*128] (q rotated in
@@ -165,6 +168,8 @@ typedef struct {
     int32_t max_new_tokens;
     float inv_repetition_penalty; /* fp32(1.0 / (double)penalty): torch's CUDA `tensor / python_float` multiplies by
                                      this value (measured: tools/penalty_probe.py); 0 = derive as 1.0f / repetition_penalty */
+    int32_t eos_token_id2;        /* second stop id (generation_config.json eos_token_id = [151645, 151643] in the
+                                     Qwen2-VL family; gen/utils.py stops on any of them), < 0 = none */
 } lcc_sampling;
 
 int lcc_sample_greedy(lcc_ctx* ctx, const float* logits_raw, float* logits_proc, int V, int64_t* seq,
@@ -238,10 +243,10 @@ int lcc_vit_forward_frames(lcc_model* m, const uint8_t* frames, int T, int H, in
 
 /* Prefill of S new tokens (Qwen2VLModel.forward + lm_head on the last token, mq2vl.py:1230-1300,
  * 828-910, 1437) followed by the first token selection. ids: device int64[S] (the new tokens);
- * pos3: device int32[3,S]; video_embeds: bf16 [n_video_tokens, hidden] or NULL; past = tokens already
+ * pos3: device int32[3,S]; video_embeds: bf16 [n_video_rows, hidden] or NULL; past = tokens already
  * cached. Host must have set scalars {KV_LEN = past+S, ROPE_POS, FINISHED=0, N_GENERATED=0, SEQ_LEN}. */
 int lcc_prefill(lcc_model* m, const lcc_stream_state* st, const int64_t* ids, const int32_t* pos3, int S,
-                int past, const void* video_embeds, const lcc_sampling* sp, lcc_stream_t stream);
+                int past, const void* video_embeds, int n_video_rows, const lcc_sampling* sp, lcc_stream_t stream);
 
 /* n_steps x (one-token forward + token selection) (the loop body of _sample, gen/utils.py:2743-2805).
  * No-ops once scalars[LCC_SC_FINISHED] is set. Capturable in a CUDA graph. nsplit: KV splits (1..64). */

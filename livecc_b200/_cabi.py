@@ -13,7 +13,7 @@ PKG_DIR = Path(__file__).resolve().parent
 LIB_PATH = PKG_DIR / "liblivecc_sm100a.so"
 HEADER_PATH = PKG_DIR.parent / "include" / "livecc_b200.h"
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 PAGE_SIZE = 64
 
 # epilogue codes (LCC_EPI_*)
@@ -30,7 +30,7 @@ class LiveCCNativeError(RuntimeError):
 class Sampling(C.Structure):
     _fields_ = [("repetition_penalty", C.c_float), ("thr_token", C.c_int32), ("thr_base", C.c_float),
                 ("thr_step", C.c_float), ("eos_token_id", C.c_int32), ("max_new_tokens", C.c_int32),
-                ("inv_repetition_penalty", C.c_float)]
+                ("inv_repetition_penalty", C.c_float), ("eos_token_id2", C.c_int32)]
 
 
 class ModelConfig(C.Structure):
@@ -225,7 +225,8 @@ class Context:
         S, H = ids.numel(), table.shape[1]
         out = torch.empty((S, H), dtype=torch.bfloat16, device=table.device)
         rank = torch.empty((S + 2,), dtype=torch.int32, device=table.device)
-        self.call("lcc_embed_gather", _ptr(ids), _ptr(table), _ptr(video_embeds), C.c_int64(video_token_id), _ptr(out),
+        n_rows = video_embeds.shape[0] if video_embeds is not None else 0
+        self.call("lcc_embed_gather", _ptr(ids), _ptr(table), _ptr(video_embeds), _i(n_rows), C.c_int64(video_token_id), _ptr(out),
                   _ptr(rank), _i(S), _i(H), C.c_int64(table.shape[0]), self.stream_ptr())
         return out, rank
 
@@ -346,7 +347,8 @@ class NativeModel:
         self._call("lcc_vit_forward_frames", _ptr(frames_u8), _i(T), _i(H), _i(W), m, sd, _ptr(out), Context.stream_ptr())
 
     def prefill(self, st: StreamState, ids, pos3, S, past, video_embeds, sampling: Sampling):
-        self._call("lcc_prefill", C.byref(st), _ptr(ids), _ptr(pos3), _i(S), _i(past), _ptr(video_embeds),
+        n_rows = video_embeds.shape[0] if video_embeds is not None else 0
+        self._call("lcc_prefill", C.byref(st), _ptr(ids), _ptr(pos3), _i(S), _i(past), _ptr(video_embeds), _i(n_rows),
                    C.byref(sampling), Context.stream_ptr())
 
     def decode_steps(self, st: StreamState, n_steps, nsplit, sampling: Sampling):

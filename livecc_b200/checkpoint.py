@@ -93,13 +93,50 @@ def hf_param_specs(cfg: LiveCCConfig) -> List[Tuple[str, Tuple[int, ...], str]]:
     return specs
 
 
+def _sharp_permutation(cfg: LiveCCConfig, device) -> torch.Tensor:
+    """pi over the text ids [0, P) (P = first special id): pi(i) = (A*i + B) mod P, A coprime with P."""
+    import math
+
+    P = min(cfg.bos_token_id, cfg.eos_token_id, cfg.im_start_token_id, cfg.text_config.vocab_size)
+    A = 48271
+    while math.gcd(A, P) != 1:
+        A += 2
+    i = torch.arange(P, dtype=torch.int64, device=device)
+    return (i * A + 12345) % P
+
+
+def sharp_chain(cfg: LiveCCConfig, start: int, n: int) -> List[int]:
+    """The id chain a `sharp` checkpoint generates after `start` (ignoring the EOS swap): pi(start), pi^2(start), ..."""
+    pi = _sharp_permutation(cfg, "cpu")
+    out, t = [], int(start)
+    for _ in range(n):
+        t = int(pi[t])
+        out.append(t)
+    return out
+
+
 def synthetic_tensors(cfg: LiveCCConfig, seed: int = 1234, dtype=torch.bfloat16, device="cpu",
-                      gen_device=None) -> Iterator[Tuple[str, torch.Tensor]]:
+                      gen_device=None, sharp: bool = False, sharp_eos_after: int = 0) -> Iterator[Tuple[str, torch.Tensor]]:
     """Yields (hf_name, tensor). Weights ~ U(-a, a) with a = sqrt(3)*0.02*sqrt(1024/fan_in) capped
     at 0.035 (std ~0.02 at fan_in <= 1024, variance-preserving beyond); biases U(-0.02, 0.02);
-    norm weights 1 + U(-0.1, 0.1); norm biases U(-0.02, 0.02). Values are rounded once to `dtype`."""
+    norm weights 1 + U(-0.1, 0.1); norm biases U(-0.02, 0.02). Values are rounded once to `dtype`.
+
+    sharp=True builds the *sharp* variant used by the id-exactness tests. Random weights give nearly flat logits
+    (top-1/top-2 gap of a few bf16 ulps), so greedy ids flip between any two correct bf16 implementations. The sharp
+    variant gives the model a confident next-token distribution the way a trained LM has one: the embedding table is
+    scaled by 4*layers (the token direction then carries ~1/3..1/2 of the final hidden state's norm at 7B depth, the
+    28 layers the rest) and lm_head[pi(i)] = embed[i] for a fixed permutation pi of the text ids, so the top-1 logit
+    leads by several logit units (>> 10x the bf16 tolerance) while every other logit is still produced by the full
+    network. The generated ids then follow pi from the last prompt token -- which is the point: id-exactness over
+    hundreds of steps checks positions, cache, penalty and stop bookkeeping end to end, while numerics are checked by
+    the teacher-forced logit tolerance on the flat checkpoint. sharp_eos_after=k > 0 additionally routes the k-th
+    token of the chain that starts at the newline id (the last prompt token of the chat template) to EOS, so streams
+    stop early under CUDA-graph replay."""
     gen_device = gen_device or device
-    for idx, (name, shape, kind) in enumerate(hf_param_specs(cfg)):
+    specs = hf_param_specs(cfg)
+    embed_idx = next(i for i, sp in enumerate(specs) if sp[0].endswith("embed_tokens.weight"))
+
+    def fill(idx, shape, kind):
         numel = 1
         for s in shape:
             numel *= s
@@ -107,19 +144,111 @@ def synthetic_tensors(cfg: LiveCCConfig, seed: int = 1234, dtype=torch.bfloat16,
         if kind == "w":
             fan_in = numel // shape[0]
             a = min(0.0346, 0.0346 * (1024.0 / fan_in) ** 0.5)
-            x = u * (2.0 * a)
-        elif kind == "b":
-            x = u * 0.04
-        elif kind == "norm_w":
-            x = u * 0.2 + 1.0
+            return u * (2.0 * a)
+        if kind == "b":
+            return u * 0.04
+        if kind == "norm_w":
+            return u * 0.2 + 1.0
+        return u * 0.04
+
+    for idx, (name, shape, kind) in enumerate(specs):
+        if sharp and name == "lm_head.weight":
+            emb = fill(embed_idx, specs[embed_idx][1], "w").view(specs[embed_idx][1])
+            pi = _sharp_permutation(cfg, emb.device)
+            x = fill(idx, shape, kind).view(shape)      # special-id rows keep their random fill
+            x[pi] = emb[: pi.numel()]                    # lm_head[pi(i)] = embed[i]
+            if sharp_eos_after > 0:
+                chain = sharp_chain(cfg, cfg.newline_token_id, sharp_eos_after)
+                src = chain[-2] if sharp_eos_after > 1 else cfg.newline_token_id   # token whose successor becomes EOS
+                nxt = chain[-1]
+                x[cfg.eos_token_id] = emb[src]
+                x[nxt] = emb[cfg.eos_token_id]
+            x = x.reshape(-1)
         else:
-            x = u * 0.04
+            x = fill(idx, shape, kind)
+            if sharp and idx == embed_idx:
+                x = x * (4.0 * cfg.text_config.num_hidden_layers)
         yield name, x.to(dtype).view(shape).to(device)
 
 
 def synthetic_state_dict(cfg: LiveCCConfig, seed: int = 1234, dtype=torch.bfloat16, device="cpu",
-                         gen_device=None) -> Dict[str, torch.Tensor]:
-    return dict(synthetic_tensors(cfg, seed, dtype, device, gen_device))
+                         gen_device=None, sharp: bool = False, sharp_eos_after: int = 0) -> Dict[str, torch.Tensor]:
+    return dict(synthetic_tensors(cfg, seed, dtype, device, gen_device, sharp, sharp_eos_after))
+
+
+# --------------------------------------------------------------------------------------------
+# HF checkpoint directories (config.json, generation_config.json, *.safetensors)
+# --------------------------------------------------------------------------------------------
+def config_from_hf_json(d: dict) -> LiveCCConfig:
+    """config.json of a Qwen2-VL / LiveCC checkpoint (flat 4.x layout or nested 5.x `text_config`) -> LiveCCConfig."""
+    from .config import TextConfig, VisionConfig
+
+    tc = d.get("text_config", d)
+    vc = d.get("vision_config", {})
+    rp = tc.get("rope_parameters") or tc.get("rope_scaling") or d.get("rope_scaling") or {}
+    text = TextConfig(
+        vocab_size=tc.get("vocab_size", 152064), hidden_size=tc.get("hidden_size", 3584),
+        intermediate_size=tc.get("intermediate_size", 18944), num_hidden_layers=tc.get("num_hidden_layers", 28),
+        num_attention_heads=tc.get("num_attention_heads", 28), num_key_value_heads=tc.get("num_key_value_heads", 4),
+        rms_norm_eps=tc.get("rms_norm_eps", 1e-6), rope_theta=rp.get("rope_theta", tc.get("rope_theta", 1e6)),
+        mrope_section=tuple(rp.get("mrope_section", (16, 24, 24))))
+    vis = VisionConfig(
+        depth=vc.get("depth", 32), embed_dim=vc.get("embed_dim", 1280), hidden_size=vc.get("hidden_size", text.hidden_size),
+        mlp_ratio=vc.get("mlp_ratio", 4), num_heads=vc.get("num_heads", 16), in_channels=vc.get("in_channels", 3),
+        patch_size=vc.get("patch_size", 14), spatial_merge_size=vc.get("spatial_merge_size", 2),
+        temporal_patch_size=vc.get("temporal_patch_size", 2))
+    eos = d.get("eos_token_id", tc.get("eos_token_id", 151645))
+    cfg = LiveCCConfig(
+        text_config=text, vision_config=vis, image_token_id=d.get("image_token_id", 151655),
+        video_token_id=d.get("video_token_id", 151656), vision_start_token_id=d.get("vision_start_token_id", 151652),
+        vision_end_token_id=d.get("vision_end_token_id", 151653), bos_token_id=d.get("bos_token_id", tc.get("bos_token_id", 151643)),
+        eos_token_id=eos[0] if isinstance(eos, (list, tuple)) else eos, name=d.get("_name_or_path", "livecc"))
+    cfg.tie_word_embeddings = bool(d.get("tie_word_embeddings", tc.get("tie_word_embeddings", False)))
+    return cfg
+
+
+def read_hf_configs(model_path: str) -> Tuple[LiveCCConfig, dict]:
+    """(LiveCCConfig, generation_config dict) of a checkpoint directory; LiveCC-7B defaults if a file is absent."""
+    import json
+    import os
+
+    cfg = LiveCCConfig.livecc_7b()
+    p = os.path.join(model_path, "config.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            cfg = config_from_hf_json(json.load(f))
+    gen = {}
+    p = os.path.join(model_path, "generation_config.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            gen = json.load(f)
+    return cfg, gen
+
+
+def canonical_hf_name(name: str) -> str:
+    """Maps pre-5.x parameter names (`visual.*`, `model.layers.*`, `model.embed_tokens.*`, `model.norm.*`) to the
+    5.x names (`model.visual.*`, `model.language_model.*`) that hf_param_specs() uses."""
+    if name.startswith("visual."):
+        return "model." + name
+    if name.startswith("model.") and not name.startswith(("model.visual.", "model.language_model.")):
+        return "model.language_model." + name[len("model."):]
+    return name
+
+
+def iter_hf_checkpoint(model_path: str) -> Iterator[Tuple[str, torch.Tensor]]:
+    """Streams (canonical_name, tensor) from every *.safetensors file of a checkpoint directory."""
+    import glob
+    import os
+
+    from safetensors import safe_open
+
+    files = sorted(glob.glob(os.path.join(model_path, "*.safetensors")))
+    if not files:
+        raise FileNotFoundError(f"no *.safetensors under {model_path!r} (checkpoints cannot be downloaded offline)")
+    for f in files:
+        with safe_open(f, framework="pt") as sf:
+            for name in sf.keys():
+                yield canonical_hf_name(name), sf.get_tensor(name)
 
 
 # --------------------------------------------------------------------------------------------
@@ -210,7 +339,9 @@ def load_engine_weights(cfg: LiveCCConfig, tensors, device, dtype=torch.bfloat16
     def dev(x):
         return x.to(device=device, dtype=dtype).contiguous()
 
+    _seen: List[str] = []
     for name, ten in it:
+        _seen.append(name)
         if name.startswith("model.visual.blocks."):
             parts = name.split(".")
             vit[int(parts[3])][".".join(parts[4:])] = dev(ten)
@@ -232,6 +363,16 @@ def load_engine_weights(cfg: LiveCCConfig, tensors, device, dtype=torch.bfloat16
         else:
             misc[name] = dev(ten)
 
+    # explicit report instead of an opaque KeyError further down
+    expected = {n for n, _, _ in hf_param_specs(cfg)}
+    seen_names = set(_seen)
+    if getattr(cfg, "tie_word_embeddings", False) or ("lm_head.weight" not in seen_names
+                                                       and "model.language_model.embed_tokens.weight" in seen_names):
+        expected.discard("lm_head.weight")  # tied checkpoints (e.g. the 2B family) carry no lm_head tensor
+    missing, unexpected = sorted(expected - seen_names), sorted(seen_names - expected - {"lm_head.weight"})
+    if missing:
+        raise KeyError(f"checkpoint misses {len(missing)} tensors, e.g. {missing[:4]}"
+                       + (f"; unexpected names, e.g. {unexpected[:4]}" if unexpected else ""))
     V = "model.visual."
     w.patch_w = misc[V + "patch_embed.proj.weight"].reshape(v.embed_dim, v.patch_dim).contiguous()
     for d in vit:
@@ -251,5 +392,5 @@ def load_engine_weights(cfg: LiveCCConfig, tensors, device, dtype=torch.bfloat16
             o_w=d["self_attn.o_proj.weight"], ln2_w=d["post_attention_layernorm.weight"],
             gate_up_w=d["gate_up_w"], down_w=d["mlp.down_proj.weight"]))
     w.final_norm_w = misc[L + "norm.weight"]
-    w.lm_head = misc["lm_head.weight"]
+    w.lm_head = misc["lm_head.weight"] if "lm_head.weight" in misc else w.embed  # tie_word_embeddings
     return w

@@ -379,11 +379,8 @@ static int launch_flash(const FlashParams& p, dim3 grid, cudaStream_t s) {
     constexpr int LDS = D + 8;
     constexpr int smem = (64 + 4 * 64) * LDS * 2;
     auto kern = flash_fwd_kernel<D, CAUSAL, PAGED>;
-    static bool set = false;
-    if (!set) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -1;
-        set = true;
-    }
+    static SmemAttrOnce once;  // per instantiation
+    if (ensure_dyn_smem(once, kern, smem)) return -1;
     kern<<<grid, 128, smem, s>>>(p);
     return 0;
 }
@@ -558,12 +555,8 @@ int vit_attention(const bf16* qkv, int ld, int64_t n_rows, bf16* out, int o_ld, 
     const int ctas128 = ((max_seg_len + 127) / 128) * heads * nseg;
     if (cu_seqlens && ctas128 >= 2 * dev_sms) {
         constexpr int smem = (128 + 4 * 64) * 88 * 2;
-        static bool set = false;
-        if (!set) {
-            if (cudaFuncSetAttribute(vit_flash_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
-                return -2;
-            set = true;
-        }
+        static SmemAttrOnce once;
+        if (ensure_dyn_smem(once, vit_flash_kernel<2>, smem)) return -2;
         vit_flash_kernel<2><<<dim3((max_seg_len + 127) / 128, heads, nseg), 128, smem, s>>>(p);
         return 0;
     }
@@ -973,12 +966,8 @@ int attn_decode(bf16* qkv, bf16* kc, bf16* vc, const int* page_table, int page_s
                 float* part_o, float* part_ml, int* counters, bf16* out, bool pdl, cudaStream_t s) {
     if (page_size != 64 || Hq % Hkv || Hq / Hkv > 8) return -1;
     constexpr int smem = (16 + 4 * 64) * 136 * 2;
-    static bool set = false;
-    if (!set) {
-        if (cudaFuncSetAttribute(attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
-            return -2;
-        set = true;
-    }
+    static SmemAttrOnce once;
+    if (ensure_dyn_smem(once, attn_decode_kernel, smem)) return -2;
     DecodeAttnParams p{};
     p.qkv = qkv; p.kc = kc; p.vc = vc; p.page_table = page_table; p.kv_len = kv_len; p.rope_pos = rope_pos;
     p.finished = finished; p.inv_freq = inv_freq; p.Hq = Hq; p.Hkv = Hkv; p.nsplit = nsplit;
@@ -996,12 +985,8 @@ int attn_oproj_decode(bf16* qkv, bf16* kc, bf16* vc, const int* page_table, int 
     if (page_size != 64 || Hq % Hkv || Hq / Hkv > 8) return -1;
     constexpr int smem = (16 + 4 * 64) * 136 * 2;
     if (Hq * 128 * 2 > smem) return -4;
-    static bool set = false;
-    if (!set) {
-        if (cudaFuncSetAttribute(attn_oproj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
-            return -2;
-        set = true;
-    }
+    static SmemAttrOnce once;
+    if (ensure_dyn_smem(once, attn_oproj_kernel, smem)) return -2;
     DecodeAttnParams p{};
     p.qkv = qkv; p.kc = kc; p.vc = vc; p.page_table = page_table; p.kv_len = kv_len; p.rope_pos = rope_pos;
     p.finished = finished; p.inv_freq = inv_freq; p.Hq = Hq; p.Hkv = Hkv; p.nsplit = nsplit;

@@ -374,14 +374,11 @@ int attn_prefill_tc(const bf16* q, int q_ld, const bf16* kc, const bf16* vc, con
     if (ptmem < 0) {
         const char* pe = getenv("LIVECC_B200_ATTN_PTMEM");
         ptmem = (pe && pe[0] == '1') ? 1 : 0;
-        if (cudaFuncSetAttribute(attn_prefill_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) !=
-                cudaSuccess ||
-            cudaFuncSetAttribute(attn_prefill_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) !=
-                cudaSuccess) {
-            ptmem = -1;
-            return -12;
-        }
     }
+    static SmemAttrOnce once_a, once_b;
+    if (ensure_dyn_smem(once_a, attn_prefill_tc_kernel<false>, SMEM_BYTES) ||
+        ensure_dyn_smem(once_b, attn_prefill_tc_kernel<true>, SMEM_BYTES))
+        return -12;
     PrefillTcParams p{out, o_ld, page_table, Hkv, G, PT, S, past, 1.4426950408889634f / sqrtf((float)D), nsplit, part_o, part_ml};
     if (ptmem)
         attn_prefill_tc_kernel<true><<<dim3(q_tiles, Hkv, nsplit), 192, SMEM_BYTES, s>>>(tq, tk, tv, p);

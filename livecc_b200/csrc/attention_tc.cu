@@ -353,12 +353,8 @@ static int launch_tc(const bf16* qkv, int ld, int64_t n_rows, const VitTcParams&
     if (make_tmap_bf16_2d_box(&tq, qkv, n_rows, (int64_t)3 * p.heads * D, ld, SLAB_COLS, BM, /*swizzle32=*/true)) return -10;
     if (make_tmap_bf16_2d_box(&tkv, qkv, n_rows, (int64_t)3 * p.heads * D, ld, SLAB_COLS, C::BN, true)) return -11;
     auto kern = vit_attn_tc_kernel<C>;
-    static bool set = false;  // per instantiation
-    if (!set) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) != cudaSuccess)
-            return -12;
-        set = true;
-    }
+    static SmemAttrOnce once;  // per instantiation
+    if (ensure_dyn_smem(once, kern, C::SMEM_BYTES)) return -12;
     kern<<<grid, 192, C::SMEM_BYTES, s>>>(tq, tkv, p);
     return 0;
 }

@@ -93,9 +93,9 @@ int lcc_vit_attention(lcc_ctx* ctx, const void* qkv, int ld, int64_t n_rows, voi
 }
 
 int lcc_embed_gather(lcc_ctx* ctx, const int64_t* ids, const void* table, const void* video_embeds,
-                     int64_t video_token_id, void* out, int32_t* rank_ws, int S, int H, int64_t vocab,
+                     int n_video_rows, int64_t video_token_id, void* out, int32_t* rank_ws, int S, int H, int64_t vocab,
                      lcc_stream_t stream) {
-    OP_RET(ctx, lcc::embed_gather(ids, (const bf16*)table, (const bf16*)video_embeds, video_token_id, (bf16*)out,
+    OP_RET(ctx, lcc::embed_gather(ids, (const bf16*)table, (const bf16*)video_embeds, n_video_rows, video_token_id, (bf16*)out,
                                   rank_ws, rank_ws + S, S, H, vocab, (cudaStream_t)stream), "lcc_embed_gather");
 }
 
@@ -164,7 +164,8 @@ int lcc_sample_greedy(lcc_ctx* ctx, const float* logits_raw, float* logits_proc,
     lcc::SampleArgs a{};
     a.logits_raw = logits_raw; a.logits_proc = logits_proc; a.V = V; a.seq = seq; a.scalars = scalars;
     a.repetition_penalty = sp->repetition_penalty; a.inv_repetition_penalty = sp->inv_repetition_penalty; a.thr_token = sp->thr_token; a.thr_base = sp->thr_base;
-    a.thr_step = sp->thr_step; a.eos_token_id = sp->eos_token_id; a.max_new_tokens = sp->max_new_tokens;
+    a.thr_step = sp->thr_step; a.eos_token_id = sp->eos_token_id; a.eos_token_id2 = sp->eos_token_id2;
+    a.max_new_tokens = sp->max_new_tokens;
     a.advance_kv = advance_kv; a.embed = (const bf16*)embed; a.h = (bf16*)h; a.H = H;
     OP_RET(ctx, lcc::sample_greedy(a, (cudaStream_t)stream), "lcc_sample_greedy");
 }

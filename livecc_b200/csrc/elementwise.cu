@@ -313,25 +313,27 @@ __global__ void video_rank_kernel(const int64_t* __restrict__ ids, int S, int64_
 
 __global__ void embed_gather_kernel(const int64_t* __restrict__ ids, const int* __restrict__ rank,
                                     const bf16* __restrict__ table, const bf16* __restrict__ video,
-                                    bf16* __restrict__ out, int S, int H, int64_t vocab) {
+                                    bf16* __restrict__ out, int S, int H, int64_t vocab, int n_video_rows) {
     const int row = blockIdx.x;
     if (row >= S) return;
     const int rk = rank[row];
     int64_t id = ids[row];
     if (id < 0) id = 0;
     if (id >= vocab) id = vocab - 1;
-    const bf16* src = rk >= 0 ? video + (size_t)rk * H : table + (size_t)id * H;
+    // A placeholder beyond the last feature row (more <|video_pad|> ids than ViT rows) keeps its text embedding:
+    // nothing is read past the end of `video`; the host raises on the count mismatch (mq2vl.py:1169-1175).
+    const bf16* src = (rk >= 0 && rk < n_video_rows) ? video + (size_t)rk * H : table + (size_t)id * H;
     bf16* dst = out + (size_t)row * H;
     for (int c = threadIdx.x * 8; c < H; c += blockDim.x * 8)
         *reinterpret_cast<uint4*>(dst + c) = *reinterpret_cast<const uint4*>(src + c);
 }
 
-int embed_gather(const int64_t* ids, const bf16* table, const bf16* video, int64_t video_id, bf16* out,
+int embed_gather(const int64_t* ids, const bf16* table, const bf16* video, int n_video_rows, int64_t video_id, bf16* out,
                  int* rank_ws, int* total_video, int S, int H, int64_t vocab, cudaStream_t s) {
     if (S <= 0) return 0;
     if (H % 8) return -1;
     video_rank_kernel<<<1, 1024, 0, s>>>(ids, S, video ? video_id : (int64_t)-1, rank_ws, total_video);
-    embed_gather_kernel<<<S, 128, 0, s>>>(ids, rank_ws, table, video, out, S, H, vocab);
+    embed_gather_kernel<<<S, 128, 0, s>>>(ids, rank_ws, table, video, out, S, H, vocab, video ? n_video_rows : 0);
     return 0;
 }
 

@@ -20,6 +20,7 @@
 
 #include "common.cuh"
 #include "gemm.h"
+#include "launch.h"
 
 namespace lcc {
 
@@ -334,13 +335,8 @@ static int launch_cfg(const GemmArgs& a, int num_sms, cudaStream_t stream) {
     if (make_tmap_bf16_2d(&ta, a.A, a.M, a.K, a.lda, BLOCK_M)) return -10;
     if (make_tmap_bf16_2d(&tb, a.B, a.N, a.K, a.ldb, BLOCK_N)) return -11;
     auto kern = gemm_bf16_tn_kernel<BLOCK_N, EPI>;
-    static bool attr_set = false;  // per template instantiation
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 Cfg::SMEM_BYTES) != cudaSuccess)
-            return -12;
-        attr_set = true;
-    }
+    static SmemAttrOnce once;  // per template instantiation
+    if (ensure_dyn_smem(once, kern, Cfg::SMEM_BYTES)) return -12;
     const int m_tiles = (a.M + BLOCK_M - 1) / BLOCK_M, n_tiles = (a.N + BLOCK_N - 1) / BLOCK_N;
     const int splits = (EPI == EPI_PARTIAL_F32 && a.splits > 1) ? a.splits : 1;
     const int tiles = m_tiles * n_tiles * splits;

@@ -4,6 +4,22 @@
 
 namespace lcc {
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute of a kernel: remember per (kernel
+// instantiation, device) that it was raised, so a second engine on another device of the same process works.
+struct SmemAttrOnce {
+    bool set[64] = {};
+};
+template <typename Kern>
+inline int ensure_dyn_smem(SmemAttrOnce& once, Kern kern, int bytes) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -1;
+    if (!once.set[dev]) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return -1;
+        once.set[dev] = true;
+    }
+    return 0;
+}
+
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
                                  bool pdl, Args... args) {

@@ -119,6 +119,7 @@ lcc::SampleArgs make_sample(const lcc_model* m, const lcc_stream_state* st, cons
     a.thr_base = sp->thr_base;
     a.thr_step = sp->thr_step;
     a.eos_token_id = sp->eos_token_id;
+    a.eos_token_id2 = sp->eos_token_id2;
     a.max_new_tokens = sp->max_new_tokens;
     a.advance_kv = advance;
     a.embed = reinterpret_cast<const bf16*>(m->w.embed);
@@ -235,7 +236,7 @@ int lcc_vit_forward_frames(lcc_model* m, const uint8_t* frames, int T, int H, in
 }
 
 int lcc_prefill(lcc_model* m, const lcc_stream_state* st, const int64_t* ids, const int32_t* pos3, int S,
-                int past, const void* video_embeds, const lcc_sampling* sp, lcc_stream_t stream) {
+                int past, const void* video_embeds, int n_video_rows, const lcc_sampling* sp, lcc_stream_t stream) {
     if (!m || !st || !sp) return -1;
     const lcc_model_config& c = m->cfg;
     cudaStream_t s = (cudaStream_t)stream;
@@ -249,7 +250,7 @@ int lcc_prefill(lcc_model* m, const lcc_stream_state* st, const int64_t* ids, co
     void* skw = ws + L.pf_splitk;  // split-K scratch of the small-N projections (opt-in, see gemm_tcgen05.cu::try_splitk)
     const size_t skb = kSplitKRows * (size_t)(qkv_dim > H ? qkv_dim : H) * 4;
 
-    STEP(lcc::embed_gather(ids, (const bf16*)m->w.embed, (const bf16*)video_embeds, c.video_token_id, hid, rank,
+    STEP(lcc::embed_gather(ids, (const bf16*)m->w.embed, (const bf16*)video_embeds, n_video_rows, c.video_token_id, hid, rank,
                            st->scalars + LCC_SC_VIDEO_TOKENS, S, H, c.vocab, s), "embed gather");
     for (int i = 0; i < c.layers; ++i) {
         const lcc_layer_weights& lw = m->layers[i];
@@ -303,7 +304,7 @@ int lcc_decode_steps(lcc_model* m, const lcc_stream_state* st, int n_steps, int 
             bf16* kc = (bf16*)st->k_pool + (size_t)i * st->layer_stride;
             bf16* vc = (bf16*)st->v_pool + (size_t)i * st->layer_stride;
             const void* next_qkv = (i + 1 < c.layers) ? m->layers[i + 1].qkv_w : m->w.lm_head;
-            const size_t next_qkv_bytes = (i + 1 < c.layers) ? qkv_bytes : kPf;
+            const size_t next_qkv_bytes = (i + 1 < c.layers) ? qkv_bytes : (size_t)c.vocab * H * 2;  // lm_head: capped below
             STEP(lcc::gemv_norm_bias((const bf16*)lw.qkv_w, H, h, (const bf16*)lw.ln1_w, c.rms_eps, (const bf16*)lw.qkv_b,
                                      qkv, qkv_dim, H, fin, lw.o_w, cap(o_bytes), m->ctx->num_sms, pdl, s), "decode qkv");
             if (m->fuse_attn_oproj) {

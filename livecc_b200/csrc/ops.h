@@ -21,7 +21,7 @@ int vit_rope_table(float* cos_t, float* sin_t, int t, int h, int w, int merge, i
                    const float* inv_freq, cudaStream_t s);
 int vit_rope_apply(bf16* qkv, int ld, const float* cos_t, const float* sin_t, int N, int heads, int hd,
                    cudaStream_t s);
-int embed_gather(const int64_t* ids, const bf16* table, const bf16* video, int64_t video_id, bf16* out,
+int embed_gather(const int64_t* ids, const bf16* table, const bf16* video, int n_video_rows, int64_t video_id, bf16* out,
                  int* rank_ws, int* total_video, int S, int H, int64_t vocab, cudaStream_t s);
 int mrope_kv_write(bf16* qkv, int ld, const int* pos3, int S, const float* inv_freq, int sec_t, int sec_h,
                    int Hq, int Hkv, bf16* kc, bf16* vc, const int* page_table, int page_size, int kv_start,
@@ -75,6 +75,7 @@ struct SampleArgs {
     int thr_token;            // < 0: disabled (ThresholdLogitsProcessor, REF/demo/infer.py:10-23)
     float thr_base, thr_step;
     int eos_token_id;
+    int eos_token_id2;        // < 0: none
     int max_new_tokens;
     int advance_kv;           // 1 after a decode forward, 0 after prefill
     const bf16* embed;        // [V, H]

@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(1024) sample_greedy_kernel(const SampleArgs a)
             sc[LCC_SC_KV_LEN] += 1;
             sc[LCC_SC_ROPE_POS] += 1;
         }
-        if (tok == a.eos_token_id || n >= a.max_new_tokens) sc[LCC_SC_FINISHED] = 1;
+        if (tok == a.eos_token_id || tok == a.eos_token_id2 || n >= a.max_new_tokens) sc[LCC_SC_FINISHED] = 1;
     }
     const bf16* src = a.embed + (size_t)tok * a.H;
     for (int c = tid * 8; c < a.H; c += blockDim.x * 8)

@@ -56,6 +56,15 @@ class GenerationDefaults:
     top_p: float = 0.001
     temperature: float = 0.01
     repetition_penalty: float = 1.0
+    eos_token_id: object = None  # int | [int, int] | None (= config.eos_token_id); HF stops on any id of the list
+
+    @classmethod
+    def from_json(cls, d: dict) -> "GenerationDefaults":
+        g = cls()
+        for k in ("do_sample", "top_k", "top_p", "temperature", "repetition_penalty", "eos_token_id"):
+            if k in d and d[k] is not None:
+                setattr(g, k, d[k])
+        return g
 
 
 class LiveCCB200ForConditionalGeneration:
@@ -109,33 +118,24 @@ class LiveCCB200ForConditionalGeneration:
 
     @classmethod
     def from_pretrained(cls, model_path: str, torch_dtype="auto", device_map="cuda", attn_implementation=None, **_):
-        """Loads an HF Qwen2-VL / LiveCC safetensors checkpoint directory (REF/demo/infer.py:43-47).
-        `attn_implementation` is accepted and ignored (attention is always the native kernels)."""
-        import glob
-        import json
+        """Loads an HF Qwen2-VL / LiveCC safetensors checkpoint directory (REF/demo/infer.py:43-47): config.json,
+        generation_config.json (EOS list, sampling defaults) and *.safetensors in the pre-5.x (`visual.*`, `model.*`)
+        or 5.x (`model.visual.*`, `model.language_model.*`) naming. `attn_implementation` is accepted and ignored
+        (attention is always the native kernels); weights are always held in bf16 (`torch_dtype` other than
+        "auto"/bf16 is rejected)."""
+        from .checkpoint import iter_hf_checkpoint, read_hf_configs
 
-        from safetensors import safe_open
+        if torch_dtype not in ("auto", None, torch.bfloat16, "bfloat16"):
+            raise NotImplementedError(f"torch_dtype={torch_dtype!r}: the sm_100a kernels compute in bf16 only")
+        cfg, gen = read_hf_configs(model_path)
+        model = cls.from_state_dict(cfg, iter_hf_checkpoint(model_path), device_map if isinstance(device_map, str) else "cuda")
+        model.generation_config = GenerationDefaults.from_json(gen)
+        if model.generation_config.do_sample and model.generation_config.top_k != 1:
+            import warnings
 
-        files = sorted(glob.glob(os.path.join(model_path, "*.safetensors")))
-        if not files:
-            raise FileNotFoundError(f"no *.safetensors under {model_path!r} (checkpoints cannot be downloaded offline)")
-        cfg = LiveCCConfig.livecc_7b()
-        cfg_path = os.path.join(model_path, "config.json")
-        if os.path.exists(cfg_path):
-            cfg = _config_from_hf_json(json.load(open(cfg_path)))
-
-        def it():
-            for f in files:
-                with safe_open(f, framework="pt") as sf:
-                    for name in sf.keys():
-                        n = name
-                        if n.startswith("visual."):
-                            n = "model." + n  # pre-5.x naming
-                        elif n.startswith("model.") and not n.startswith(("model.visual.", "model.language_model.")):
-                            n = "model.language_model." + n[len("model."):]
-                        yield n, sf.get_tensor(name)
-
-        return cls.from_state_dict(cfg, it(), device_map if isinstance(device_map, str) else "cuda")
+            warnings.warn(f"generation_config.json has top_k={model.generation_config.top_k}: do_sample=True will be "
+                          "rejected (the native sampling kernel is greedy, i.e. top_k = 1)")
+        return model
 
     def _build_native(self) -> _cabi.NativeModel:
         t, v, w = self.config.text_config, self.config.vision_config, self.weights
@@ -187,8 +187,14 @@ class LiveCCB200ForConditionalGeneration:
             else:
                 raise NotImplementedError(f"logits processor {type(proc).__name__} is not supported by the native "
                                           "sampling kernel (supported: ThresholdLogitsProcessor)")
-        return _cabi.Sampling(float(repetition_penalty), thr_token, thr_base, thr_step, int(self.config.eos_token_id),
-                              int(max_new_tokens), 1.0 / float(repetition_penalty))
+        eos = self.generation_config.eos_token_id
+        if eos is None:
+            eos = self.config.eos_token_id
+        eos = [int(e) for e in (eos if isinstance(eos, (list, tuple)) else [eos])]
+        if len(eos) > 2:
+            raise NotImplementedError(f"at most two EOS ids are supported by the native sampling kernel, got {eos}")
+        return _cabi.Sampling(float(repetition_penalty), thr_token, thr_base, thr_step, eos[0],
+                              int(max_new_tokens), 1.0 / float(repetition_penalty), eos[1] if len(eos) > 1 else -1)
 
     # ------------------------------------------------------------------------------------------
     # the hot path
@@ -332,26 +338,39 @@ class LiveCCB200ForConditionalGeneration:
         nsplit = min(nsplit, self.max_nsplit)
         self.nsplit = nsplit
         n_steps = max_new_tokens - 1
-        if output_logits or _forced_ids is not None:
+        logits_hist = None
+        if _forced_ids is not None:
+            # teacher forcing (parity tests): eager per-step launches, the host swaps the token between steps
             for i in range(n_steps):
                 self._native.decode_steps(st, 1, nsplit, sp)
                 if output_logits:
                     logits_out.append(self._raw_logits().clone())
-                if _forced_ids is not None and i + 1 < len(_forced_ids):
+                if i + 1 < len(_forced_ids):
                     self._force_token(cache, L, i + 1, _forced_ids, max_new_tokens)
         elif n_steps > 0:
-            self._run_decode(cache, st, sp, n_steps, nsplit)
+            if output_logits:
+                # production (CUDA-graph replay) path with the logits of every step copied out inside the replay loop:
+                # the path whose logits the parity tests read is the path the benchmark times
+                logits_hist = torch.empty((n_steps, self.config.text_config.vocab_size), dtype=torch.float32,
+                                          device=self.device)
+            self._run_decode(cache, st, sp, n_steps, nsplit, logits_hist)
 
         self._ev[3].record()
         # ---- one host sync per generate(): read the stream scalars ----
         sc = cache.scalars.tolist()
         n_gen = sc[_cabi.SC_N_GENERATED]
-        cache.seq_len = sc[_cabi.SC_KV_LEN]
         if n_video_expected >= 0:
             n_video_ids = sc[_cabi.SC_VIDEO_TOKENS]
             if n_video_ids != n_video_expected:
+                # the reference validates before the forward (mq2vl.py:1169-1175); here the count comes back with the
+                # step's scalars, so the stream state is rolled back to what it was before this call: the cache still
+                # reports `past` tokens (the pages written behind it are dead) and a first turn forgets its rope_delta
+                cache.seq_len = past
+                if past == 0:
+                    cache.rope_delta = None
                 raise ValueError(f"Video features and video tokens do not match, tokens: {n_video_ids}, "
-                                 f"features: {n_video_expected}")  # mq2vl.py:1169-1175
+                                 f"features: {n_video_expected}")
+        cache.seq_len = sc[_cabi.SC_KV_LEN]
         sequences = cache.seq_buf[: L + n_gen].clone().view(1, -1)
         ph = [self._ev[i].elapsed_time(self._ev[i + 1]) for i in range(3)]
         self.last_stats = {"prefill_tokens": S, "generated": n_gen, "kv_len": cache.seq_len, "vit_ms": ph[0],
@@ -360,17 +379,24 @@ class LiveCCB200ForConditionalGeneration:
         tot["vit"] += ph[0]; tot["prefill"] += ph[1]; tot["decode"] += ph[2]
         tot["calls"] += 1; tot["decode_steps"] += max(n_gen - 1, 0)
         if output_logits and logits_out is not None:
+            if logits_hist is not None:
+                logits_out += list(logits_hist[: max(n_gen - 1, 0)])
             logits_out = logits_out[:n_gen]
         out = GenerateOutput(sequences=sequences, past_key_values=cache, logits=logits_out)
         return out if return_dict_in_generate else sequences
 
     # ------------------------------------------------------------------------------------------
-    def _run_decode(self, cache: PagedKVCache, st, sp: _cabi.Sampling, n_steps: int, nsplit: int):
+    def _run_decode(self, cache: PagedKVCache, st, sp: _cabi.Sampling, n_steps: int, nsplit: int, logits_hist=None):
         if not self.use_cuda_graph:
-            self._native.decode_steps(st, n_steps, nsplit, sp)
+            if logits_hist is None:
+                self._native.decode_steps(st, n_steps, nsplit, sp)
+            else:
+                for i in range(n_steps):
+                    self._native.decode_steps(st, 1, nsplit, sp)
+                    logits_hist[i].copy_(self._raw_logits())
             return
         key = (cache.graph_key(), self._native.workspace.data_ptr(), nsplit, sp.repetition_penalty, sp.thr_token,
-               sp.thr_base, sp.thr_step, sp.eos_token_id, sp.max_new_tokens)
+               sp.thr_base, sp.thr_step, sp.eos_token_id, sp.eos_token_id2, sp.max_new_tokens)
         g = self._graphs.get(key)
         if g is None:
             # capture ONE decode step (28 layers + lm_head + token selection); replay it n_steps times.
@@ -385,8 +411,10 @@ class LiveCCB200ForConditionalGeneration:
                     self._native.decode_steps(st, 1, nsplit, sp)
             torch.cuda.current_stream(self.device).wait_stream(side)
             self._graphs[key] = g
-        for _ in range(n_steps):
+        for i in range(n_steps):
             g.replay()
+            if logits_hist is not None:  # a finished stream replays no-ops and leaves the last logits in place
+                logits_hist[i].copy_(self._raw_logits())
 
     def _raw_logits(self) -> torch.Tensor:
         off = self._native.logits_offset
@@ -403,27 +431,3 @@ class LiveCCB200ForConditionalGeneration:
         cache.scalars[_cabi.SC_LAST_TOKEN] = tok
         done = tok == self.config.eos_token_id or step + 1 >= max_new_tokens or step + 1 >= len(forced)
         cache.scalars[_cabi.SC_FINISHED] = 1 if done else 0
-
-
-def _config_from_hf_json(d: dict) -> LiveCCConfig:
-    from .config import TextConfig, VisionConfig
-
-    tc = d.get("text_config", d)
-    vc = d.get("vision_config", {})
-    rp = tc.get("rope_parameters") or tc.get("rope_scaling") or d.get("rope_scaling") or {}
-    text = TextConfig(
-        vocab_size=tc.get("vocab_size", 152064), hidden_size=tc.get("hidden_size", 3584),
-        intermediate_size=tc.get("intermediate_size", 18944), num_hidden_layers=tc.get("num_hidden_layers", 28),
-        num_attention_heads=tc.get("num_attention_heads", 28), num_key_value_heads=tc.get("num_key_value_heads", 4),
-        rms_norm_eps=tc.get("rms_norm_eps", 1e-6), rope_theta=rp.get("rope_theta", tc.get("rope_theta", 1e6)),
-        mrope_section=tuple(rp.get("mrope_section", (16, 24, 24))))
-    vis = VisionConfig(
-        depth=vc.get("depth", 32), embed_dim=vc.get("embed_dim", 1280), hidden_size=vc.get("hidden_size", 3584),
-        mlp_ratio=vc.get("mlp_ratio", 4), num_heads=vc.get("num_heads", 16), in_channels=vc.get("in_channels", 3),
-        patch_size=vc.get("patch_size", 14), spatial_merge_size=vc.get("spatial_merge_size", 2),
-        temporal_patch_size=vc.get("temporal_patch_size", 2))
-    return LiveCCConfig(
-        text_config=text, vision_config=vis, image_token_id=d.get("image_token_id", 151655),
-        video_token_id=d.get("video_token_id", 151656), vision_start_token_id=d.get("vision_start_token_id", 151652),
-        vision_end_token_id=d.get("vision_end_token_id", 151653), bos_token_id=d.get("bos_token_id", 151643),
-        eos_token_id=d.get("eos_token_id", 151645), name=d.get("_name_or_path", "livecc"))

@@ -296,7 +296,7 @@ def test_sample_greedy(ctx):
     seq[:5000] = hist
     sc = torch.zeros(A.SC_COUNT, dtype=torch.int32, device=DEV)
     sc[A.SC_KV_LEN], sc[A.SC_ROPE_POS], sc[A.SC_SEQ_LEN] = 5000, 4000, 5000
-    sp = A.Sampling(1.05, -1, 0.0, 0.0, 7, 16, 1.0 / 1.05)
+    sp = A.Sampling(1.05, -1, 0.0, 0.0, 7, 16, 1.0 / 1.05, -1)
     proc = raw.clone()
     h = torch.empty(H, dtype=torch.bfloat16, device=DEV)
     ctx.sample_greedy(raw, proc, seq, sc, sp, 1, embed, h)
@@ -317,7 +317,7 @@ def test_sample_greedy(ctx):
     sc2 = torch.zeros(A.SC_COUNT, dtype=torch.int32, device=DEV)
     sc2[A.SC_SEQ_LEN] = 5000
     proc2 = raw.clone()
-    sp2 = A.Sampling(1.0, tok, 1.1, 0.0, 7, 1, 1.0)
+    sp2 = A.Sampling(1.0, tok, 1.1, 0.0, 7, 1, 1.0, -1)
     ctx.sample_greedy(raw, proc2, seq, sc2, sp2, 0, embed, h)
     ref2 = raw.clone()
     ref2[tok] = -float("inf")
@@ -327,3 +327,53 @@ def test_sample_greedy(ctx):
     before = seq.clone()
     ctx.sample_greedy(raw, proc2, seq, sc2, sp2, 0, embed, h)
     assert torch.equal(seq, before)
+
+
+def test_threshold_processor_matches_reference_golden(ctx):
+    """ThresholdLogitsProcessor inside the sampling kernel vs the reference's own class (REF/demo/infer.py:10-23)
+    executed verbatim by tests/golden/make_threshold_golden.py: the `<=` boundary, a threshold that rises with
+    `count` (= tokens generated so far in this generate(), a new processor is built per chunk: infer.py:161-162) and
+    the canonical caller's base 0.0 / step 0 (REF/demo/cli.py:16-19)."""
+    import json
+    import os
+
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "threshold_golden.json")))
+    V, H = gold["V"], 64
+    embed = _rand((V, H), 41)
+    for c in gold["cases"]:
+        raw = torch.tensor(c["scores"], dtype=torch.float32, device=DEV)
+        for k in range(c["n_calls"]):
+            seq = torch.zeros(64, dtype=torch.int64, device=DEV)
+            sc = torch.zeros(A.SC_COUNT, dtype=torch.int32, device=DEV)
+            sc[A.SC_N_GENERATED] = k          # == the reference processor's `count` at this call
+            sp = A.Sampling(1.0, c["token"], c["base"], c["step"], V + 7, 64, 1.0, -1)
+            proc = raw.clone()
+            h = torch.empty(H, dtype=torch.bfloat16, device=DEV)
+            ctx.sample_greedy(raw, proc, seq, sc, sp, 0, embed, h)
+            torch.cuda.synchronize()
+            masked = bool(torch.isinf(proc[c["token"]]) and proc[c["token"]] < 0)
+            assert masked == c["masked"][k], (c["name"], k, masked, c["prob"], c["base"] + c["step"] * k)
+            assert int(seq[0]) == c["argmax"][k], (c["name"], k, int(seq[0]), c["argmax"][k])
+            assert sc.tolist()[A.SC_N_GENERATED] == k + 1
+
+
+def test_embed_gather_never_reads_past_the_video_rows(ctx):
+    """More <|video_pad|> ids than ViT rows (the mismatch the engine raises on, mq2vl.py:1169-1175): placeholders
+    beyond the last feature row keep their text embedding instead of reading past the end of `video_embeds`."""
+    H, V, vid = 256, 1000, 999
+    table = _rand((V, H), 51)
+    # the feature buffer is the tail of an allocation whose neighbour is poisoned with NaN
+    buf = torch.full((8, H), float("nan"), dtype=torch.bfloat16, device=DEV)
+    buf[:3] = _rand((3, H), 52)
+    feats = buf[:3]
+    ids = torch.tensor([5, vid, vid, 6, vid, vid, vid, 7], dtype=torch.int64, device=DEV)  # 5 placeholders, 3 rows
+    out, rank = ctx.embed_gather(ids, table, feats, vid)
+    torch.cuda.synchronize()
+    assert int(rank[ids.numel()]) == 5                       # the count the host compares with the feature rows
+    assert torch.equal(out[1], feats[0]) and torch.equal(out[2], feats[1]) and torch.equal(out[4], feats[2])
+    assert torch.equal(out[5], table[vid]) and torch.equal(out[6], table[vid])
+    assert torch.equal(out[0], table[5]) and not torch.isnan(out.float()).any()
+    # no features at all: placeholders are plain text ids, as in the reference when pixel values are absent
+    out2, rank2 = ctx.embed_gather(ids, table, None, vid)
+    torch.cuda.synchronize()
+    assert torch.equal(out2, table[ids]) and int(rank2[ids.numel()]) == 0
