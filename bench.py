@@ -15,6 +15,8 @@ checkpoint (no weights exist offline) and synthetic frames.
   cpu_baseline  : the reference's own eager CPU path (HF transformers fp32) on a bounded sample
 
 `--impl reference` times only that CPU path (rank 0), same metric/config keys.
+`--impl hf_gpu [--liger]` times the reference's own GPU path (installed transformers, bf16, flash_attention_2, through
+oracle/hf_oracle.py) on the same clip and config: the "kernel to beat" line, printed with per-phase device time.
 """
 from __future__ import annotations
 
@@ -39,7 +41,10 @@ def parse_args():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--impl", default="native", choices=["native", "reference", "hf_gpu"],
+                    help="native: this repo; reference: the reference's CPU path (driver arm); hf_gpu: the reference's GPU "
+                         "path (HF bf16 + flash_attention_2, optionally --liger) on the same B200 = the kernel to beat")
+    ap.add_argument("--liger", action="store_true", help="hf_gpu: apply_liger_kernel_to_qwen2_vl() first (REF/demo/infer.py:2-3)")
     ap.add_argument("--model", default="7b", choices=["7b", "small"])
     ap.add_argument("--seconds", type=int, default=60, help="clip length in seconds of video (2 fps)")
     ap.add_argument("--size", type=int, default=448)
@@ -223,11 +228,14 @@ def time_dominant_kernel(eng, iters=5):
 # ------------------------------------------------------------------------------------------------
 # CPU reference arm (HF eager fp32 on host cores)
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_sample(cfg, size, max_new=8, steps=1, warmup=0, budget_s=150.0):
+def cpu_reference_sample(cfg, size, max_new=16, steps=1, warmup=0, budget_s=150.0):
     """The reference's own CPU path: transformers Qwen2VLForConditionalGeneration, fp32, eager attention, through
-    oracle/hf_oracle.py. Bounded sample: a fresh stream's first turn with ONE 2-frame chunk at size x size and
-    `max_new` greedy tokens (repetition_penalty 1.05). Threads: min(host cores, 32) — oversubscribing a
-    128-core box made the eager path several times slower. Stops early once `budget_s` of samples were timed."""
+    oracle/hf_oracle.py. Bounded sample = one steady-state streaming second: a fresh stream's turn with ONE 2-frame
+    chunk at size x size (ViT on 1024 patches + prefill of ~281 tokens) and `max_new` = 16 greedy tokens
+    (repetition_penalty 1.05), i.e. the per-chunk work of REF/demo/infer.py:165-172 at KV length ~300 (the CPU cost per
+    chunk is dominated by the 7B weights, not by the KV length, so this does not flatter the GPU arm). Threads:
+    min(host cores, 32) — oversubscribing a 128-core box made the eager path several times slower. Stops early once
+    `budget_s` of samples were timed."""
     from livecc_b200.checkpoint import synthetic_tensors
     from livecc_b200.processing import StubProcessor
     from oracle.hf_oracle import build_hf_model, hf_generate_chunk
@@ -261,8 +269,107 @@ def cpu_reference_sample(cfg, size, max_new=8, steps=1, warmup=0, budget_s=150.0
     sec = sum(times) / len(times)
     return {"tokens_per_s": toks / sec, "frames_per_s": 2 / sec, "sec_per_sample": sec, "cores": nthreads,
             "host_cores": ncores, "tokens": toks, "timed_samples": len(times),
-            "sample": f"first turn of a fresh stream: one 2-frame {size}x{size} chunk + {toks} greedy tokens, fp32 eager, "
-                      f"{nthreads} threads, {len(times)} timed sample(s)"}
+            "sample": f"one streaming chunk of a fresh stream: 2 frames {size}x{size} (ViT 1024 patches + prefill) + {toks} "
+                      f"greedy tokens (max_new_tokens=16 as REF/demo/infer.py:170), fp32 eager, {nthreads} threads, "
+                      f"{len(times)} timed sample(s); tokens/s = {toks} / seconds per chunk"}
+
+
+# ------------------------------------------------------------------------------------------------
+# "kernel to beat": the reference's own GPU path (HF bf16 + flash_attention_2 [+ liger]) on the same B200
+# ------------------------------------------------------------------------------------------------
+def run_hf_gpu(args, cfg, config, dev):
+    """REF/demo/infer.py:43-47,165-172 with the installed transformers / flash-attn (/ liger_kernel) stack: same
+    synthetic checkpoint, same clip, same per-chunk generate() arguments, inputs resident on the device. Per-phase device
+    time from CUDA events around the vision tower and the language-model forwards (prefill = S > 1, decode = S == 1)."""
+    from livecc_b200.checkpoint import synthetic_tensors
+    from oracle.hf_oracle import build_hf_model, hf_generate_chunk, oracle_variant
+
+    tensors = synthetic_tensors(cfg, 1234, torch.bfloat16, dev, gen_device=dev)
+    impl = "flash_attention_2"
+    try:
+        model = build_hf_model(cfg, tensors, dtype=torch.bfloat16, device=dev, attn_implementation=impl, liger=args.liger)
+    except Exception as e:  # noqa: BLE001
+        print(json.dumps({"impl": "hf_gpu", "unavailable": f"{type(e).__name__}: {e}"}))
+        return 0
+    chunks, _ = build_chunks(cfg, args.seconds, args.size, seed=0)
+    chunks = [dict(input_ids=c.input_ids.to(dev), pixel_values_videos=c.pixel_values_videos.to(dev),
+                   video_grid_thw=c.video_grid_thw.to(dev), frames=int(c.video_grid_thw[0, 0]) * 2) for c in chunks]
+    ev = {"vit": [], "prefill": [], "decode": []}
+
+    def hook(kind_of):
+        def pre(mod, a, kw):
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            mod._lcc_e0 = (e, kind_of(a, kw))
+
+        def post(mod, a, kw, out):
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            e0, kind = mod._lcc_e0
+            ev[kind].append((e0, e1))
+        return pre, post
+
+    def lm_kind(a, kw):
+        x = kw.get("inputs_embeds")
+        x = x if x is not None else kw.get("input_ids")
+        return "decode" if x is not None and x.shape[1] == 1 else "prefill"
+
+    pre, post = hook(lambda a, kw: "vit")
+    model.model.visual.register_forward_pre_hook(pre, with_kwargs=True)
+    model.model.visual.register_forward_hook(post, with_kwargs=True)
+    pre, post = hook(lm_kind)
+    model.model.language_model.register_forward_pre_hook(pre, with_kwargs=True)
+    model.model.language_model.register_forward_hook(post, with_kwargs=True)
+
+    def one_stream():
+        kv = past = None
+        model.model.rope_deltas = None
+        tok = frames = 0
+        lat = []
+        for ch in chunks:
+            t0 = time.perf_counter()
+            out, L = hf_generate_chunk(model, ch, kv, past, max_new_tokens=args.max_new_tokens)
+            kv, past = out.past_key_values, out.sequences[:, :-1]
+            tok += out.sequences.shape[1] - L
+            frames += ch["frames"]
+            torch.cuda.synchronize()
+            lat.append((time.perf_counter() - t0) / ch["frames"])
+        return tok, frames, lat, kv.get_seq_length()
+
+    for _ in range(args.warmup):
+        one_stream()
+    for v in ev.values():
+        v.clear()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(dev.index or 0)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    tok = frames = 0
+    lat = []
+    for _ in range(args.steps):
+        a, b, c, kv_end = one_stream()
+        tok += a
+        frames += b
+        lat += c
+    e1.record()
+    torch.cuda.synchronize()
+    sec = e0.elapsed_time(e1) / 1e3
+    clocks = sampler.stop()
+    n_chunks = len(chunks) * args.steps
+    ph = {k: sum(a.elapsed_time(b) for a, b in v) for k, v in ev.items()}
+    lat.sort()
+    line = {"impl": "hf_gpu", "variant": oracle_variant(impl), "metric": METRIC, "value": tok / sec, "unit": "tokens/s",
+            "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec / args.steps * 1e3,
+            "higher_is_better": True, "dtype": "bf16", "data": "synthetic", "config": config,
+            "frames_per_s": frames / sec, "p50_frame_latency_ms": lat[len(lat) // 2] * 1e3, "kv_len_end": kv_end,
+            "clocks": clocks,
+            "phases_ms_per_chunk": {"vit": ph["vit"] / n_chunks, "prefill": ph["prefill"] / n_chunks,
+                                    "decode": ph["decode"] / n_chunks,
+                                    "host_and_other": sec * 1e3 / n_chunks - sum(ph.values()) / n_chunks},
+            "decode_ms_per_step": ph["decode"] / max(len(ev["decode"]), 1)}
+    print(json.dumps(line))
+    return 0
 
 
 # ------------------------------------------------------------------------------------------------
@@ -281,7 +388,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        r = cpu_reference_sample(cfg, args.size, max_new=4, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+        r = cpu_reference_sample(cfg, args.size, max_new=args.max_new_tokens, steps=max(1, args.steps), warmup=min(args.warmup, 1))
         line = {"impl": "reference", "metric": METRIC, "value": r["tokens_per_s"], "unit": "tokens/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["sec_per_sample"] * 1e3,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -296,6 +403,8 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a B200; there is no CPU fallback for the native arm"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if args.impl == "hf_gpu":
+        return run_hf_gpu(args, cfg, config, dev) if rank == 0 else 0
     if world > 1:
         import torch.distributed as dist
 
@@ -331,6 +440,7 @@ def main():
     kv_end = 0
     for k in eng.phase_ms_total:
         eng.phase_ms_total[k] = 0
+    launches0 = eng.kernel_launches()
     for _ in range(args.steps):
         a, b, c, kv_end = run_stream_device(eng, chunks_dev, args.max_new_tokens)
         tok += a
@@ -338,6 +448,7 @@ def main():
         lat += c
     e1.record()
     barrier()
+    gpu_launches = eng.kernel_launches() - launches0  # counted at the library's launch sites (+ graph nodes per replay)
     sec = e0.elapsed_time(e1) / 1e3
     clocks = sampler.stop()
     phases = dict(eng.phase_ms_total)
@@ -382,23 +493,19 @@ def main():
     p50 = lat_sorted[len(lat_sorted) // 2] * 1e3
     peak, peak_src = load_peaks()
     kbytes, ksec = time_dominant_kernel(eng)
-    traffic = None
+    traffic, traffic_src = None, None
     try:  # dram bytes of the same kernel from the committed `ncu --set full` capture (7B dims only)
         if args.model == "7b":
             tr = json.load(open(os.path.join(ROOT, "profiles", "r01_gateup_ncu.json")))
             traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+            traffic_src = "static: one `ncu --set full` capture of this kernel (profiles/r01_gateup_ncu.json), not measured in this run"
     except Exception:
         traffic = None
     t = cfg.text_config
     step_weight_bytes = (t.num_hidden_layers * ((t.num_attention_heads + 2 * t.num_key_value_heads) * 128 * t.hidden_size
                                                 + t.hidden_size * t.hidden_size + 3 * t.intermediate_size * t.hidden_size
                                                 + 2 * t.hidden_size) + t.hidden_size + t.vocab_size * t.hidden_size) * 2
-    v = cfg.vision_config
-    launches_vit = lambda: 4 + v.depth * 8 + 3
-    launches_prefill = 2 + t.num_hidden_layers * 8 + 2
-    launches_decode = t.num_hidden_layers * 6 + 2
     n_chunks = len(chunks)
-    gpu_launches = args.steps * (n_chunks * (launches_vit() + launches_prefill) + (tok // args.steps - n_chunks) * launches_decode)
     line = {
         "metric": METRIC, "value": tot_tok / max_sec, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": max_sec / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -407,7 +514,8 @@ def main():
         "kv_len_end": kv_end, "clocks": clocks, "gpu_launches": int(gpu_launches),
         "roofline": {"kernel": "gemv_rows_kernel<2,NORM,SWIGLU> (decode gate/up + RMSNorm + SwiGLU)", "bound": "hbm",
                      "achieved": kbytes / ksec / 1e9, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                     "frac": kbytes / ksec / 1e9 / peak, "traffic": traffic, "bytes_per_launch": kbytes,
+                     "frac": kbytes / ksec / 1e9 / peak, "traffic": traffic, "traffic_source": traffic_src,
+                     "bytes_per_launch": kbytes,
                      "us_per_launch": ksec * 1e6},
     }
     if e2e:
@@ -434,7 +542,7 @@ def main():
                              "frac": bytes_avg / (ms_per_dstep / 1e3) / 1e9 / peak, "decode_steps": dsteps}
     if not args.no_cpu_baseline and world == 1:
         try:
-            r = cpu_reference_sample(cfg, args.size, max_new=4, steps=1, warmup=0, budget_s=60.0)
+            r = cpu_reference_sample(cfg, args.size, max_new=args.max_new_tokens, steps=1, warmup=0, budget_s=60.0)
             line["cpu_baseline"] = {"value": r["tokens_per_s"], "unit": "tokens/s", "frames_per_s": r["frames_per_s"],
                                     "cores": r["cores"], "kind": "reference", "sample": r["sample"]}
         except Exception as ex:  # the baseline must never take the GPU number down with it

@@ -66,6 +66,9 @@ lcc_ctx* lcc_create(int device);
 void lcc_destroy(lcc_ctx* ctx);
 const char* lcc_last_error(lcc_ctx* ctx);
 int lcc_num_sms(lcc_ctx* ctx);
+/* Kernel launches issued by this library in this process so far (launches recorded into a CUDA graph count once,
+ * at capture). */
+uint64_t lcc_launch_count(void);
 
 /* ---- op level (each is unit-tested against the oracle) ---------------------------------- */
 

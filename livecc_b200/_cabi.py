@@ -92,6 +92,8 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     lib.lcc_last_error.restype = C.c_char_p
     lib.lcc_last_error.argtypes = [C.c_void_p]
     lib.lcc_num_sms.argtypes = [C.c_void_p]
+    lib.lcc_launch_count.restype = C.c_uint64
+    lib.lcc_launch_count.argtypes = []
     lib.lcc_model_create.restype = C.c_void_p
     lib.lcc_model_create.argtypes = [C.c_void_p, C.POINTER(ModelConfig), C.POINTER(ModelWeights)]
     lib.lcc_model_destroy.argtypes = [C.c_void_p]
@@ -101,6 +103,11 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     lib.lcc_ws_offset.argtypes = [C.c_void_p, C.c_int]
     _lib = lib
     return lib
+
+
+def launch_count() -> int:
+    """Kernel launches issued by the library so far (graph-captured launches count once, at capture)."""
+    return int(load_library().lcc_launch_count())
 
 
 def _ptr(t):

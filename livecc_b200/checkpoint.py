@@ -116,7 +116,8 @@ def sharp_chain(cfg: LiveCCConfig, start: int, n: int) -> List[int]:
 
 
 def synthetic_tensors(cfg: LiveCCConfig, seed: int = 1234, dtype=torch.bfloat16, device="cpu",
-                      gen_device=None, sharp: bool = False, sharp_eos_after: int = 0) -> Iterator[Tuple[str, torch.Tensor]]:
+                      gen_device=None, sharp: bool = False, sharp_eos_after: int = 0,
+                      only=None) -> Iterator[Tuple[str, torch.Tensor]]:
     """Yields (hf_name, tensor). Weights ~ U(-a, a) with a = sqrt(3)*0.02*sqrt(1024/fan_in) capped
     at 0.035 (std ~0.02 at fan_in <= 1024, variance-preserving beyond); biases U(-0.02, 0.02);
     norm weights 1 + U(-0.1, 0.1); norm biases U(-0.02, 0.02). Values are rounded once to `dtype`.
@@ -124,14 +125,14 @@ def synthetic_tensors(cfg: LiveCCConfig, seed: int = 1234, dtype=torch.bfloat16,
     sharp=True builds the *sharp* variant used by the id-exactness tests. Random weights give nearly flat logits
     (top-1/top-2 gap of a few bf16 ulps), so greedy ids flip between any two correct bf16 implementations. The sharp
     variant gives the model a confident next-token distribution the way a trained LM has one: the embedding table is
-    scaled by 4*layers (the token direction then carries ~1/3..1/2 of the final hidden state's norm at 7B depth, the
-    28 layers the rest) and lm_head[pi(i)] = embed[i] for a fixed permutation pi of the text ids, so the top-1 logit
+    scaled by max(8, 2*layers) (the token direction then carries about half of the final hidden state's norm at 7B
+    depth, the 28 layers the rest) and lm_head[pi(i)] = embed[i] for a fixed permutation pi of the text ids, so the top-1 logit
     leads by several logit units (>> 10x the bf16 tolerance) while every other logit is still produced by the full
     network. The generated ids then follow pi from the last prompt token -- which is the point: id-exactness over
     hundreds of steps checks positions, cache, penalty and stop bookkeeping end to end, while numerics are checked by
     the teacher-forced logit tolerance on the flat checkpoint. sharp_eos_after=k > 0 additionally routes the k-th
     token of the chain that starts at the newline id (the last prompt token of the chat template) to EOS, so streams
-    stop early under CUDA-graph replay."""
+    stop early under CUDA-graph replay. `only`: optional set of names to generate (the others are skipped)."""
     gen_device = gen_device or device
     specs = hf_param_specs(cfg)
     embed_idx = next(i for i, sp in enumerate(specs) if sp[0].endswith("embed_tokens.weight"))
@@ -152,6 +153,8 @@ def synthetic_tensors(cfg: LiveCCConfig, seed: int = 1234, dtype=torch.bfloat16,
         return u * 0.04
 
     for idx, (name, shape, kind) in enumerate(specs):
+        if only is not None and name not in only:
+            continue
         if sharp and name == "lm_head.weight":
             emb = fill(embed_idx, specs[embed_idx][1], "w").view(specs[embed_idx][1])
             pi = _sharp_permutation(cfg, emb.device)
@@ -167,13 +170,21 @@ def synthetic_tensors(cfg: LiveCCConfig, seed: int = 1234, dtype=torch.bfloat16,
         else:
             x = fill(idx, shape, kind)
             if sharp and idx == embed_idx:
-                x = x * (4.0 * cfg.text_config.num_hidden_layers)
+                x = x * max(8.0, 2.0 * cfg.text_config.num_hidden_layers)
         yield name, x.to(dtype).view(shape).to(device)
 
 
 def synthetic_state_dict(cfg: LiveCCConfig, seed: int = 1234, dtype=torch.bfloat16, device="cpu",
                          gen_device=None, sharp: bool = False, sharp_eos_after: int = 0) -> Dict[str, torch.Tensor]:
     return dict(synthetic_tensors(cfg, seed, dtype, device, gen_device, sharp, sharp_eos_after))
+
+
+def sharp_overrides(cfg: LiveCCConfig, seed: int = 1234, dtype=torch.bfloat16, device="cpu", gen_device=None,
+                    sharp_eos_after: int = 0) -> Dict[str, torch.Tensor]:
+    """The two tensors in which the sharp checkpoint differs from the flat one (embed_tokens, lm_head):
+    `dict(flat_state_dict, **sharp_overrides(...))` is the sharp state dict without regenerating 8 B parameters."""
+    names = {"model.language_model.embed_tokens.weight", "lm_head.weight"}
+    return dict(synthetic_tensors(cfg, seed, dtype, device, gen_device, True, sharp_eos_after, only=names))
 
 
 # --------------------------------------------------------------------------------------------

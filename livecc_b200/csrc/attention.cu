@@ -381,7 +381,7 @@ static int launch_flash(const FlashParams& p, dim3 grid, cudaStream_t s) {
     auto kern = flash_fwd_kernel<D, CAUSAL, PAGED>;
     static SmemAttrOnce once;  // per instantiation
     if (ensure_dyn_smem(once, kern, smem)) return -1;
-    kern<<<grid, 128, smem, s>>>(p);
+    { lcc::count_launch(); kern<<<grid, 128, smem, s>>>(p); }
     return 0;
 }
 
@@ -557,7 +557,7 @@ int vit_attention(const bf16* qkv, int ld, int64_t n_rows, bf16* out, int o_ld, 
         constexpr int smem = (128 + 4 * 64) * 88 * 2;
         static SmemAttrOnce once;
         if (ensure_dyn_smem(once, vit_flash_kernel<2>, smem)) return -2;
-        vit_flash_kernel<2><<<dim3((max_seg_len + 127) / 128, heads, nseg), 128, smem, s>>>(p);
+        { lcc::count_launch(); vit_flash_kernel<2><<<dim3((max_seg_len + 127) / 128, heads, nseg), 128, smem, s>>>(p); }
         return 0;
     }
     dim3 grid((max_seg_len + 63) / 64, heads, nseg);
@@ -582,6 +582,7 @@ int attn_prefill_paged(const bf16* q, int q_ld, const bf16* kc, const bf16* vc, 
             return r;
         if (ns > 1) {
             const int G = Hq / Hkv;
+            lcc::count_launch();
             flash_merge_kernel<<<dim3(S * G, Hkv), 128, 0, s>>>(part_o, part_ml, ns, Hkv, S * G, G,
                                                                 1.4426950408889634f / sqrtf(128.f), out, o_ld);
         }
@@ -606,7 +607,7 @@ int attn_prefill_paged(const bf16* q, int q_ld, const bf16* kc, const bf16* vc, 
     dim3 grid(q_tiles, Hkv, nsplit);
     if (int r = launch_flash<128, true, true>(p, grid, s)) return r;
     if (nsplit > 1)
-        flash_merge_kernel<<<dim3(S * p.G, Hkv), 128, 0, s>>>(part_o, part_ml, nsplit, Hkv, S * p.G, p.G, p.scale_log2, out, o_ld);
+        { lcc::count_launch(); flash_merge_kernel<<<dim3(S * p.G, Hkv), 128, 0, s>>>(part_o, part_ml, nsplit, Hkv, S * p.G, p.G, p.scale_log2, out, o_ld); }
     return 0;
 }
 
@@ -973,6 +974,7 @@ int attn_decode(bf16* qkv, bf16* kc, bf16* vc, const int* page_table, int page_s
     p.finished = finished; p.inv_freq = inv_freq; p.Hq = Hq; p.Hkv = Hkv; p.nsplit = nsplit;
     p.part_o = part_o; p.part_ml = part_ml; p.counters = counters; p.out = out;
     p.scale_log2 = 1.4426950408889634f / sqrtf(128.f);
+    count_launch();
     if (launch_kernel(attn_decode_kernel, dim3(Hkv, nsplit), dim3(128), (size_t)smem, s, pdl, p) != cudaSuccess) return -3;
     return 0;
 }
@@ -995,6 +997,7 @@ int attn_oproj_decode(bf16* qkv, bf16* kc, bf16* vc, const int* page_table, int 
     p.done_groups = sync;
     OprojParams o{};
     o.W = o_w; o.ldw = o_ldw; o.N = o_N; o.K = Hq * 128; o.h = h; o.sync = sync; o.n_cta = (o_N + 15) / 16;
+    lcc::count_launch();
     attn_oproj_kernel<<<Hkv * nsplit + o.n_cta, 128, smem, s>>>(p, o);
     return 0;
 }

@@ -381,9 +381,9 @@ int attn_prefill_tc(const bf16* q, int q_ld, const bf16* kc, const bf16* vc, con
         return -12;
     PrefillTcParams p{out, o_ld, page_table, Hkv, G, PT, S, past, 1.4426950408889634f / sqrtf((float)D), nsplit, part_o, part_ml};
     if (ptmem)
-        attn_prefill_tc_kernel<true><<<dim3(q_tiles, Hkv, nsplit), 192, SMEM_BYTES, s>>>(tq, tk, tv, p);
+        { lcc::count_launch(); attn_prefill_tc_kernel<true><<<dim3(q_tiles, Hkv, nsplit), 192, SMEM_BYTES, s>>>(tq, tk, tv, p); }
     else
-        attn_prefill_tc_kernel<false><<<dim3(q_tiles, Hkv, nsplit), 192, SMEM_BYTES, s>>>(tq, tk, tv, p);
+        { lcc::count_launch(); attn_prefill_tc_kernel<false><<<dim3(q_tiles, Hkv, nsplit), 192, SMEM_BYTES, s>>>(tq, tk, tv, p); }
     *nsplit_out = nsplit;
     return 0;
 }

@@ -355,7 +355,7 @@ static int launch_tc(const bf16* qkv, int ld, int64_t n_rows, const VitTcParams&
     auto kern = vit_attn_tc_kernel<C>;
     static SmemAttrOnce once;  // per instantiation
     if (ensure_dyn_smem(once, kern, C::SMEM_BYTES)) return -12;
-    kern<<<grid, 192, C::SMEM_BYTES, s>>>(tq, tkv, p);
+    { lcc::count_launch(); kern<<<grid, 192, C::SMEM_BYTES, s>>>(tq, tkv, p); }
     return 0;
 }
 

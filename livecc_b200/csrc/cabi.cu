@@ -3,6 +3,7 @@
 #include "../../include/livecc_b200.h"
 #include "cabi_common.h"
 #include "gemm.h"
+#include "launch.h"
 #include "ops.h"
 
 using lcc::bf16;
@@ -30,6 +31,8 @@ void lcc_destroy(lcc_ctx* ctx) { delete ctx; }
 const char* lcc_last_error(lcc_ctx* ctx) { return ctx ? ctx->err : "null ctx"; }
 
 int lcc_num_sms(lcc_ctx* ctx) { return ctx ? ctx->num_sms : -1; }
+
+uint64_t lcc_launch_count(void) { return lcc::g_launches.load(std::memory_order_relaxed); }
 
 int lcc_gemm_bf16(lcc_ctx* ctx, const void* A, int lda, const void* B, int ldb, void* C, int ldc,
                   int M, int N, int K, const void* bias, const void* residual, int ldr, int epilogue,

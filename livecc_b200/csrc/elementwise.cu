@@ -2,6 +2,7 @@
 // paged-KV append, embedding gather/scatter. One warp per row wherever a row fits a warp's registers;
 // 16-byte vectorised, coalesced accesses; grids sized from the row count.
 #include "common.cuh"
+#include "launch.h"
 #include "ops.h"
 
 namespace lcc {
@@ -32,7 +33,7 @@ int cast_f32_bf16(const float* in, bf16* out, int64_t n, int num_sms, cudaStream
     int64_t blocks = (n / 8 + 255) / 256;
     if (blocks < 1) blocks = 1;
     if (blocks > (int64_t)num_sms * 16) blocks = (int64_t)num_sms * 16;
-    cast_f32_bf16_kernel<<<(int)blocks, 256, 0, s>>>(in, out, n);
+    { lcc::count_launch(); cast_f32_bf16_kernel<<<(int)blocks, 256, 0, s>>>(in, out, n); }
     return 0;
 }
 
@@ -76,6 +77,7 @@ int patchify_u8(const uint8_t* frames, int T, int H, int W, bf16* out, const flo
                 cudaStream_t s) {
     if (T <= 0 || H % 28 || W % 28) return -1;
     const int64_t total = (int64_t)((T + 1) / 2) * (H / 14) * (W / 14) * (1176 / 2);
+    lcc::count_launch();
     patchify_u8_kernel<<<(int)((total + 255) / 256), 256, 0, s>>>(frames, T, H, W, out, mean255[0], mean255[1],
                                                                   mean255[2], std255[0], std255[1], std255[2]);
     return 0;
@@ -135,6 +137,7 @@ int layernorm(const bf16* x, int ldx, const bf16* w, const bf16* b, bf16* y, int
     if (rows <= 0) return 0;
     if (dim % 8 || ldx % 8 || ldy % 8) return -1;
     const int warps_per_block = 8;
+    lcc::count_launch();
     layernorm_kernel<<<(rows + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, s>>>(
         x, ldx, w, b, y, ldy, rows, dim, eps);
     return 0;
@@ -178,6 +181,7 @@ int rmsnorm(const bf16* x, int ldx, const bf16* w, bf16* y, int ldy, int rows, i
     if (rows <= 0) return 0;
     if (dim % 8 || ldx % 8 || ldy % 8) return -1;
     const int warps_per_block = 8;
+    lcc::count_launch();
     rmsnorm_kernel<<<(rows + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, s>>>(
         x, ldx, w, y, ldy, rows, dim, eps);
     return 0;
@@ -215,7 +219,7 @@ int vit_rope_table(float* cos_t, float* sin_t, int t, int h, int w, int merge, i
     const int half = head_dim / 2;
     const int total = t * h * w * half;
     if (total <= 0) return 0;
-    vit_rope_table_kernel<<<(total + 255) / 256, 256, 0, s>>>(cos_t, sin_t, t, h, w, merge, half, inv_freq);
+    { lcc::count_launch(); vit_rope_table_kernel<<<(total + 255) / 256, 256, 0, s>>>(cos_t, sin_t, t, h, w, merge, half, inv_freq); }
     return 0;
 }
 
@@ -265,7 +269,7 @@ int vit_rope_apply(bf16* qkv, int ld, const float* cos_t, const float* sin_t, in
     if ((hd / 2) % 8 || ld % 8) return -1;
     const int64_t total = (int64_t)N * 2 * heads * (hd / 16);
     if (total <= 0) return 0;
-    vit_rope_apply_kernel<<<(int)((total + 255) / 256), 256, 0, s>>>(qkv, ld, cos_t, sin_t, N, heads, hd);
+    { lcc::count_launch(); vit_rope_apply_kernel<<<(int)((total + 255) / 256), 256, 0, s>>>(qkv, ld, cos_t, sin_t, N, heads, hd); }
     return 0;
 }
 
@@ -332,7 +336,8 @@ int embed_gather(const int64_t* ids, const bf16* table, const bf16* video, int n
                  int* rank_ws, int* total_video, int S, int H, int64_t vocab, cudaStream_t s) {
     if (S <= 0) return 0;
     if (H % 8) return -1;
-    video_rank_kernel<<<1, 1024, 0, s>>>(ids, S, video ? video_id : (int64_t)-1, rank_ws, total_video);
+    { lcc::count_launch(); video_rank_kernel<<<1, 1024, 0, s>>>(ids, S, video ? video_id : (int64_t)-1, rank_ws, total_video); }
+    lcc::count_launch();
     embed_gather_kernel<<<S, 128, 0, s>>>(ids, rank_ws, table, video, out, S, H, vocab, video ? n_video_rows : 0);
     return 0;
 }
@@ -413,6 +418,7 @@ int mrope_kv_write(bf16* qkv, int ld, const int* pos3, int S, const float* inv_f
     const int64_t warps = (int64_t)S * (Hq + 2 * Hkv);
     const int wpb = 8;
     MropeSections sec{sec_t, sec_h};
+    lcc::count_launch();
     mrope_kv_write_kernel<<<(int)((warps + wpb - 1) / wpb), wpb * 32, 0, s>>>(
         qkv, ld, pos3, S, inv_freq, sec, Hq, Hkv, kc, vc, page_table, page_size, kv_start);
     return 0;

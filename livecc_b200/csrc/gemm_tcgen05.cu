@@ -341,6 +341,7 @@ static int launch_cfg(const GemmArgs& a, int num_sms, cudaStream_t stream) {
     const int splits = (EPI == EPI_PARTIAL_F32 && a.splits > 1) ? a.splits : 1;
     const int tiles = m_tiles * n_tiles * splits;
     const int grid = tiles < num_sms ? tiles : num_sms;
+    lcc::count_launch();
     kern<<<grid, 384, Cfg::SMEM_BYTES, stream>>>(ta, tb, (bf16*)a.C, a.M, a.N, a.K, a.ldc,
                                                  (const bf16*)a.bias, (const bf16*)a.residual,
                                                  a.ldr, splits);
@@ -444,6 +445,7 @@ static int try_splitk(const GemmArgs& a, int num_sms, cudaStream_t stream) {
     }
     if (r) return r;
     const int64_t threads = (int64_t)a.M * (a.N / 8);
+    lcc::count_launch();
     splitk_reduce_kernel<<<(int)((threads + 255) / 256), 256, 0, stream>>>(
         (const float*)a.splitk_ws, splits, a.M, a.N, (const bf16*)a.bias, (const bf16*)a.residual, a.ldr, (bf16*)a.C,
         a.ldc, a.epi);

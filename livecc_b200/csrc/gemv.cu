@@ -299,6 +299,7 @@ static int check_common(const GemvParams& p) {
     do {                                                                                               \
         static SmemAttrOnce once_;                                                                     \
         if (ensure_dyn_smem(once_, kern, 200 * 1024)) return -3;                                       \
+        count_launch();                                                                                \
         if (launch_kernel(kern, dim3(grid), dim3(block), (size_t)(smem), s, pdl, p) != cudaSuccess) return -4; \
     } while (0)
 #define LCC_LAUNCH(kern, grid, smem) LCC_LAUNCH_B(kern, grid, 256, smem)

@@ -2,7 +2,16 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
+#include <stdint.h>
+
 namespace lcc {
+
+// Process-wide count of kernel launches issued by this library (every launch site calls count_launch()). Launches
+// recorded into a CUDA graph are counted once at capture; the host adds (nodes x replays) itself. Read through
+// lcc_launch_count() (bench.py's `gpu_launches` is this counter, not arithmetic).
+inline std::atomic<uint64_t> g_launches{0};
+inline void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute of a kernel: remember per (kernel
 // instantiation, device) that it was raised, so a second engine on another device of the same process works.

@@ -10,6 +10,7 @@
 #include "../../include/livecc_b200.h"
 #include "cabi_common.h"
 #include "gemm.h"
+#include "launch.h"
 #include "ops.h"
 
 using lcc::bf16;
@@ -201,6 +202,7 @@ static int vit_forward_impl(lcc_model* m, const float* pixel_values, const uint8
     STEP(gemm(m, vx, c.patch_dim, m->w.patch_w, c.patch_dim, vh, dim, N, dim, c.patch_dim, nullptr, nullptr, 0,
               lcc::EPI_NONE, s), "vit patch_embed");
     STEP(lcc::vit_rope_table(vcos, vsin, t, h, w, c.merge, hd, m->w.vit_inv_freq, s), "vit rope table");
+    lcc::count_launch();
     fill_cu_seqlens_kernel<<<(t + 256) / 256, 256, 0, s>>>(vcu, t, h * w);
     for (int i = 0; i < c.vit_depth; ++i) {
         const lcc_vit_block_weights& b = m->vit_blocks[i];

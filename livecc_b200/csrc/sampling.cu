@@ -8,6 +8,7 @@
 // Everything the next step needs stays on the device, so a whole generate() call runs without a host sync.
 #include "../../include/livecc_b200.h"
 #include "common.cuh"
+#include "launch.h"
 #include "ops.h"
 
 namespace lcc {
@@ -131,7 +132,7 @@ __global__ void __launch_bounds__(1024) sample_greedy_kernel(const SampleArgs a)
 
 int sample_greedy(const SampleArgs& a, cudaStream_t s) {
     if (a.V <= 0 || a.H % 8) return -1;
-    sample_greedy_kernel<<<1, 1024, 0, s>>>(a);
+    { lcc::count_launch(); sample_greedy_kernel<<<1, 1024, 0, s>>>(a); }
     return 0;
 }
 

@@ -95,6 +95,8 @@ class LiveCCB200ForConditionalGeneration:
         self._cap_patches, self._cap_tokens = 0, 0
         self._ensure_workspace(3072, 1024)
         self._graphs = {}
+        self._captured_launches = 0   # launches recorded into graphs (counted by the library at capture, never executed then)
+        self._replayed_launches = 0   # kernel nodes executed through graph replays
         self.use_cuda_graph = os.environ.get("LIVECC_B200_NO_GRAPH", "0") != "1"
         # split-KV factor of the decode attention: at most one CTA per SM, at least ~8 KV tiles (512 tokens) per split
         self.max_nsplit = max(1, min(64, (self.ctx.num_sms + t.num_key_value_heads - 1) // t.num_key_value_heads))
@@ -406,15 +408,24 @@ class LiveCCB200ForConditionalGeneration:
             side = torch.cuda.Stream(device=self.device)
             side.wait_stream(torch.cuda.current_stream(self.device))
             g = torch.cuda.CUDAGraph()
+            n0 = _cabi.launch_count()
             with torch.cuda.stream(side):
                 with torch.cuda.graph(g, stream=side, capture_error_mode="thread_local"):
                     self._native.decode_steps(st, 1, nsplit, sp)
             torch.cuda.current_stream(self.device).wait_stream(side)
+            g.lcc_nodes = _cabi.launch_count() - n0
+            self._captured_launches += g.lcc_nodes
             self._graphs[key] = g
         for i in range(n_steps):
             g.replay()
+            self._replayed_launches += g.lcc_nodes
             if logits_hist is not None:  # a finished stream replays no-ops and leaves the last logits in place
                 logits_hist[i].copy_(self._raw_logits())
+
+    def kernel_launches(self) -> int:
+        """Kernels of liblivecc_sm100a.so executed so far in this process (counted at the launch sites; launches
+        recorded into CUDA graphs are counted per replay). NB: process-wide for the eager part."""
+        return _cabi.launch_count() - self._captured_launches + self._replayed_launches
 
     def _raw_logits(self) -> torch.Tensor:
         off = self._native.logits_offset

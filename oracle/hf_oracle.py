@@ -44,10 +44,31 @@ def to_hf_config(cfg, attn_implementation: str = "eager"):
     return hf
 
 
+_LIGER_APPLIED = [False]
+
+
+def apply_liger():
+    """Oracle variant (B) of SURVEY.md §7: the reference's real GPU path calls
+    `liger_kernel.transformers.apply_liger_kernel_to_qwen2_vl()` before the model is built (REF/demo/infer.py:2-3,
+    REF/inference.md:14). The patch swaps module-level symbols of transformers for the rest of the process, so a
+    test that uses it must run after every variant-(A) test of the same process."""
+    from liger_kernel.transformers import apply_liger_kernel_to_qwen2_vl
+
+    apply_liger_kernel_to_qwen2_vl()
+    _LIGER_APPLIED[0] = True
+
+
+def oracle_variant(attn_implementation: str) -> str:
+    return f"HF transformers bf16 + {attn_implementation}" + (" + liger_kernel (variant B)" if _LIGER_APPLIED[0] else " (variant A)")
+
+
 def build_hf_model(cfg, tensors: Iterable[Tuple[str, torch.Tensor]] | Dict[str, torch.Tensor],
-                   dtype=torch.float32, device="cpu", attn_implementation: str = "eager"):
+                   dtype=torch.float32, device="cpu", attn_implementation: str = "eager", liger: bool = False):
     """Instantiates HF Qwen2-VL the way `from_pretrained(torch_dtype=...)` does (parameters created in
-    `dtype`, the fp32 rotary `inv_freq` buffers left in fp32) and loads the given HF-named tensors."""
+    `dtype`, the fp32 rotary `inv_freq` buffers left in fp32) and loads the given HF-named tensors.
+    liger=True: apply_liger() first (process-wide!)."""
+    if liger:
+        apply_liger()
     from transformers import Qwen2VLForConditionalGeneration
 
     hf_cfg = to_hf_config(cfg, attn_implementation)
@@ -95,10 +116,10 @@ def hf_generate_chunk(model, inputs: dict, past_key_values, past_ids: Optional[t
     `inputs`: processor output for the new turn (input_ids = new tokens only)."""
     dev = model.device
     new_ids = inputs["input_ids"].to(dev)
-    kw = dict(
-        pixel_values_videos=inputs["pixel_values_videos"].to(dev),
-        video_grid_thw=inputs["video_grid_thw"].to(dev),
-    )
+    kw = {}
+    if inputs.get("pixel_values_videos") is not None:  # text-only turns (history building) carry no pixels
+        kw = dict(pixel_values_videos=inputs["pixel_values_videos"].to(dev),
+                  video_grid_thw=inputs["video_grid_thw"].to(dev))
     if past_ids is not None:
         input_ids = torch.cat([past_ids, new_ids], dim=1)
     else:
