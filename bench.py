@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--max-new-tokens", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-batch", action="store_true", help="skip the multi-stream (generate_batch) sweep")
     return ap.parse_args()
 
 
@@ -134,7 +135,7 @@ def build_chunks(cfg, seconds, size, seed):
     return out, path
 
 
-def run_stream_device(eng, chunks_dev, max_new):
+def run_stream_device(eng, chunks_dev, max_new, keep_cache=False):
     """Device-resident inputs: one generate() per chunk, ids threaded on the device."""
     cache, past_ids = None, None
     n_tok = n_frames = 0
@@ -151,8 +152,31 @@ def run_stream_device(eng, chunks_dev, max_new):
         n_frames += ch["frames"]
         lat.append((time.perf_counter() - t0) / ch["frames"])
     kv = cache.get_seq_length()
+    if keep_cache:
+        return n_tok, n_frames, lat, kv, cache
     cache.release()
     return n_tok, n_frames, lat, kv
+
+
+def run_streams_batched(eng, chunks_dev, max_new, B, n_chunks=None):
+    """B concurrent streams on ONE GPU through generate_batch: per chunk the ViT and the prefill
+    run per stream, the decode steps run batched in the persistent kernel (weights read once per step for all B)."""
+    caches, pasts = [None] * B, [None] * B
+    n_tok = n_frames = 0
+    for ch in chunks_dev[:n_chunks]:
+        reqs = []
+        for b in range(B):
+            ids = ch["input_ids"] if pasts[b] is None else torch.cat([pasts[b], ch["input_ids"]], dim=1)
+            reqs.append(dict(input_ids=ids, pixel_values_videos=ch["pixel_values_videos"], video_grid_thw=ch["video_grid_thw"],
+                             past_key_values=caches[b]))
+        outs = eng.generate_batch(reqs, repetition_penalty=1.05, max_new_tokens=max_new, do_sample=False)
+        for b, o in enumerate(outs):
+            caches[b], pasts[b] = o.past_key_values, o.sequences[:, :-1]
+            n_tok += o.sequences.shape[1] - reqs[b]["input_ids"].shape[1]
+            n_frames += ch["frames"]
+    for c in caches:
+        c.release()
+    return n_tok, n_frames
 
 
 _E2E_RUN = [0]
@@ -200,29 +224,37 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def time_dominant_kernel(eng, iters=5):
-    """decode gate/up GEMV (gemv_rows_kernel<2,true,SWIGLU>): fused RMSNorm + [2I,H] weight stream + SwiGLU.
-    Algorithmic bytes/launch = 2I*H*2 (weights) + H*2 (x) + H*2 (norm w) + I*2 (out). Cycles through all layers
-    so every launch streams a different 271 MB (7B) weight, i.e. inputs >> L2."""
+def time_dominant_kernel(eng, chunks_dev, max_new, iters=20):
+    """The dominant kernel = decode_mega_kernel: one launch = one decode step of one stream (28 layers + lm_head).
+    Timed alone with CUDA events on its launch stream (the sub-range hook of the C ABI launches exactly the kernel the
+    CUDA-graph step contains, without the token selection, so the stream state does not advance and every launch
+    re-reads the same bytes): algorithmic bytes per launch = all decoder weights + lm_head + the stream's KV at the
+    clip's final length; inputs (14 GB) >> L2 (126 MB)."""
+    from livecc_b200 import _cabi
+
     t = eng.config.text_config
-    H, I = t.hidden_size, t.intermediate_size
-    x = torch.randn(H, device=eng.device).to(torch.bfloat16)
+    _, _, _, kv, cache = run_stream_device(eng, chunks_dev, max_new, keep_cache=True)
+    cache.scalars[_cabi.SC_FINISHED] = 0
+    st = [cache.stream_state()]
+    L = t.num_hidden_layers
     stream = torch.cuda.current_stream()
-    for lw in eng.weights.layers:  # warm-up
-        eng.ctx.gemv_norm_swiglu(lw.gate_up_w, x, lw.ln2_w, t.rms_norm_eps)
+    for _ in range(3):
+        eng._native.decode_mega_debug(st, 0, L, 31, 1)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n = 0
     e0.record(stream)
     for _ in range(iters):
-        for lw in eng.weights.layers:
-            eng.ctx.gemv_norm_swiglu(lw.gate_up_w, x, lw.ln2_w, t.rms_norm_eps)
-            n += 1
+        eng._native.decode_mega_debug(st, 0, L, 31, 1)
     e1.record(stream)
     torch.cuda.synchronize()
-    sec = e0.elapsed_time(e1) / 1e3 / n
-    nbytes = 2 * I * H * 2 + 2 * H * 2 + I * 2
-    return nbytes, sec
+    sec = e0.elapsed_time(e1) / 1e3 / iters
+    err = eng._native.mega_error()
+    cache.release()
+    weight_bytes = (L * ((t.num_attention_heads + 2 * t.num_key_value_heads) * 128 * t.hidden_size + t.hidden_size * t.hidden_size
+                         + 3 * t.intermediate_size * t.hidden_size + 2 * t.hidden_size) + t.hidden_size
+                    + t.vocab_size * t.hidden_size) * 2
+    kv_bytes = 2 * L * t.num_key_value_heads * 128 * 2 * kv
+    return weight_bytes + kv_bytes, sec, kv, err
 
 
 # ------------------------------------------------------------------------------------------------
@@ -492,13 +524,14 @@ def main():
     lat_sorted = sorted(lat)
     p50 = lat_sorted[len(lat_sorted) // 2] * 1e3
     peak, peak_src = load_peaks()
-    kbytes, ksec = time_dominant_kernel(eng)
+    kbytes, ksec, k_kv, k_err = time_dominant_kernel(eng, chunks_dev, args.max_new_tokens)
     traffic, traffic_src = None, None
     try:  # dram bytes of the same kernel from the committed `ncu --set full` capture (7B dims only)
         if args.model == "7b":
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_gateup_ncu.json")))
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r02_mega_ncu.json")))
             traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
-            traffic_src = "static: one `ncu --set full` capture of this kernel (profiles/r01_gateup_ncu.json), not measured in this run"
+            traffic_src = ("static: one `ncu --set full` capture of this kernel at kv_len %d (profiles/r02_mega_ncu.json), "
+                           "not measured in this run" % tr.get("kv_len", -1))
     except Exception:
         traffic = None
     t = cfg.text_config
@@ -512,7 +545,8 @@ def main():
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic (hash-filled checkpoint, synthetic frames and token ids)",
         "config": config, "frames_per_s": tot_frames / max_sec, "p50_frame_latency_ms": p50,
         "kv_len_end": kv_end, "clocks": clocks, "gpu_launches": int(gpu_launches),
-        "roofline": {"kernel": "gemv_rows_kernel<2,NORM,SWIGLU> (decode gate/up + RMSNorm + SwiGLU)", "bound": "hbm",
+        "roofline": {"kernel": "decode_mega_kernel (persistent decode step: 28 layers + lm_head, 1 stream, kv_len %d)" % k_kv,
+                     "bound": "hbm", "native_error": k_err,
                      "achieved": kbytes / ksec / 1e9, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                      "frac": kbytes / ksec / 1e9 / peak, "traffic": traffic, "traffic_source": traffic_src,
                      "bytes_per_launch": kbytes,
@@ -540,6 +574,23 @@ def main():
                              "bound": "hbm", "bytes_per_step_mean": int(bytes_avg), "ms_per_step": ms_per_dstep,
                              "achieved": bytes_avg / (ms_per_dstep / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
                              "frac": bytes_avg / (ms_per_dstep / 1e3) / 1e9 / peak, "decode_steps": dsteps}
+    if not args.no_batch and world == 1:
+        # multi-stream batching on one GPU: aggregate tokens/s of B concurrent streams over the same clip
+        ms = {}
+        for B in (2, 4, 8):
+            run_streams_batched(eng, chunks_dev, args.max_new_tokens, B, n_chunks=3)  # warm-up: graphs, workspace
+            torch.cuda.synchronize()
+            eng.phase_ms_total.update(decode=0.0, decode_steps=0)
+            b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            b0.record()
+            a, b = run_streams_batched(eng, chunks_dev, args.max_new_tokens, B)
+            b1.record()
+            torch.cuda.synchronize()
+            bs = b0.elapsed_time(b1) / 1e3
+            ms[f"B{B}"] = {"tokens_per_s": a / bs, "frames_per_s": b / bs, "speedup_vs_B1": a / bs / (tot_tok / max_sec),
+                           "decode_ms_per_step": eng.phase_ms_total["decode"] / max(eng.phase_ms_total["decode_steps"], 1)}
+        line["multi_stream"] = {"api": "LiveCCB200ForConditionalGeneration.generate_batch (B streams, one GPU, one clip pass each)",
+                                **ms}
     if not args.no_cpu_baseline and world == 1:
         try:
             r = cpu_reference_sample(cfg, args.size, max_new=args.max_new_tokens, steps=1, warmup=0, budget_s=60.0)

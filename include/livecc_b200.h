@@ -56,6 +56,7 @@ typedef void* lcc_stream_t; /* cudaStream_t */
 #define LCC_SC_SEQ_LEN 4      /* ids in the sequence buffer (history + generated) */
 #define LCC_SC_LAST_TOKEN 5
 #define LCC_SC_VIDEO_TOKENS 6 /* number of video placeholder ids seen by the last lcc_prefill (mq2vl.py:1169-1175 check) */
+#define LCC_SC_NATIVE_ERROR 7 /* non-zero: a bounded wait inside the persistent decode kernel gave up (results invalid) */
 #define LCC_SC_COUNT 8
 
 int lcc_abi_version(void);
@@ -247,19 +248,38 @@ int lcc_vit_forward_frames(lcc_model* m, const uint8_t* frames, int T, int H, in
 /* Prefill of S new tokens (Qwen2VLModel.forward + lm_head on the last token, mq2vl.py:1230-1300,
  * 828-910, 1437) followed by the first token selection. ids: device int64[S] (the new tokens);
  * pos3: device int32[3,S]; video_embeds: bf16 [n_video_rows, hidden] or NULL; past = tokens already
- * cached. Host must have set scalars {KV_LEN = past+S, ROPE_POS, FINISHED=0, N_GENERATED=0, SEQ_LEN}. */
+ * cached. Host must have set scalars {KV_LEN = past+S, ROPE_POS, FINISHED=0, N_GENERATED=0, SEQ_LEN}.
+ * slot (0..7): which row of the decode-step buffers receives the first token's embedding and logits; 0 for the
+ * one-stream path, b for stream b of a lcc_decode_batch group. */
 int lcc_prefill(lcc_model* m, const lcc_stream_state* st, const int64_t* ids, const int32_t* pos3, int S,
-                int past, const void* video_embeds, int n_video_rows, const lcc_sampling* sp, lcc_stream_t stream);
+                int past, const void* video_embeds, int n_video_rows, const lcc_sampling* sp, int slot, lcc_stream_t stream);
 
 /* n_steps x (one-token forward + token selection) (the loop body of _sample, gen/utils.py:2743-2805).
  * No-ops once scalars[LCC_SC_FINISHED] is set. Capturable in a CUDA graph. nsplit: KV splits (1..64). */
 int lcc_decode_steps(lcc_model* m, const lcc_stream_state* st, int n_steps, int nsplit, const lcc_sampling* sp,
                      lcc_stream_t stream);
 
+/* Batched decode (the reference demo admits 5 concurrent sessions on one model,
+ * REF/demo/app.py:178): n_steps x (one persistent kernel = every decoder layer + lm_head for all n_streams <= 8 streams,
+ * each weight byte read once per step, then one token selection per stream). states[b] must have been prefilled with
+ * slot = b and share one page pool. A stream's ids and logits are bit-identical to decoding it alone (same kernel,
+ * same reduction order). lcc_decode_steps routes through this with n_streams = 1 unless LIVECC_B200_MEGA=0. */
+int lcc_decode_batch(lcc_model* m, const lcc_stream_state* states, int n_streams, int n_steps, const lcc_sampling* sp,
+                     lcc_stream_t stream);
+/* Test hook: run layers [layer_begin, layer_end) and the phases in phase_mask (1 qkv, 2 attention, 4 o_proj,
+ * 8 gate/up, 16 down_proj) of the persistent decode kernel, optionally the lm_head, without token selection. */
+int lcc_decode_mega_debug(lcc_model* m, const lcc_stream_state* states, int n_streams, int layer_begin, int layer_end,
+                          int phase_mask, int do_head, lcc_stream_t stream);
+
 /* Debug/parity hooks: byte offsets of buffers inside the bound workspace. */
 #define LCC_WS_PREFILL_HIDDEN 0 /* bf16 [S, hidden] residual stream of the last prefill */
-#define LCC_WS_LOGITS 1         /* f32 [vocab] raw logits of the last token selection */
-#define LCC_WS_DECODE_HIDDEN 2  /* bf16 [hidden] embedding row / residual stream of the decode step */
+#define LCC_WS_LOGITS 1         /* f32 [8][vocab] raw logits of the last token selection (row = slot) */
+#define LCC_WS_DECODE_HIDDEN 2  /* bf16 [8][hidden] embedding row / residual stream of the decode step (row = slot) */
+#define LCC_WS_DECODE_QKV 3     /* bf16 [8][(Hq+2Hkv)*128] */
+#define LCC_WS_DECODE_ATTN 4    /* bf16 [8][Hq*128] */
+#define LCC_WS_DECODE_ACT 5     /* bf16 [8][inter] */
+#define LCC_WS_LOGITS_PROC 6    /* f32 [8][vocab] processed logits */
+#define LCC_WS_MEGA_ERROR 7     /* int32: sticky error flag of the persistent decode kernel (0 = ok) */
 size_t lcc_ws_offset(const lcc_model* m, int which);
 
 #ifdef __cplusplus

@@ -19,8 +19,9 @@ PAGE_SIZE = 64
 # epilogue codes (LCC_EPI_*)
 EPI_NONE, EPI_BIAS, EPI_BIAS_QUICKGELU, EPI_BIAS_GELU, EPI_RESIDUAL, EPI_BIAS_RESIDUAL, EPI_SWIGLU = range(7)
 # stream scalar slots (LCC_SC_*)
-SC_KV_LEN, SC_ROPE_POS, SC_FINISHED, SC_N_GENERATED, SC_SEQ_LEN, SC_LAST_TOKEN, SC_VIDEO_TOKENS = range(7)
+SC_KV_LEN, SC_ROPE_POS, SC_FINISHED, SC_N_GENERATED, SC_SEQ_LEN, SC_LAST_TOKEN, SC_VIDEO_TOKENS, SC_NATIVE_ERROR = range(8)
 SC_COUNT = 8
+MAX_BATCH = 8  # streams per persistent decode launch (MG_MAXB)
 
 
 class LiveCCNativeError(RuntimeError):
@@ -343,6 +344,18 @@ class NativeModel:
         self.hidden_offset = self.lib.lcc_ws_offset(C.c_void_p(self.handle), 0)
         self.logits_offset = self.lib.lcc_ws_offset(C.c_void_p(self.handle), 1)
         self.decode_hidden_offset = self.lib.lcc_ws_offset(C.c_void_p(self.handle), 2)
+        self.decode_qkv_offset = self.lib.lcc_ws_offset(C.c_void_p(self.handle), 3)
+        self.decode_attn_offset = self.lib.lcc_ws_offset(C.c_void_p(self.handle), 4)
+        self.decode_act_offset = self.lib.lcc_ws_offset(C.c_void_p(self.handle), 5)
+        self.logits_proc_offset = self.lib.lcc_ws_offset(C.c_void_p(self.handle), 6)
+        self.mega_error_offset = self.lib.lcc_ws_offset(C.c_void_p(self.handle), 7)
+
+    def mega_error(self) -> int:
+        """Sticky error flag of the persistent decode kernel (synchronises the device)."""
+        import torch
+
+        off = self.mega_error_offset
+        return int(self.workspace[off:off + 4].view(torch.int32).item())
 
     def vit_forward(self, pixel_values, t, h, w, out):
         self._call("lcc_vit_forward", _ptr(pixel_values), _i(t), _i(h), _i(w), _ptr(out), Context.stream_ptr())
@@ -353,10 +366,20 @@ class NativeModel:
         sd = (C.c_float * 3)(*std255)
         self._call("lcc_vit_forward_frames", _ptr(frames_u8), _i(T), _i(H), _i(W), m, sd, _ptr(out), Context.stream_ptr())
 
-    def prefill(self, st: StreamState, ids, pos3, S, past, video_embeds, sampling: Sampling):
+    def prefill(self, st: StreamState, ids, pos3, S, past, video_embeds, sampling: Sampling, slot: int = 0):
         n_rows = video_embeds.shape[0] if video_embeds is not None else 0
         self._call("lcc_prefill", C.byref(st), _ptr(ids), _ptr(pos3), _i(S), _i(past), _ptr(video_embeds), _i(n_rows),
-                   C.byref(sampling), Context.stream_ptr())
+                   C.byref(sampling), _i(slot), Context.stream_ptr())
 
     def decode_steps(self, st: StreamState, n_steps, nsplit, sampling: Sampling):
         self._call("lcc_decode_steps", C.byref(st), _i(n_steps), _i(nsplit), C.byref(sampling), Context.stream_ptr())
+
+    def decode_batch(self, states, n_steps, sampling: Sampling):
+        """states: list of StreamState (<= MAX_BATCH), stream b prefilled with slot=b."""
+        arr = (StreamState * len(states))(*states)
+        self._call("lcc_decode_batch", arr, _i(len(states)), _i(n_steps), C.byref(sampling), Context.stream_ptr())
+
+    def decode_mega_debug(self, states, layer_begin, layer_end, phase_mask, do_head):
+        arr = (StreamState * len(states))(*states)
+        self._call("lcc_decode_mega_debug", arr, _i(len(states)), _i(layer_begin), _i(layer_end), _i(phase_mask),
+                   _i(do_head), Context.stream_ptr())

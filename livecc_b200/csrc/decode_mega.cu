@@ -1,0 +1,737 @@
+// Persistent decode-step kernel ("megakernel"): ONE launch runs all decoder layers + lm_head of one generated token
+// for up to 8 independent streams (Qwen2VLDecoderLayer.forward x L + norm + lm_head, mq2vl.py:613-662, 905, 1437;
+// the loop body of GenerationMixin._sample, gen/utils.py:2743-2805). It replaces the 6 kernels per layer of the
+// per-op path (gemv.cu + attention.cu), whose launch / first-load / tail latency kept the step at 70 % of the HBM
+// roofline, and it is what makes multi-stream batching a weight-read-once
+// operation.
+//
+// Structure (grid = #SMs, one CTA per SM, 288 threads):
+//   warp 8 (one lane)  : TMA producer. Walks the whole step's weight/KV tile sequence of this CTA (a pure function of
+//                        the model shape, the streams' KV lengths and the CTA index) and streams it through a shared
+//                        memory ring of 4 KB tiles (cp.async.bulk.tensor, SWIZZLE_128B, mbarrier complete_tx). It never
+//                        waits for a phase boundary: while the consumers sit in a grid barrier the next phase's weights
+//                        keep arriving, so HBM stays busy across the 5 dependent phases of a layer.
+//   warps 0-7          : consumers. A weight tile is 32 rows x 64 k; `mma.sync.m16n8k16` with the weights as the A
+//                        operand (ldmatrix from the swizzled tile) and the <= 8 stream activations as the 8 columns of
+//                        the B operand, fp32 accumulate. The K range of a row block is split across the 8 warps and
+//                        reduced through shared memory in a fixed order, so a stream's result does not depend on how
+//                        many other streams share the launch.
+//   phases per layer   : qkv (RMSNorm + bias) | attention (RoPE, KV append, paged split-KV, merge) | o_proj + residual
+//                        | gate/up (RMSNorm + SwiGLU) | down_proj + residual ; then final norm + lm_head.
+//                        Phases are separated by a grid barrier (atomic counter, bounded spin).
+// Attention work is cut into items of a fixed number of 32-token units per (stream, kv head) — a function of that
+// stream's KV length only — so the split-KV partials, and therefore the logits, are identical whether a stream is
+// decoded alone or in a batch.
+// Every wait is bounded: a lost signal sets an error flag (reported through the stream scalars) instead of hanging.
+#include <math.h>
+#include <stdlib.h>
+
+#include "../../include/livecc_b200.h"
+#include "common.cuh"
+#include "gemm.h"
+#include "launch.h"
+#include "mega.h"
+#include "mma.cuh"
+
+namespace lcc {
+
+namespace {
+
+constexpr int NCW = 8;                  // consumer warps
+constexpr int NCT = NCW * 32;           // consumer threads
+constexpr int TILE = 4096;              // bytes per ring slot
+constexpr int QPITCH = 136;             // bf16 elements per staged q row
+constexpr int SCRATCH = 45056;
+// scratch carve-up (bytes)
+constexpr int SC_RED = 0;               // GEMV: float [2][8][32][8]                       (16384)
+constexpr int SC_PART = 16384;          // RMSNorm partial sums float [8] + flags int [8]  (64)
+constexpr int SC_QS = 0;                // attention: bf16 [16][136]                       (4352)
+constexpr int SC_KNEW = 4352;           // bf16 [128]
+constexpr int SC_VNEW = 4608;           // bf16 [128]
+constexpr int SC_SML = 4864;            // float [9][8][2]                                 (576)
+constexpr int SC_SO = 5632;             // float [9][8][128]                               (36864) -> 42496
+constexpr int SC_FLAG = 42496;          // int [4]
+
+__device__ __forceinline__ uint32_t ld_cg_u32(const void* p) {
+    uint32_t v;
+    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float ld_cg_bf16(const bf16* p) {
+    unsigned short v;
+    asm volatile("ld.global.cg.u16 %0, [%1];" : "=h"(v) : "l"(p));
+    return bf2f(__ushort_as_bfloat16(v));
+}
+__device__ __forceinline__ uint4 ld_cg_u128(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float ld_cg_f32(const float* p) {
+    float v;
+    asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float4 ld_cg_f32x4(const float* p) {
+    float4 r;
+    asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NCT) : "memory"); }
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ int ld_volatile_i32(const int* p) {
+    int v;
+    asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+constexpr unsigned long long kWaitLimitNs = 2000000000ull;  // 2 s: far beyond any legitimate wait inside one step
+
+// Bounded mbarrier wait: a lost signal flags the error (sticky, global) and lets the kernel run to completion with
+// garbage instead of hanging the GPU; once the flag is up every later wait gives up immediately.
+__device__ __forceinline__ bool mbar_wait_bounded(uint64_t* bar, uint32_t parity, int* err, int code) {
+    const uint32_t a = smem_u32(bar);
+    unsigned long long t0 = 0;
+    for (int it = 0;; ++it) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred P1;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, P1;\n\t}"
+            : "=r"(ok)
+            : "r"(a), "r"(parity)
+            : "memory");
+        if (ok) return true;
+        if (it < 64) continue;
+        if (ld_volatile_i32(err)) return false;
+        if (t0 == 0) t0 = globaltimer_ns();
+        else if (globaltimer_ns() - t0 > kWaitLimitNs) { atomicExch(err, code); return false; }
+    }
+}
+
+struct Shared {
+    uint8_t* ring;      // nslot x TILE, 1024-aligned
+    bf16* xs;           // [bpad][xpitch]
+    uint8_t* scratch;   // SCRATCH bytes
+    uint64_t* full;     // [nslot]
+    uint64_t* empty;    // [nslot]
+    int* s_T;           // [8] old tokens in the cache per stream
+    int* s_pos;         // [8] rope position of the new token
+    int* s_active;      // [8]
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// work enumeration shared by the producer and the consumers
+// ------------------------------------------------------------------------------------------------------------
+struct PairPlan {
+    int units;   // 32-token units of old tokens (>= 1)
+    int cu;      // units per item
+    int nitems;
+};
+__device__ __forceinline__ PairPlan plan_pair(int T) {
+    PairPlan pp;
+    pp.units = max(1, (T + 31) >> 5);
+    pp.cu = 8;
+    while ((pp.units + pp.cu - 1) / pp.cu > MG_MAX_ITEMS) pp.cu <<= 1;
+    pp.nitems = (pp.units + pp.cu - 1) / pp.cu;
+    return pp;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// producer
+// ------------------------------------------------------------------------------------------------------------
+struct Ring {
+    uint8_t* base;
+    uint64_t *full, *empty;
+    int nslot;
+    unsigned tile;  // running tile index of this CTA
+    int* err;
+};
+
+__device__ __forceinline__ void produce_tile(Ring& r, const CUtensorMap* tm, int c0, int c1) {
+    const unsigned slot = r.tile % r.nslot, ph = (r.tile / r.nslot) & 1;
+    mbar_wait_bounded(&r.empty[slot], ph ^ 1, r.err, 2);
+    mbar_arrive_expect_tx(&r.full[slot], TILE);
+    tma_load_2d(r.base + (size_t)slot * TILE, tm, &r.full[slot], c0, c1);
+    ++r.tile;
+}
+
+__device__ void producer_gemv(Ring& r, const CUtensorMap* tm, int N, int K, unsigned& rr, int cta, int G) {
+    const int RB = N >> 5, KC = K >> 6;
+    const int first = (int)(((unsigned)cta + (unsigned)G - rr % (unsigned)G) % (unsigned)G);
+    for (int b = first; b < RB; b += G)
+        for (int kc = 0; kc < KC; ++kc) produce_tile(r, tm, kc * 64, b * 32);
+    rr += RB;
+}
+
+__device__ void producer_attn(Ring& r, const MegaParams& p, const Shared& sh, const CUtensorMap* tk, const CUtensorMap* tv,
+                              int layer, unsigned& rr, int cta, int G) {
+    unsigned gi = 0;
+    for (int b = 0; b < p.B; ++b) {
+        if (!sh.s_active[b]) continue;
+        const PairPlan pp = plan_pair(sh.s_T[b]);
+        const int* pt = p.st[b].page_table;
+        for (int g = 0; g < p.Hkv; ++g, gi += pp.nitems) {
+            // item `it` of this pair has global index gi + it and belongs to CTA (rr + gi + it) mod G
+            const int it0 = (int)(((unsigned)cta + (unsigned)G - (rr + gi) % (unsigned)G) % (unsigned)G);
+            for (int it = it0; it < pp.nitems; it += G) {
+                const int u1 = min(pp.units, (it + 1) * pp.cu);
+                for (int u = it * pp.cu; u < u1; ++u) {
+                    const int t0 = u << 5;
+                    const int page = pt[t0 >> 6];
+                    const int row = layer * p.kv_rows_per_layer + (page * p.Hkv + g) * 64 + (t0 & 32);
+                    produce_tile(r, tk, 0, row);
+                    produce_tile(r, tk, 64, row);
+                    produce_tile(r, tv, 0, row);
+                    produce_tile(r, tv, 64, row);
+                }
+            }
+        }
+    }
+    rr += gi;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// consumers
+// ------------------------------------------------------------------------------------------------------------
+struct Cons {
+    uint8_t* ring;
+    uint64_t *full, *empty;
+    int nslot;
+    unsigned tile;  // tile index of the first tile of the current phase for this CTA
+    int* err;
+    int warp, lane, tid;
+};
+
+__device__ __forceinline__ uint32_t wait_tile(const Cons& c, unsigned t) {
+    const unsigned slot = t % c.nslot, ph = (t / c.nslot) & 1;
+    mbar_wait_bounded(&c.full[slot], ph, c.err, 3);
+    return smem_u32(c.ring + (size_t)slot * TILE);
+}
+__device__ __forceinline__ void release_tile(const Cons& c, unsigned t) {
+    __syncwarp();
+    if (c.lane == 0) mbar_arrive(&c.empty[t % c.nslot]);
+}
+
+// Grid-wide barrier among the consumer halves of all CTAs (the producers never wait here).
+__device__ __forceinline__ void grid_sync(const MegaParams& p, const Cons& c, unsigned& epoch, int G) {
+    consumer_sync();
+    ++epoch;
+    if (c.tid == 0) {
+        __threadfence();
+        atomicAdd(p.bar, 1u);
+        const unsigned target = epoch * (unsigned)G;
+        unsigned long long t0 = 0;
+        for (int it = 0; ld_acquire_u32(p.bar) < target; ++it) {
+            if (it < 256) continue;
+            if (ld_volatile_i32(p.err)) break;
+            if (t0 == 0) t0 = globaltimer_ns();
+            else if (globaltimer_ns() - t0 > kWaitLimitNs) { atomicExch(p.err, 1); break; }
+            __nanosleep(20);
+        }
+        __threadfence();
+    }
+    consumer_sync();
+}
+
+// xs[s][k] = (norm_w ? norm_w[k] * bf16(x[s][k] * rsqrt(mean(x^2) + eps)) : x[s][k]) for s < B, zeros for s >= B.
+__device__ void stage_x(const MegaParams& p, const Cons& c, const Shared& sh, const bf16* src, int K, const bf16* norm_w,
+                        int xpitch, int bpad) {
+    const int s = c.warp % bpad, sl = c.warp / bpad, nsl = NCW / bpad;
+    const int chunks = K >> 3;
+    const int c0 = (int)((long long)chunks * sl / nsl), c1 = (int)((long long)chunks * (sl + 1) / nsl);
+    float* part = reinterpret_cast<float*>(sh.scratch + SC_PART);
+    const bool live = s < p.B;
+    const bf16* row = src + (size_t)s * K;
+    if (norm_w) {
+        float sq = 0.f;
+        if (live)
+            for (int ch = c0 + c.lane; ch < c1; ch += 32) {
+                const uint4 u = ld_cg_u128(row + ch * 8);
+                const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { const float2 f = unpack_bf16x2(uw[j]); sq += f.x * f.x + f.y * f.y; }
+            }
+        sq = warp_sum(sq);
+        if (c.lane == 0) part[c.warp] = sq;
+        consumer_sync();
+        float tot = 0.f;
+        for (int j = 0; j < nsl; ++j) tot += part[s + bpad * j];
+        const float rs = rsqrtf(tot / (float)K + p.eps);
+        for (int ch = c0 + c.lane; ch < c1; ch += 32) {
+            uint4 o = make_uint4(0u, 0u, 0u, 0u);
+            if (live) {
+                const uint4 u = ld_cg_u128(row + ch * 8);
+                const uint4 wv = *reinterpret_cast<const uint4*>(norm_w + ch * 8);
+                const uint32_t uw[4] = {u.x, u.y, u.z, u.w}, ww[4] = {wv.x, wv.y, wv.z, wv.w};
+                uint32_t ov[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 f = unpack_bf16x2(uw[j]), g = unpack_bf16x2(ww[j]);
+                    ov[j] = pack_bf16x2(g.x * rbf(f.x * rs), g.y * rbf(f.y * rs));
+                }
+                o = make_uint4(ov[0], ov[1], ov[2], ov[3]);
+            }
+            *reinterpret_cast<uint4*>(sh.xs + (size_t)s * xpitch + ch * 8) = o;
+        }
+    } else {
+        for (int ch = c0 + c.lane; ch < c1; ch += 32) {
+            const uint4 o = live ? ld_cg_u128(row + ch * 8) : make_uint4(0u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(sh.xs + (size_t)s * xpitch + ch * 8) = o;
+        }
+    }
+    consumer_sync();
+}
+
+enum { EP_BIAS = 0, EP_RESIDUAL = 1, EP_SWIGLU = 2, EP_LOGITS = 3 };
+
+struct GemvOut {
+    const bf16* bias;   // EP_BIAS [N]
+    bf16* out;          // EP_BIAS: [8][N]; EP_RESIDUAL: residual stream [8][N] in/out; EP_SWIGLU: [8][N/2]
+    float *lg_raw, *lg_proc;  // EP_LOGITS [8][N]
+};
+
+// One GEMV phase over this CTA's row blocks. XG: activations read from global memory ([8][K], K too large for smem).
+template <int EP, bool XG>
+__device__ void consumer_gemv(const MegaParams& p, Cons& c, const Shared& sh, int N, int K, const bf16* xg, int xpitch,
+                              const GemvOut& o, unsigned& rr, int cta, int G) {
+    const int RB = N >> 5, KC = K >> 6;
+    const int first = (int)(((unsigned)cta + (unsigned)G - rr % (unsigned)G) % (unsigned)G);
+    rr += RB;
+    float* red = reinterpret_cast<float*>(sh.scratch + SC_RED);
+    const int g = c.lane >> 2, t = c.lane & 3;
+    int biter = 0;
+    for (int b = first; b < RB; b += G, ++biter) {
+        float acc[2][4];
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[m][j] = 0.f;
+        const unsigned tbase = c.tile + (unsigned)biter * KC;
+        for (int kc = c.warp; kc < KC; kc += NCW) {
+            uint32_t bx[4][2];
+            if (XG) {  // issue the activation loads before waiting for the weight tile
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    const bf16* xp = xg + (size_t)g * K + kc * 64 + kk * 16 + 2 * t;
+                    bx[kk][0] = g < p.B ? ld_cg_u32(xp) : 0u;
+                    bx[kk][1] = g < p.B ? ld_cg_u32(xp + 8) : 0u;
+                }
+            }
+            const uint32_t tb = wait_tile(c, tbase + kc);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                if (!XG) {
+                    const bf16* xp = sh.xs + (size_t)g * xpitch + kc * 64 + kk * 16 + 2 * t;
+                    bx[kk][0] = *reinterpret_cast<const uint32_t*>(xp);
+                    bx[kk][1] = *reinterpret_cast<const uint32_t*>(xp + 8);
+                }
+                const int r = (c.lane & 7) + ((c.lane >> 3) & 1) * 8;
+                const int ch = 2 * kk + (c.lane >> 4);
+                const uint32_t a0 = tb + r * 128 + ((ch ^ (r & 7)) << 4);
+                uint32_t af[4];
+                asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                             : "=r"(af[0]), "=r"(af[1]), "=r"(af[2]), "=r"(af[3]) : "r"(a0));
+                mma_bf16_16816(acc[0], af, bx[kk][0], bx[kk][1]);
+                asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                             : "=r"(af[0]), "=r"(af[1]), "=r"(af[2]), "=r"(af[3]) : "r"(a0 + 16 * 128));
+                mma_bf16_16816(acc[1], af, bx[kk][0], bx[kk][1]);
+            }
+            release_tile(c, tbase + kc);
+        }
+        // cross-warp K reduction, fixed order
+        float* rb = red + (biter & 1) * (NCW * 32 * 8);
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+            float* d0 = rb + ((c.warp * 32 + m * 16 + g) * 8) + 2 * t;
+            d0[0] = acc[m][0]; d0[1] = acc[m][1];
+            d0[8 * 8] = acc[m][2]; d0[8 * 8 + 1] = acc[m][3];
+        }
+        consumer_sync();
+        const int row = c.tid >> 3, col = c.tid & 7;
+        if (EP == EP_SWIGLU) {
+            if (c.tid < 128 && col < p.B) {
+                float gt = 0.f, up = 0.f;
+#pragma unroll
+                for (int w = 0; w < NCW; ++w) {
+                    gt += rb[(w * 32 + row) * 8 + col];
+                    up += rb[(w * 32 + 16 + row) * 8 + col];
+                }
+                gt = rbf(gt); up = rbf(up);
+                const float sl = rbf(gt / (1.0f + expf(-gt)));   // same rounding points as gemv.cu / mq2vl.py:503
+                o.out[(size_t)col * (N >> 1) + b * 16 + row] = f2bf(sl * up);
+            }
+        } else if (col < p.B) {
+            float v = 0.f;
+#pragma unroll
+            for (int w = 0; w < NCW; ++w) v += rb[(w * 32 + row) * 8 + col];
+            const int n = b * 32 + row;
+            if (EP == EP_BIAS) o.out[(size_t)col * N + n] = f2bf(v + bf2f(o.bias[n]));
+            else if (EP == EP_RESIDUAL) {
+                bf16* hp = o.out + (size_t)col * N + n;
+                *hp = f2bf(rbf(v) + ld_cg_bf16(hp));   // o_proj / down_proj + residual (mq2vl.py:645,660)
+            } else {
+                const float l = rbf(v);
+                o.lg_raw[(size_t)col * N + n] = l;
+                o.lg_proc[(size_t)col * N + n] = l;
+            }
+        }
+    }
+    c.tile += (unsigned)biter * KC;
+}
+
+__device__ __forceinline__ void rope_pair(const bf16* src, bf16* dst, int j, float pos, const float* inv_freq) {
+    // one (j, j+64) pair; torch bf16 semantics (each product and the sum rounded to bf16), as attention.cu::rope1d_row
+    const float ang = __fmul_rn(pos, inv_freq[j]);
+    const float cs = rbf(cosf(ang)), sn = rbf(sinf(ang));
+    const float x1 = ld_cg_bf16(src + j), x2 = ld_cg_bf16(src + j + 64);  // written by other CTAs in this launch: L2, not L1
+    dst[j] = f2bf(rbf(rbf(x1 * cs) + rbf(-x2 * sn)));
+    dst[j + 64] = f2bf(rbf(rbf(x2 * cs) + rbf(x1 * sn)));
+}
+
+// Attention phase: this CTA's items.
+__device__ void consumer_attn(const MegaParams& p, Cons& c, const Shared& sh, int layer, unsigned& rr, int cta, int G) {
+    constexpr int D = 128;
+    const int Gq = p.Hq / p.Hkv;  // query heads per KV head (<= 8)
+    bf16* qs = reinterpret_cast<bf16*>(sh.scratch + SC_QS);
+    bf16* knew = reinterpret_cast<bf16*>(sh.scratch + SC_KNEW);
+    bf16* vnew = reinterpret_cast<bf16*>(sh.scratch + SC_VNEW);
+    float* sml = reinterpret_cast<float*>(sh.scratch + SC_SML);
+    float* so = reinterpret_cast<float*>(sh.scratch + SC_SO);
+    int* flag = reinterpret_cast<int*>(sh.scratch + SC_FLAG);
+    const int g4 = c.lane >> 2, t4 = c.lane & 3;
+    unsigned gi = 0, tiles_done = 0;
+    for (int b = 0; b < p.B; ++b) {
+        if (!sh.s_active[b]) continue;
+        const int T = sh.s_T[b];
+        const PairPlan pp = plan_pair(T);
+        const float pos = (float)sh.s_pos[b];
+        const bf16* qkv = p.qkv + (size_t)b * p.qkv_dim;
+        for (int g = 0; g < p.Hkv; ++g, gi += pp.nitems) {
+            const int it0 = (int)(((unsigned)cta + (unsigned)G - (rr + gi) % (unsigned)G) % (unsigned)G);
+            for (int it = it0; it < pp.nitems; it += G) {
+                const int u0 = it * pp.cu, u1 = min(pp.units, (it + 1) * pp.cu);
+                const bool last_item = it == pp.nitems - 1;
+                // ---- stage the rotated q heads of this KV group (rows >= Gq zero); the owner of the pair's last
+                //      item also rotates + appends the new token's k and v ----
+                for (int i = c.tid; i < 16 * 64; i += NCT) {
+                    const int r = i >> 6, j = i & 63;
+                    if (r < Gq) rope_pair(qkv + (size_t)(g * Gq + r) * D, qs + r * QPITCH, j, pos, p.inv_freq);
+                    else { qs[r * QPITCH + j] = f2bf(0.f); qs[r * QPITCH + j + 64] = f2bf(0.f); }
+                }
+                if (last_item) {
+                    const int page = p.st[b].page_table[T >> 6], slot = T & 63;
+                    const size_t base = (size_t)layer * p.layer_stride + (((size_t)page * p.Hkv + g) * 64 + slot) * D;
+                    if (c.tid < 64) {
+                        rope_pair(qkv + (size_t)(p.Hq + g) * D, knew, c.tid, pos, p.inv_freq);
+                        p.k_pool[base + c.tid] = knew[c.tid];
+                        p.k_pool[base + c.tid + 64] = knew[c.tid + 64];
+                    } else if (c.tid < 80) {
+                        const int ch = c.tid - 64;
+                        const uint4 v = ld_cg_u128(qkv + (size_t)(p.Hq + p.Hkv + g) * D + ch * 8);
+                        *reinterpret_cast<uint4*>(vnew + ch * 8) = v;
+                        *reinterpret_cast<uint4*>(p.v_pool + base + ch * 8) = v;
+                    }
+                    if (slot == 0) {  // first token of a (possibly recycled) page: later rows must be finite for P = 0
+                        bf16* vt = p.v_pool + base + D;
+                        for (int i = c.tid; i < 63 * 16; i += NCT) *reinterpret_cast<uint4*>(vt + i * 8) = make_uint4(0u, 0u, 0u, 0u);
+                    }
+                }
+                consumer_sync();
+                // ---- per warp: flash pass over its 32-token units ----
+                uint32_t qf[D / 16][4];
+#pragma unroll
+                for (int kk = 0; kk < D / 16; ++kk) {
+                    const int mat = c.lane >> 3, r = c.lane & 7;
+                    ldmatrix_x4(qf[kk][0], qf[kk][1], qf[kk][2], qf[kk][3],
+                                qs + (size_t)((mat & 1) * 8 + r) * QPITCH + kk * 16 + (mat >> 1) * 8);
+                }
+                float oacc[D / 8][4];
+#pragma unroll
+                for (int d = 0; d < D / 8; ++d)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) oacc[d][j] = 0.f;
+                float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
+                for (int u = u0 + c.warp; u < u1; u += NCW) {
+                    const unsigned tb = c.tile + tiles_done + (unsigned)(u - u0) * 4;
+                    const uint32_t k_lo = wait_tile(c, tb), k_hi = wait_tile(c, tb + 1);
+                    const uint32_t v_lo = wait_tile(c, tb + 2), v_hi = wait_tile(c, tb + 3);
+                    const int valid = min(32, T - (u << 5));  // tokens of this unit that are old cache entries
+                    if (valid < 32) {  // rows >= valid may hold anything (recycled page / stale prefetch): P = 0 needs finite V
+                        for (int i = c.lane; i < (32 - valid) * 16; i += 32) {
+                            const int r = valid + (i >> 4), ch = i & 15;
+                            const uint32_t a = ((ch & 8) ? v_hi : v_lo) + r * 128 + (((ch & 7) ^ (r & 7)) << 4);
+                            asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%1};" ::"r"(a), "r"(0u) : "memory");
+                        }
+                        __syncwarp();
+                    }
+                    float s[4][4];
+#pragma unroll
+                    for (int n = 0; n < 4; ++n)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) s[n][j] = 0.f;
+#pragma unroll
+                    for (int kk = 0; kk < D / 16; ++kk) {
+                        const uint32_t kt = kk < 4 ? k_lo : k_hi;
+#pragma unroll
+                        for (int nt = 0; nt < 2; ++nt) {
+                            // x4: (tok 0-7,k 0-7) (tok 0-7,k 8-15) (tok 8-15,k 0-7) (tok 8-15,k 8-15)
+                            const int mat = c.lane >> 3, r = nt * 16 + (mat >> 1) * 8 + (c.lane & 7);
+                            const int ch = 2 * (kk & 3) + (mat & 1);
+                            uint32_t b0, b1, b2, b3;
+                            asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                                         : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3)
+                                         : "r"(kt + r * 128 + ((ch ^ (r & 7)) << 4)));
+                            mma_bf16_16816(s[nt * 2], qf[kk], b0, b1);
+                            mma_bf16_16816(s[nt * 2 + 1], qf[kk], b2, b3);
+                        }
+                    }
+                    if (valid < 32) {
+#pragma unroll
+                        for (int n = 0; n < 4; ++n) {
+                            const int kidx = n * 8 + 2 * t4;
+                            if (kidx >= valid) { s[n][0] = -INFINITY; s[n][2] = -INFINITY; }
+                            if (kidx + 1 >= valid) { s[n][1] = -INFINITY; s[n][3] = -INFINITY; }
+                        }
+                    }
+                    uint32_t pf[2][4];
+                    softmax_step<D, 2>(s, p.scale_log2, m, l, oacc, pf);
+#pragma unroll
+                    for (int kt2 = 0; kt2 < 2; ++kt2)
+#pragma unroll
+                        for (int dn = 0; dn < D / 16; ++dn) {
+                            // trans x4: (tok 0-7,d 0-7) (tok 8-15,d 0-7) (tok 0-7,d 8-15) (tok 8-15,d 8-15)
+                            const int mat = c.lane >> 3, r = kt2 * 16 + (mat & 1) * 8 + (c.lane & 7);
+                            const int ch = 2 * (dn & 3) + (mat >> 1);
+                            const uint32_t vt = dn < 4 ? v_lo : v_hi;
+                            uint32_t b0, b1, b2, b3;
+                            asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                                         : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3)
+                                         : "r"(vt + r * 128 + ((ch ^ (r & 7)) << 4)));
+                            mma_bf16_16816(oacc[dn * 2], pf[kt2], b0, b1);
+                            mma_bf16_16816(oacc[dn * 2 + 1], pf[kt2], b2, b3);
+                        }
+                    release_tile(c, tb); release_tile(c, tb + 1); release_tile(c, tb + 2); release_tile(c, tb + 3);
+                }
+                tiles_done += (unsigned)(u1 - u0) * 4;
+                l[0] += __shfl_xor_sync(0xffffffffu, l[0], 1);
+                l[0] += __shfl_xor_sync(0xffffffffu, l[0], 2);
+                // ---- merge the warps (+ the new token) of this item through shared memory; rows g4 < 8 only ----
+                consumer_sync();  // everybody is done with qs (SC_SO overlaps nothing, but SC_QS is re-staged next item)
+                {
+                    float* dst = so + ((size_t)c.warp * 8 + g4) * D + 2 * t4;
+#pragma unroll
+                    for (int d = 0; d < D / 8; ++d) { dst[d * 8] = oacc[d][0]; dst[d * 8 + 1] = oacc[d][1]; }
+                    if (t4 == 0) { sml[(c.warp * 8 + g4) * 2] = m[0]; sml[(c.warp * 8 + g4) * 2 + 1] = l[0]; }
+                }
+                if (last_item) {  // 9th contributor: the new token itself (score from the staged q and the rotated k)
+                    if (c.warp < Gq) {
+                        float dot = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) dot += bf2f(qs[c.warp * QPITCH + c.lane * 4 + j]) * bf2f(knew[c.lane * 4 + j]);
+                        dot = warp_sum(dot);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) so[((size_t)8 * 8 + c.warp) * D + c.lane * 4 + j] = bf2f(vnew[c.lane * 4 + j]);
+                        if (c.lane == 0) { sml[(8 * 8 + c.warp) * 2] = dot; sml[(8 * 8 + c.warp) * 2 + 1] = 1.f; }
+                    }
+                }
+                consumer_sync();
+                const int nsrc = last_item ? 9 : 8;
+                const size_t pbase = (((size_t)b * p.Hkv + g) * MG_MAX_ITEMS + it) * 8;
+                for (int i = c.tid; i < Gq * D; i += NCT) {
+                    const int r = i / D, d = i % D;
+                    float M = -INFINITY;
+                    for (int w = 0; w < nsrc; ++w) M = fmaxf(M, sml[(w * 8 + r) * 2]);
+                    float acc = 0.f, L = 0.f;
+                    for (int w = 0; w < nsrc; ++w) {
+                        const float mw = sml[(w * 8 + r) * 2];
+                        const float f = (mw == -INFINITY) ? 0.f : exp2f((mw - M) * p.scale_log2);
+                        acc += f * so[((size_t)w * 8 + r) * D + d];
+                        L += f * sml[(w * 8 + r) * 2 + 1];
+                    }
+                    p.part_o[(pbase + r) * D + d] = acc;
+                    if (d == 0) { p.part_ml[(pbase + r) * 2] = M; p.part_ml[(pbase + r) * 2 + 1] = L; }
+                }
+                __threadfence();
+                consumer_sync();
+                if (c.tid == 0) {
+                    const int prev = atomicAdd(&p.pair_cnt[b * p.Hkv + g], 1);
+                    flag[0] = (prev == pp.nitems - 1) ? 1 : 0;
+                    if (flag[0]) p.pair_cnt[b * p.Hkv + g] = 0;  // re-armed for the next layer
+                }
+                consumer_sync();
+                if (flag[0]) {  // last item of this (stream, kv head) to finish: merge the items in index order
+                    __threadfence();
+                    const size_t pb = ((size_t)b * p.Hkv + g) * MG_MAX_ITEMS * 8;
+                    for (int i = c.tid; i < Gq * (D / 4); i += NCT) {
+                        const int r = i / (D / 4), d4 = (i % (D / 4)) * 4;
+                        float M = -INFINITY;
+                        for (int q = 0; q < pp.nitems; ++q) M = fmaxf(M, ld_cg_f32(p.part_ml + (pb + (size_t)q * 8 + r) * 2));
+                        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                        float L = 0.f;
+                        for (int q = 0; q < pp.nitems; ++q) {
+                            const float mq = ld_cg_f32(p.part_ml + (pb + (size_t)q * 8 + r) * 2);
+                            const float f = (mq == -INFINITY) ? 0.f : exp2f((mq - M) * p.scale_log2);
+                            const float4 v = ld_cg_f32x4(p.part_o + (pb + (size_t)q * 8 + r) * D + d4);
+                            acc.x += f * v.x; acc.y += f * v.y; acc.z += f * v.z; acc.w += f * v.w;
+                            L += f * ld_cg_f32(p.part_ml + (pb + (size_t)q * 8 + r) * 2 + 1);
+                        }
+                        const float inv = L > 0.f ? 1.f / L : 0.f;
+                        uint2 o;
+                        o.x = pack_bf16x2(acc.x * inv, acc.y * inv);
+                        o.y = pack_bf16x2(acc.z * inv, acc.w * inv);
+                        *reinterpret_cast<uint2*>(p.attn + (size_t)b * p.Hq * D + (size_t)(g * Gq + r) * D + d4) = o;
+                    }
+                }
+                consumer_sync();
+            }
+        }
+    }
+    rr += gi;
+    c.tile += tiles_done;
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(MG_THREADS, 1)
+decode_mega_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
+                   const MegaParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int bpad = p.B <= 1 ? 1 : (p.B <= 2 ? 2 : (p.B <= 4 ? 4 : 8));
+    const int xpitch = p.H + 8;
+    Shared sh;
+    sh.ring = sm;
+    sh.xs = reinterpret_cast<bf16*>(sm + (size_t)p.nslot * TILE);
+    sh.scratch = reinterpret_cast<uint8_t*>(sh.xs) + (((size_t)bpad * xpitch * 2 + 127) & ~size_t(127));
+    sh.full = reinterpret_cast<uint64_t*>(sh.scratch + SCRATCH);
+    sh.empty = sh.full + MG_MAX_SLOTS;
+    sh.s_T = reinterpret_cast<int*>(sh.empty + MG_MAX_SLOTS);
+    sh.s_pos = sh.s_T + 8;
+    sh.s_active = sh.s_pos + 8;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cta = blockIdx.x, G = gridDim.x;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < p.nslot; ++i) { mbar_init(&sh.full[i], 1); mbar_init(&sh.empty[i], 1); }
+        fence_barrier_init();
+    }
+    if (threadIdx.x < 8) {
+        const int b = threadIdx.x;
+        int T = 0, pos = 0, act = 0;
+        if (b < p.B) {
+            const int* sc = p.st[b].scalars;
+            T = sc[LCC_SC_KV_LEN]; pos = sc[LCC_SC_ROPE_POS]; act = sc[LCC_SC_FINISHED] ? 0 : 1;
+        }
+        sh.s_T[b] = T; sh.s_pos[b] = pos; sh.s_active[b] = act;
+    }
+    __syncthreads();
+    int any = 0;
+    for (int b = 0; b < p.B; ++b) any |= sh.s_active[b];
+    if (!any) return;  // every stream is finished: the step is a no-op (graph replay after EOS)
+
+    const bool ph_qkv = p.phase_mask & 1, ph_attn = p.phase_mask & 2, ph_o = p.phase_mask & 4, ph_gu = p.phase_mask & 8,
+               ph_down = p.phase_mask & 16;
+    unsigned rr = 0;
+    if (warp == NCW) {
+        // ================================= producer =================================
+        if (lane == 0) {
+            Ring r{sh.ring, sh.full, sh.empty, p.nslot, 0u, p.err};
+            for (int l = p.layer_begin; l < p.layer_end; ++l) {
+                const CUtensorMap* wm = p.wmaps + 4 * l;
+                if (ph_qkv) producer_gemv(r, wm + 0, p.qkv_dim, p.H, rr, cta, G);
+                if (ph_attn) producer_attn(r, p, sh, &tmap_k, &tmap_v, l, rr, cta, G);
+                if (ph_o) producer_gemv(r, wm + 1, p.H, p.Hq * 128, rr, cta, G);
+                if (ph_gu) producer_gemv(r, wm + 2, 2 * p.I, p.H, rr, cta, G);
+                if (ph_down) producer_gemv(r, wm + 3, p.H, p.I, rr, cta, G);
+            }
+            if (p.do_head) producer_gemv(r, p.wmaps + 4 * p.L, p.V, p.H, rr, cta, G);
+        }
+        return;
+    }
+    // ================================= consumers =================================
+    Cons c{sh.ring, sh.full, sh.empty, p.nslot, 0u, p.err, warp, lane, (int)threadIdx.x};
+    unsigned epoch = 0;
+    for (int l = p.layer_begin; l < p.layer_end; ++l) {
+        const MegaLayer& ly = p.layers[l];
+        if (ph_qkv) {
+            stage_x(p, c, sh, p.h, p.H, ly.ln1_w, xpitch, bpad);
+            GemvOut o{ly.qkv_b, p.qkv, nullptr, nullptr};
+            consumer_gemv<EP_BIAS, false>(p, c, sh, p.qkv_dim, p.H, nullptr, xpitch, o, rr, cta, G);
+            grid_sync(p, c, epoch, G);
+        }
+        if (ph_attn) {
+            consumer_attn(p, c, sh, l, rr, cta, G);
+            grid_sync(p, c, epoch, G);
+        }
+        if (ph_o) {
+            stage_x(p, c, sh, p.attn, p.Hq * 128, nullptr, xpitch, bpad);
+            GemvOut o{nullptr, p.h, nullptr, nullptr};
+            consumer_gemv<EP_RESIDUAL, false>(p, c, sh, p.H, p.Hq * 128, nullptr, xpitch, o, rr, cta, G);
+            grid_sync(p, c, epoch, G);
+        }
+        if (ph_gu) {
+            stage_x(p, c, sh, p.h, p.H, ly.ln2_w, xpitch, bpad);
+            GemvOut o{nullptr, p.act, nullptr, nullptr};
+            consumer_gemv<EP_SWIGLU, false>(p, c, sh, 2 * p.I, p.H, nullptr, xpitch, o, rr, cta, G);
+            grid_sync(p, c, epoch, G);
+        }
+        if (ph_down) {
+            GemvOut o{nullptr, p.h, nullptr, nullptr};
+            consumer_gemv<EP_RESIDUAL, true>(p, c, sh, p.H, p.I, p.act, xpitch, o, rr, cta, G);
+            grid_sync(p, c, epoch, G);
+        }
+    }
+    if (p.do_head) {
+        stage_x(p, c, sh, p.h, p.H, p.final_norm_w, xpitch, bpad);
+        GemvOut o{nullptr, nullptr, p.logits_raw, p.logits_proc};
+        consumer_gemv<EP_LOGITS, false>(p, c, sh, p.V, p.H, nullptr, xpitch, o, rr, cta, G);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------
+int mega_smem_bytes(int H, int B, int* nslot_out) {
+    const int bpad = B <= 1 ? 1 : (B <= 2 ? 2 : (B <= 4 ? 4 : 8));
+    const int xs = ((bpad * (H + 8) * 2) + 127) & ~127;
+    const int fixed = 1024 /*align*/ + xs + SCRATCH + MG_MAX_SLOTS * 16 + 128;
+    int nslot = (232448 - fixed) / TILE;
+    if (nslot > MG_MAX_SLOTS) nslot = MG_MAX_SLOTS;
+    *nslot_out = nslot;
+    return fixed + nslot * TILE;
+}
+
+int mega_make_weight_tmap(CUtensorMap* tm, const void* w, int N, int K) {
+    return make_tmap_bf16_2d_box(tm, w, N, K, K, 64, 32, false);
+}
+
+int decode_mega_launch(const MegaParams& p_in, const void* k_pool, const void* v_pool, long long pool_rows, int num_sms,
+                       cudaStream_t s) {
+    MegaParams p = p_in;
+    if (p.B < 1 || p.B > MG_MAXB || p.Hq % p.Hkv || p.Hq / p.Hkv > 8) return -1;
+    if ((p.qkv_dim % 32) || (p.H % 64) || (p.I % 64) || ((2 * p.I) % 32) || (p.V % 32) || ((p.Hq * 128) % 64)) return -2;
+    int nslot = 0;
+    const int smem = mega_smem_bytes(p.H, p.B, &nslot);
+    if (nslot < 16) return -3;
+    p.nslot = nslot;
+    CUtensorMap tk, tv;
+    if (make_tmap_bf16_2d_box(&tk, k_pool, pool_rows, 128, 128, 64, 32, false)) return -10;
+    if (make_tmap_bf16_2d_box(&tv, v_pool, pool_rows, 128, 128, 64, 32, false)) return -11;
+    static SmemAttrOnce once;
+    if (ensure_dyn_smem(once, decode_mega_kernel, smem)) return -12;
+    count_launch();
+    decode_mega_kernel<<<num_sms, MG_THREADS, smem, s>>>(tk, tv, p);
+    return cudaGetLastError() == cudaSuccess ? 0 : -13;
+}
+
+}  // namespace lcc

@@ -11,6 +11,7 @@
 #include "cabi_common.h"
 #include "gemm.h"
 #include "launch.h"
+#include "mega.h"
 #include "ops.h"
 
 using lcc::bf16;
@@ -25,6 +26,8 @@ struct lcc_model {
     uint8_t* ws = nullptr;
     size_t ws_bytes = 0;
     int cap_patches = 0, cap_tokens = 0;
+    bool use_mega = true;   // persistent decode-step kernel (decode_mega.cu); LIVECC_B200_MEGA=0 selects the per-op kernels
+    bool mega_ok = false;   // geometry supported by the persistent kernel and its tables are uploaded
     bool fuse_attn_oproj = false;  // LIVECC_B200_FUSE=1: one launch for decode attention + o_proj (flag-synchronised roles)
     bool use_pdl = false;  // programmatic dependent launch between the decode-step kernels (LIVECC_B200_PDL=1 enables)
 };
@@ -40,7 +43,8 @@ int get_layout(const lcc_model* m, int need_patches, int need_tokens, WsLayout* 
 struct WsLayout {
     size_t vx, vh, vn, vqkv, vattn, vmlp, vcos, vsin, vcu;  // ViT
     size_t hid, normed, qkv, attn, act, rank, pf_part_o, pf_part_ml, pf_splitk;  // prefill
-    size_t h1, qkv1, attn1, act1, logits_raw, logits_proc, part_o, part_ml, attn_cnt;  // decode
+    size_t h1, qkv1, attn1, act1, logits_raw, logits_proc, part_o, part_ml, attn_cnt;  // decode (8 stream rows each)
+    size_t mg_part_o, mg_part_ml, mg_cnt, mg_tmaps, mg_layers;  // persistent decode kernel
     size_t total;
 };
 
@@ -72,15 +76,21 @@ WsLayout make_layout(const lcc_model_config& c, int NP, int NT) {
     L.pf_part_o = take(kPrefillSplitRows * (size_t)c.q_heads * 128 * 4);
     L.pf_part_ml = take(kPrefillSplitRows * (size_t)c.q_heads * 2 * 4);
     L.pf_splitk = take(kSplitKRows * (qkv_dim > (size_t)c.hidden ? qkv_dim : (size_t)c.hidden) * 4);
-    L.h1 = take((size_t)c.hidden * 2);
-    L.qkv1 = take(qkv_dim * 2);
-    L.attn1 = take((size_t)c.q_heads * 128 * 2);
-    L.act1 = take((size_t)c.inter * 2);
-    L.logits_raw = take((size_t)c.vocab * 4);
-    L.logits_proc = take((size_t)c.vocab * 4);
+    // decode-step vectors: row b belongs to stream slot b of a batched step (slot 0 = the single-stream path)
+    L.h1 = take((size_t)lcc::MG_MAXB * c.hidden * 2);
+    L.qkv1 = take((size_t)lcc::MG_MAXB * qkv_dim * 2);
+    L.attn1 = take((size_t)lcc::MG_MAXB * c.q_heads * 128 * 2);
+    L.act1 = take((size_t)lcc::MG_MAXB * c.inter * 2);
+    L.logits_raw = take((size_t)lcc::MG_MAXB * c.vocab * 4);
+    L.logits_proc = take((size_t)lcc::MG_MAXB * c.vocab * 4);
     L.part_o = take((size_t)kMaxSplit * c.q_heads * 128 * 4);
     L.part_ml = take((size_t)kMaxSplit * c.q_heads * 2 * 4);
     L.attn_cnt = take(64 * 4);
+    L.mg_part_o = take((size_t)lcc::MG_MAXB * c.kv_heads * lcc::MG_MAX_ITEMS * 8 * 128 * 4);
+    L.mg_part_ml = take((size_t)lcc::MG_MAXB * c.kv_heads * lcc::MG_MAX_ITEMS * 8 * 2 * 4);
+    L.mg_cnt = take(128 * 4);  // [0, 8*kv_heads): pair counters; [96]: grid barrier; [97]: sticky error flag
+    L.mg_tmaps = take((size_t)(4 * c.layers + 1) * sizeof(CUtensorMap));
+    L.mg_layers = take((size_t)c.layers * sizeof(lcc::MegaLayer));
     L.total = off;
     return L;
 }
@@ -107,13 +117,13 @@ int gemm(lcc_model* m, const void* A, int lda, const void* B, int ldb, void* C, 
     } while (0)
 
 lcc::SampleArgs make_sample(const lcc_model* m, const lcc_stream_state* st, const lcc_sampling* sp, uint8_t* ws,
-                            const WsLayout& L, int advance) {
+                            const WsLayout& L, int advance, int slot = 0) {
     lcc::SampleArgs a{};
-    a.logits_raw = reinterpret_cast<const float*>(ws + L.logits_raw);
-    a.logits_proc = reinterpret_cast<float*>(ws + L.logits_proc);
+    a.logits_raw = reinterpret_cast<const float*>(ws + L.logits_raw) + (size_t)slot * m->cfg.vocab;
+    a.logits_proc = reinterpret_cast<float*>(ws + L.logits_proc) + (size_t)slot * m->cfg.vocab;
     a.V = m->cfg.vocab;
-    a.seq = st->seq;
-    a.scalars = st->scalars;
+    a.seq = st ? st->seq : nullptr;
+    a.scalars = st ? st->scalars : nullptr;
     a.repetition_penalty = sp->repetition_penalty;
     a.inv_repetition_penalty = sp->inv_repetition_penalty;
     a.thr_token = sp->thr_token;
@@ -124,7 +134,7 @@ lcc::SampleArgs make_sample(const lcc_model* m, const lcc_stream_state* st, cons
     a.max_new_tokens = sp->max_new_tokens;
     a.advance_kv = advance;
     a.embed = reinterpret_cast<const bf16*>(m->w.embed);
-    a.h = reinterpret_cast<bf16*>(ws + L.h1);
+    a.h = reinterpret_cast<bf16*>(ws + L.h1) + (size_t)slot * m->cfg.hidden;
     a.H = m->cfg.hidden;
     return a;
 }
@@ -148,6 +158,8 @@ lcc_model* lcc_model_create(lcc_ctx* ctx, const lcc_model_config* cfg, const lcc
     m->layers.assign(w->layers, w->layers + cfg->layers);
     m->w.vit_blocks = m->vit_blocks.data();
     m->w.layers = m->layers.data();
+    const char* mega_env = getenv("LIVECC_B200_MEGA");
+    m->use_mega = !(mega_env && mega_env[0] == '0');
     const char* fuse_env = getenv("LIVECC_B200_FUSE");
     m->fuse_attn_oproj = fuse_env && fuse_env[0] == '1';
 #ifdef LCC_ENABLE_PDL
@@ -171,6 +183,11 @@ size_t lcc_ws_offset(const lcc_model* m, int which) {
         case LCC_WS_PREFILL_HIDDEN: return L.hid;
         case LCC_WS_LOGITS: return L.logits_raw;
         case LCC_WS_DECODE_HIDDEN: return L.h1;
+        case LCC_WS_DECODE_QKV: return L.qkv1;
+        case LCC_WS_DECODE_ATTN: return L.attn1;
+        case LCC_WS_DECODE_ACT: return L.act1;
+        case LCC_WS_LOGITS_PROC: return L.logits_proc;
+        case LCC_WS_MEGA_ERROR: return L.mg_cnt + 97 * 4;
     }
     return 0;
 }
@@ -238,8 +255,9 @@ int lcc_vit_forward_frames(lcc_model* m, const uint8_t* frames, int T, int H, in
 }
 
 int lcc_prefill(lcc_model* m, const lcc_stream_state* st, const int64_t* ids, const int32_t* pos3, int S,
-                int past, const void* video_embeds, int n_video_rows, const lcc_sampling* sp, lcc_stream_t stream) {
+                int past, const void* video_embeds, int n_video_rows, const lcc_sampling* sp, int slot, lcc_stream_t stream) {
     if (!m || !st || !sp) return -1;
+    if (slot < 0 || slot >= lcc::MG_MAXB) LCC_FAIL(m->ctx, -2, "lcc_prefill: slot must be in [0,%d)", lcc::MG_MAXB);
     const lcc_model_config& c = m->cfg;
     cudaStream_t s = (cudaStream_t)stream;
     if (S <= 0) LCC_FAIL(m->ctx, -2, "lcc_prefill: S must be positive");
@@ -272,10 +290,89 @@ int lcc_prefill(lcc_model* m, const lcc_stream_state* st, const int64_t* ids, co
     }
     // final norm + lm_head on the last position only (logits_to_keep = 1, gen/utils.py:2487-2491)
     STEP(lcc::gemv_norm_logits((const bf16*)m->w.lm_head, H, hid + (size_t)(S - 1) * H, (const bf16*)m->w.final_norm_w,
-                               c.rms_eps, (float*)(ws + L.logits_raw), (float*)(ws + L.logits_proc), c.vocab, H,
+                               c.rms_eps, (float*)(ws + L.logits_raw) + (size_t)slot * c.vocab,
+                               (float*)(ws + L.logits_proc) + (size_t)slot * c.vocab, c.vocab, H,
                                nullptr, m->ctx->num_sms, false, s), "lm_head");
-    STEP(lcc::sample_greedy(make_sample(m, st, sp, ws, L, 0), s), "token selection");
+    STEP(lcc::sample_greedy(make_sample(m, st, sp, ws, L, 0, slot), s), "token selection");
     LCC_CHECK_LAUNCH(m->ctx, "lcc_prefill");
+    return 0;
+}
+
+// ---- persistent decode-step kernel (decode_mega.cu) --------------------------------------------------------------
+static int mega_step_params(lcc_model* m, const lcc_stream_state* sts, int B, const WsLayout& L, lcc::MegaParams* out) {
+    const lcc_model_config& c = m->cfg;
+    uint8_t* ws = m->ws;
+    lcc::MegaParams p{};
+    p.wmaps = reinterpret_cast<const CUtensorMap*>(ws + L.mg_tmaps);
+    p.layers = reinterpret_cast<const lcc::MegaLayer*>(ws + L.mg_layers);
+    p.final_norm_w = (const bf16*)m->w.final_norm_w;
+    p.inv_freq = m->w.text_inv_freq;
+    p.L = c.layers; p.H = c.hidden; p.I = c.inter; p.Hq = c.q_heads; p.Hkv = c.kv_heads; p.V = c.vocab;
+    p.qkv_dim = (c.q_heads + 2 * c.kv_heads) * 128;
+    p.eps = c.rms_eps;
+    p.B = B;
+    for (int b = 0; b < B; ++b) {
+        if (sts[b].k_pool != sts[0].k_pool || sts[b].v_pool != sts[0].v_pool || sts[b].layer_stride != sts[0].layer_stride)
+            return -1;  // all streams of a batch live in one page pool
+        p.st[b].page_table = sts[b].page_table;
+        p.st[b].scalars = sts[b].scalars;
+    }
+    p.k_pool = (bf16*)sts[0].k_pool; p.v_pool = (bf16*)sts[0].v_pool;
+    p.layer_stride = sts[0].layer_stride;
+    p.kv_rows_per_layer = (int)(sts[0].layer_stride / 128);
+    p.h = (bf16*)(ws + L.h1); p.qkv = (bf16*)(ws + L.qkv1); p.attn = (bf16*)(ws + L.attn1); p.act = (bf16*)(ws + L.act1);
+    p.logits_raw = (float*)(ws + L.logits_raw); p.logits_proc = (float*)(ws + L.logits_proc);
+    p.part_o = (float*)(ws + L.mg_part_o); p.part_ml = (float*)(ws + L.mg_part_ml);
+    int* cnt = (int*)(ws + L.mg_cnt);
+    p.pair_cnt = cnt; p.bar = (unsigned*)(cnt + 96); p.err = cnt + 97;
+    p.layer_begin = 0; p.layer_end = c.layers; p.phase_mask = 31; p.do_head = 1;
+    p.scale_log2 = 1.4426950408889634f / sqrtf(128.f);
+    *out = p;
+    return 0;
+}
+
+static int mega_launch(lcc_model* m, const lcc::MegaParams& p, cudaStream_t s) {
+    if (cudaMemsetAsync(p.bar, 0, sizeof(unsigned), s) != cudaSuccess) return -20;  // grid barrier counter starts at 0
+    const long long pool_rows = (long long)p.kv_rows_per_layer * p.L;
+    return lcc::decode_mega_launch(p, p.k_pool, p.v_pool, pool_rows, m->ctx->num_sms, s);
+}
+
+int lcc_decode_batch(lcc_model* m, const lcc_stream_state* states, int n_streams, int n_steps, const lcc_sampling* sp,
+                     lcc_stream_t stream) {
+    if (!m || !states || !sp) return -1;
+    if (n_streams < 1 || n_streams > lcc::MG_MAXB) LCC_FAIL(m->ctx, -2, "lcc_decode_batch: 1..%d streams per launch", lcc::MG_MAXB);
+    if (!m->mega_ok) LCC_FAIL(m->ctx, -4, "lcc_decode_batch: model geometry is not supported by the persistent decode kernel");
+    WsLayout L;
+    if (get_layout(m, 0, 0, &L)) LCC_FAIL(m->ctx, -3, "lcc_decode_batch: no workspace bound");
+    cudaStream_t s = (cudaStream_t)stream;
+    lcc::MegaParams p;
+    if (mega_step_params(m, states, n_streams, L, &p)) LCC_FAIL(m->ctx, -5, "lcc_decode_batch: streams must share one page pool");
+    lcc::SampleBatch sb{};
+    sb.B = n_streams;
+    for (int b = 0; b < n_streams; ++b) { sb.seq[b] = states[b].seq; sb.scalars[b] = states[b].scalars; }
+    sb.err = p.err;
+    const lcc::SampleArgs base = make_sample(m, nullptr, sp, m->ws, L, 1);
+    for (int step = 0; step < n_steps; ++step) {
+        STEP(mega_launch(m, p, s), "persistent decode step");
+        STEP(lcc::sample_greedy_batch(base, sb, s), "batched token selection");
+    }
+    LCC_CHECK_LAUNCH(m->ctx, "lcc_decode_batch");
+    return 0;
+}
+
+int lcc_decode_mega_debug(lcc_model* m, const lcc_stream_state* states, int n_streams, int layer_begin, int layer_end,
+                          int phase_mask, int do_head, lcc_stream_t stream) {
+    if (!m || !states) return -1;
+    if (!m->mega_ok) LCC_FAIL(m->ctx, -4, "lcc_decode_mega_debug: geometry not supported");
+    WsLayout L;
+    if (get_layout(m, 0, 0, &L)) LCC_FAIL(m->ctx, -3, "lcc_decode_mega_debug: no workspace bound");
+    lcc::MegaParams p;
+    if (n_streams < 1 || n_streams > lcc::MG_MAXB || mega_step_params(m, states, n_streams, L, &p))
+        LCC_FAIL(m->ctx, -5, "lcc_decode_mega_debug: bad streams");
+    if (layer_begin < 0 || layer_end > m->cfg.layers || layer_begin > layer_end) LCC_FAIL(m->ctx, -6, "bad layer range");
+    p.layer_begin = layer_begin; p.layer_end = layer_end; p.phase_mask = phase_mask; p.do_head = do_head;
+    STEP(mega_launch(m, p, (cudaStream_t)stream), "persistent decode step (sub-range)");
+    LCC_CHECK_LAUNCH(m->ctx, "lcc_decode_mega_debug");
     return 0;
 }
 
@@ -285,6 +382,7 @@ int lcc_decode_steps(lcc_model* m, const lcc_stream_state* st, int n_steps, int 
     const lcc_model_config& c = m->cfg;
     cudaStream_t s = (cudaStream_t)stream;
     if (nsplit < 1 || nsplit > kMaxSplit) LCC_FAIL(m->ctx, -2, "lcc_decode_steps: nsplit must be in [1,%d]", kMaxSplit);
+    if (m->use_mega && m->mega_ok) return lcc_decode_batch(m, st, 1, n_steps, sp, stream);  // persistent kernel, 1 stream
     WsLayout L;
     if (get_layout(m, 0, 0, &L)) LCC_FAIL(m->ctx, -3, "lcc_decode_steps: no workspace bound");
     uint8_t* ws = m->ws;
@@ -357,5 +455,30 @@ extern "C" int lcc_model_bind_workspace(lcc_model* m, void* ws, size_t ws_bytes,
         LCC_FAIL(m->ctx, -3, "lcc_model_bind_workspace: cudaMemset failed");
     m->cap_patches = max_patches;
     m->cap_tokens = max_tokens;
+    // tables of the persistent decode kernel: one TMA descriptor per weight matrix (box = 32 rows x 64 k, SWIZZLE_128B)
+    // and the per-layer vector pointers; uploaded synchronously (bind happens outside the hot loop)
+    const lcc_model_config& c = m->cfg;
+    const WsLayout L = make_layout(c, max_patches, max_tokens);
+    const int qkv_dim = (c.q_heads + 2 * c.kv_heads) * 128;
+    m->mega_ok = false;
+    if (!(qkv_dim % 32) && !(c.hidden % 64) && !(c.inter % 64) && !(c.vocab % 32) && c.q_heads / c.kv_heads <= 8) {
+        std::vector<CUtensorMap> maps(4 * c.layers + 1);
+        std::vector<lcc::MegaLayer> lays(c.layers);
+        bool ok = true;
+        for (int i = 0; i < c.layers && ok; ++i) {
+            const lcc_layer_weights& lw = m->layers[i];
+            ok = !lcc::mega_make_weight_tmap(&maps[4 * i + 0], lw.qkv_w, qkv_dim, c.hidden) &&
+                 !lcc::mega_make_weight_tmap(&maps[4 * i + 1], lw.o_w, c.hidden, c.q_heads * 128) &&
+                 !lcc::mega_make_weight_tmap(&maps[4 * i + 2], lw.gate_up_w, 2 * c.inter, c.hidden) &&
+                 !lcc::mega_make_weight_tmap(&maps[4 * i + 3], lw.down_w, c.hidden, c.inter);
+            lays[i] = lcc::MegaLayer{(const bf16*)lw.ln1_w, (const bf16*)lw.qkv_b, (const bf16*)lw.ln2_w};
+        }
+        ok = ok && !lcc::mega_make_weight_tmap(&maps[4 * c.layers], m->w.lm_head, c.vocab, c.hidden);
+        if (ok &&
+            cudaMemcpy(m->ws + L.mg_tmaps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice) == cudaSuccess &&
+            cudaMemcpy(m->ws + L.mg_layers, lays.data(), lays.size() * sizeof(lcc::MegaLayer), cudaMemcpyHostToDevice) == cudaSuccess &&
+            cudaMemset(m->ws + L.mg_cnt, 0, 128 * 4) == cudaSuccess)
+            m->mega_ok = true;
+    }
     return 0;
 }

@@ -83,5 +83,13 @@ struct SampleArgs {
     int H;
 };
 int sample_greedy(const SampleArgs& a, cudaStream_t s);
+struct SampleBatch {
+    int B;
+    int64_t* seq[8];
+    int* scalars[8];
+    const int* err;  // optional: sticky error flag of the decode kernel, copied into scalars[LCC_SC_NATIVE_ERROR]
+};
+// `base` carries the shared arguments; logits_raw / logits_proc / h are [B][V] / [B][V] / [B][H] row arrays.
+int sample_greedy_batch(const SampleArgs& base, const SampleBatch& sb, cudaStream_t s);
 
 }  // namespace lcc

@@ -13,7 +13,7 @@
 
 namespace lcc {
 
-__global__ void __launch_bounds__(1024) sample_greedy_kernel(const SampleArgs a) {
+__device__ __forceinline__ void sample_greedy_body(const SampleArgs& a) {
     int* sc = a.scalars;
     if (sc[LCC_SC_FINISHED]) return;
     __shared__ float red_v[32];
@@ -130,9 +130,36 @@ __global__ void __launch_bounds__(1024) sample_greedy_kernel(const SampleArgs a)
         *reinterpret_cast<uint4*>(a.h + c) = *reinterpret_cast<const uint4*>(src + c);
 }
 
+__global__ void __launch_bounds__(1024) sample_greedy_kernel(const SampleArgs a) { sample_greedy_body(a); }
+
+// One CTA per stream of a batched decode step: stream b uses row b of the logits / hidden buffers and its own id
+// buffer and scalars. Also publishes the decode kernel's sticky error flag in scalars[LCC_SC_NATIVE_ERROR].
+__global__ void __launch_bounds__(1024) sample_greedy_batch_kernel(const SampleArgs base, const SampleBatch sb) {
+    const int b = blockIdx.x;
+    SampleArgs a = base;
+    a.logits_raw = base.logits_raw + (size_t)b * base.V;
+    a.logits_proc = base.logits_proc + (size_t)b * base.V;
+    a.h = base.h + (size_t)b * base.H;
+    a.seq = sb.seq[b];
+    a.scalars = sb.scalars[b];
+    if (sb.err && threadIdx.x == 0) {
+        const int e = *sb.err;
+        if (e) a.scalars[LCC_SC_NATIVE_ERROR] = e;
+    }
+    sample_greedy_body(a);
+}
+
 int sample_greedy(const SampleArgs& a, cudaStream_t s) {
     if (a.V <= 0 || a.H % 8) return -1;
-    { lcc::count_launch(); sample_greedy_kernel<<<1, 1024, 0, s>>>(a); }
+    lcc::count_launch();
+    sample_greedy_kernel<<<1, 1024, 0, s>>>(a);
+    return 0;
+}
+
+int sample_greedy_batch(const SampleArgs& base, const SampleBatch& sb, cudaStream_t s) {
+    if (base.V <= 0 || base.H % 8 || sb.B < 1 || sb.B > 8) return -1;
+    lcc::count_launch();
+    sample_greedy_batch_kernel<<<sb.B, 1024, 0, s>>>(base, sb);
     return 0;
 }
 

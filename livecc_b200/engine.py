@@ -257,16 +257,120 @@ class LiveCCB200ForConditionalGeneration:
         the Qwen2-VL generation defaults, top_k = 1, which is greedy)."""
         if unsupported:
             raise TypeError(f"generate() got unsupported arguments {sorted(unsupported)}")
+        self._check_common(pixel_values, image_grid_thw, do_sample, max_new_tokens)
+        sp = self._sampling(repetition_penalty, logits_processor, max_new_tokens)
+        self._ev[0].record()
+        rec = self._begin_stream(input_ids, pixel_values_videos, video_grid_thw, past_key_values, video_frames, sp,
+                                 max_new_tokens, slot=0, timed=True)
+        cache, st, L = rec["cache"], rec["st"], rec["L"]
+        logits_out = [self._raw_logits().clone()] if output_logits else None
+        if _forced_ids is not None:
+            self._force_token(cache, L, 0, _forced_ids, max_new_tokens)
+
+        self._ev[2].record()
+        # ---- decode steps ----
+        nsplit = self._pick_nsplit(rec["past"] + rec["S"] + max_new_tokens)
+        n_steps = max_new_tokens - 1
+        logits_hist = None
+        if _forced_ids is not None:
+            # teacher forcing (parity tests): eager per-step launches, the host swaps the token between steps
+            for i in range(n_steps):
+                self._native.decode_steps(st, 1, nsplit, sp)
+                if output_logits:
+                    logits_out.append(self._raw_logits().clone())
+                if i + 1 < len(_forced_ids):
+                    self._force_token(cache, L, i + 1, _forced_ids, max_new_tokens)
+        elif n_steps > 0:
+            if output_logits:
+                # production (CUDA-graph replay) path with the logits of every step copied out inside the replay loop:
+                # the path whose logits the parity tests read is the path the benchmark times
+                logits_hist = torch.empty((n_steps, self.config.text_config.vocab_size), dtype=torch.float32,
+                                          device=self.device)
+            self._run_decode([cache], [st], sp, n_steps, nsplit, logits_hist)
+
+        self._ev[3].record()
+        # ---- one host sync per generate(): read the stream scalars ----
+        out = self._finish_stream(rec, cache.scalars.tolist(), logits_out, logits_hist, output_logits)
+        ph = [self._ev[i].elapsed_time(self._ev[i + 1]) for i in range(3)]
+        self.last_stats = {"prefill_tokens": rec["S"], "generated": rec["n_gen"], "kv_len": cache.seq_len, "vit_ms": ph[0],
+                           "prefill_ms": ph[1], "decode_ms": ph[2]}
+        tot = self.phase_ms_total
+        tot["vit"] += ph[0]; tot["prefill"] += ph[1]; tot["decode"] += ph[2]
+        tot["calls"] += 1; tot["decode_steps"] += max(rec["n_gen"] - 1, 0)
+        return out if return_dict_in_generate else out.sequences
+
+    @torch.inference_mode()
+    def generate_batch(self, requests: List[dict], repetition_penalty: float = 1.0, logits_processor=None,
+                       max_new_tokens: int = 16, do_sample: Optional[bool] = None, output_logits: bool = False,
+                       pad_token_id: Optional[int] = None) -> List[GenerateOutput]:
+        """Multi-stream batching: one generate() for up to 8 independent streams of this model
+        (the reference demo admits 5 concurrent sessions on one model object, REF/demo/app.py:178, and serves them one
+        after another). Every request is a dict with the per-stream arguments of generate() (`input_ids` [1, L],
+        `pixel_values_videos` | `video_frames`, `video_grid_thw`, `past_key_values`). The ViT and the prefill run per
+        stream; all decode steps run batched in the persistent decode kernel, which reads every weight byte once per
+        step for all streams. Each stream's ids, logits and cache are bit-identical to calling generate() on it alone
+        (tests/test_engine_gpu.py::test_batched_decode_equals_sequential)."""
+        if not 1 <= len(requests) <= _cabi.MAX_BATCH:
+            raise ValueError(f"generate_batch takes 1..{_cabi.MAX_BATCH} streams")
+        self._check_common(None, None, do_sample, max_new_tokens)
+        sp = self._sampling(repetition_penalty, logits_processor, max_new_tokens)
+        allowed = {"input_ids", "pixel_values_videos", "video_grid_thw", "past_key_values", "video_frames",
+                   "mm_token_type_ids", "attention_mask"}
+        recs = []
+        t_ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        t_ev[0].record()
+        for b, rq in enumerate(requests):
+            if set(rq) - allowed:
+                raise TypeError(f"request {b} has unsupported keys {sorted(set(rq) - allowed)}")
+            recs.append(self._begin_stream(rq.get("input_ids"), rq.get("pixel_values_videos"), rq.get("video_grid_thw"),
+                                           rq.get("past_key_values"), rq.get("video_frames"), sp, max_new_tokens, slot=b))
+        if len({id(r["cache"]) for r in recs}) != len(recs):
+            raise ValueError("the same cache object appears in two requests of one batch")
+        V = self.config.text_config.vocab_size
+        B = len(recs)
+        first_logits = self._raw_logits_all()[:B].clone() if output_logits else None
+        t_ev[1].record()
+        n_steps = max_new_tokens - 1
+        logits_hist = torch.empty((n_steps, B, V), dtype=torch.float32, device=self.device) if output_logits and n_steps else None
+        if n_steps > 0:
+            self._run_decode([r["cache"] for r in recs], [r["st"] for r in recs], sp, n_steps, 1, logits_hist)
+        t_ev[2].record()
+        scal = torch.stack([r["cache"].scalars for r in recs]).tolist()   # the one host sync of the call
+        outs = []
+        for b, r in enumerate(recs):
+            lo = [first_logits[b]] if output_logits else None
+            outs.append(self._finish_stream(r, scal[b], lo, logits_hist[:, b] if logits_hist is not None else None, output_logits))
+        tot = self.phase_ms_total
+        tot["prefill"] += t_ev[0].elapsed_time(t_ev[1]); tot["decode"] += t_ev[1].elapsed_time(t_ev[2])
+        tot["calls"] += B; tot["decode_steps"] += max(max(r["n_gen"] for r in recs) - 1, 0)
+        return outs
+
+    # ------------------------------------------------------------------------------------------
+    def _check_common(self, pixel_values, image_grid_thw, do_sample, max_new_tokens):
         if pixel_values is not None or image_grid_thw is not None:
             raise NotImplementedError("image inputs are outside the LiveCC streaming path (video only)")
-        if input_ids is None or input_ids.dim() != 2 or input_ids.shape[0] != 1:
-            raise ValueError("input_ids must be [1, L] (one stream per call)")
-        if do_sample is None:
-            do_sample = False
         if do_sample and self.generation_config.top_k != 1:
             raise NotImplementedError("do_sample=True is only supported with top_k=1 (the Qwen2-VL generation default)")
         if max_new_tokens < 1:
             raise ValueError("max_new_tokens must be >= 1")
+
+    def _pick_nsplit(self, kv_tokens: int) -> int:
+        """Split-KV factor of the per-op decode attention (unused by the persistent kernel, which plans its own items)."""
+        kv_tiles = (kv_tokens + 63) // 64
+        div = int(os.environ.get("LIVECC_B200_NSPLIT_DIV", "8"))
+        want = max(1, (kv_tiles + div - 1) // div)   # >= ~8 KV tiles (512 tokens) per split
+        nsplit = 1
+        while nsplit < want and nsplit < self.max_nsplit:  # quantised to powers of two: at most 7 captured graphs
+            nsplit *= 2
+        self.nsplit = min(nsplit, self.max_nsplit)
+        return self.nsplit
+
+    def _begin_stream(self, input_ids, pixel_values_videos, video_grid_thw, past_key_values, video_frames, sp,
+                      max_new_tokens, slot, timed=False):
+        """Everything of one stream's turn up to and including the prefill and the first token selection; the first
+        token's embedding and logits land in row `slot` of the decode-step buffers."""
+        if input_ids is None or input_ids.dim() != 2 or input_ids.shape[0] != 1:
+            raise ValueError("input_ids must be [1, L] (one stream per call)")
         cfg = self.config
         cache = past_key_values if past_key_values is not None else self.new_cache()
         if not isinstance(cache, PagedKVCache) or cache.pool is not self.pool:
@@ -294,7 +398,6 @@ class LiveCCB200ForConditionalGeneration:
             pos3_dev = base.view(1, -1).expand(3, -1).contiguous()
 
         # ---- vision tower ----
-        self._ev[0].record()
         video_embeds = None
         n_video_expected = -1
         if pixel_values_videos is not None and video_frames is not None:
@@ -307,11 +410,8 @@ class LiveCCB200ForConditionalGeneration:
         elif video_frames is not None:
             video_embeds = self.get_video_features_from_frames(video_frames)
             n_video_expected = video_embeds.shape[0]
-            if video_grid_thw is None:
-                T, _, H, W = video_frames.shape
-                video_grid_thw = torch.tensor([[(T + 1) // 2, H // 14, W // 14]])
-
-        self._ev[1].record()
+        if timed:
+            self._ev[1].record()
         # ---- capacity, buffers, device scalars ----
         self._ensure_workspace(0, S)
         cache.ensure_tokens(past + S + max_new_tokens)
@@ -319,51 +419,22 @@ class LiveCCB200ForConditionalGeneration:
         cache.seq_buf[:L].copy_(ids_dev[0])
         sc_host = torch.tensor([past + S, past + S + cache.rope_delta, 0, 0, L, 0, 0, 0], dtype=torch.int32)
         cache.scalars.copy_(sc_host, non_blocking=False)
-        sp = self._sampling(repetition_penalty, logits_processor, max_new_tokens)
         st = cache.stream_state()
         new_ids = cache.seq_buf[past:L]
-
         # ---- prefill + first token ----
-        self._native.prefill(st, new_ids, pos3_dev, S, past, video_embeds, sp)
-        logits_out = [self._raw_logits().clone()] if output_logits else None
-        if _forced_ids is not None:
-            self._force_token(cache, L, 0, _forced_ids, max_new_tokens)
+        self._native.prefill(st, new_ids, pos3_dev, S, past, video_embeds, sp, slot=slot)
+        return dict(cache=cache, st=st, L=L, S=S, past=past, n_video_expected=n_video_expected, n_gen=0)
 
-        self._ev[2].record()
-        # ---- decode steps ----
-        kv_tiles = (past + S + max_new_tokens + 63) // 64
-        div = int(os.environ.get("LIVECC_B200_NSPLIT_DIV", "8"))
-        want = max(1, (kv_tiles + div - 1) // div)   # >= ~8 KV tiles (512 tokens) per split
-        nsplit = 1
-        while nsplit < want and nsplit < self.max_nsplit:  # quantised to powers of two: at most 7 captured graphs
-            nsplit *= 2
-        nsplit = min(nsplit, self.max_nsplit)
-        self.nsplit = nsplit
-        n_steps = max_new_tokens - 1
-        logits_hist = None
-        if _forced_ids is not None:
-            # teacher forcing (parity tests): eager per-step launches, the host swaps the token between steps
-            for i in range(n_steps):
-                self._native.decode_steps(st, 1, nsplit, sp)
-                if output_logits:
-                    logits_out.append(self._raw_logits().clone())
-                if i + 1 < len(_forced_ids):
-                    self._force_token(cache, L, i + 1, _forced_ids, max_new_tokens)
-        elif n_steps > 0:
-            if output_logits:
-                # production (CUDA-graph replay) path with the logits of every step copied out inside the replay loop:
-                # the path whose logits the parity tests read is the path the benchmark times
-                logits_hist = torch.empty((n_steps, self.config.text_config.vocab_size), dtype=torch.float32,
-                                          device=self.device)
-            self._run_decode(cache, st, sp, n_steps, nsplit, logits_hist)
-
-        self._ev[3].record()
-        # ---- one host sync per generate(): read the stream scalars ----
-        sc = cache.scalars.tolist()
+    def _finish_stream(self, rec, sc, logits_out, logits_hist, output_logits) -> GenerateOutput:
+        cache, L, past = rec["cache"], rec["L"], rec["past"]
+        if sc[_cabi.SC_NATIVE_ERROR]:
+            raise _cabi.LiveCCNativeError(f"persistent decode kernel gave up on a bounded wait (code "
+                                          f"{sc[_cabi.SC_NATIVE_ERROR]}); the results of this call are invalid")
         n_gen = sc[_cabi.SC_N_GENERATED]
-        if n_video_expected >= 0:
+        rec["n_gen"] = n_gen
+        if rec["n_video_expected"] >= 0:
             n_video_ids = sc[_cabi.SC_VIDEO_TOKENS]
-            if n_video_ids != n_video_expected:
+            if n_video_ids != rec["n_video_expected"]:
                 # the reference validates before the forward (mq2vl.py:1169-1175); here the count comes back with the
                 # step's scalars, so the stream state is rolled back to what it was before this call: the cache still
                 # reports `past` tokens (the pages written behind it are dead) and a first turn forgets its rope_delta
@@ -371,37 +442,43 @@ class LiveCCB200ForConditionalGeneration:
                 if past == 0:
                     cache.rope_delta = None
                 raise ValueError(f"Video features and video tokens do not match, tokens: {n_video_ids}, "
-                                 f"features: {n_video_expected}")
+                                 f"features: {rec['n_video_expected']}")
         cache.seq_len = sc[_cabi.SC_KV_LEN]
         sequences = cache.seq_buf[: L + n_gen].clone().view(1, -1)
-        ph = [self._ev[i].elapsed_time(self._ev[i + 1]) for i in range(3)]
-        self.last_stats = {"prefill_tokens": S, "generated": n_gen, "kv_len": cache.seq_len, "vit_ms": ph[0],
-                           "prefill_ms": ph[1], "decode_ms": ph[2]}
-        tot = self.phase_ms_total
-        tot["vit"] += ph[0]; tot["prefill"] += ph[1]; tot["decode"] += ph[2]
-        tot["calls"] += 1; tot["decode_steps"] += max(n_gen - 1, 0)
         if output_logits and logits_out is not None:
             if logits_hist is not None:
                 logits_out += list(logits_hist[: max(n_gen - 1, 0)])
             logits_out = logits_out[:n_gen]
-        out = GenerateOutput(sequences=sequences, past_key_values=cache, logits=logits_out)
-        return out if return_dict_in_generate else sequences
+        return GenerateOutput(sequences=sequences, past_key_values=cache, logits=logits_out if output_logits else None)
 
     # ------------------------------------------------------------------------------------------
-    def _run_decode(self, cache: PagedKVCache, st, sp: _cabi.Sampling, n_steps: int, nsplit: int, logits_hist=None):
+    def _run_decode(self, caches, sts, sp: _cabi.Sampling, n_steps: int, nsplit: int, logits_hist=None):
+        """n_steps decode steps for one stream (caches = [cache]) or a batch (<= 8 caches, persistent kernel)."""
+        B = len(caches)
+
+        def launch(n):
+            if B == 1:
+                self._native.decode_steps(sts[0], n, nsplit, sp)
+            else:
+                self._native.decode_batch(sts, n, sp)
+
+        def copy_logits(i):
+            if logits_hist is not None:  # a finished stream replays no-ops and leaves its last logits in place
+                logits_hist[i].copy_(self._raw_logits() if B == 1 else self._raw_logits_all()[:B])
+
         if not self.use_cuda_graph:
             if logits_hist is None:
-                self._native.decode_steps(st, n_steps, nsplit, sp)
+                launch(n_steps)
             else:
                 for i in range(n_steps):
-                    self._native.decode_steps(st, 1, nsplit, sp)
-                    logits_hist[i].copy_(self._raw_logits())
+                    launch(1)
+                    copy_logits(i)
             return
-        key = (cache.graph_key(), self._native.workspace.data_ptr(), nsplit, sp.repetition_penalty, sp.thr_token,
-               sp.thr_base, sp.thr_step, sp.eos_token_id, sp.eos_token_id2, sp.max_new_tokens)
+        key = (tuple(c.graph_key() for c in caches), self._native.workspace.data_ptr(), nsplit, sp.repetition_penalty,
+               sp.thr_token, sp.thr_base, sp.thr_step, sp.eos_token_id, sp.eos_token_id2, sp.max_new_tokens)
         g = self._graphs.get(key)
         if g is None:
-            # capture ONE decode step (28 layers + lm_head + token selection); replay it n_steps times.
+            # capture ONE decode step (every layer + lm_head + token selection); replay it n_steps times.
             # All step-varying state (kv_len, position, token, finished flag) lives in device memory.
             if len(self._graphs) > 32:
                 self._graphs.clear()
@@ -411,7 +488,7 @@ class LiveCCB200ForConditionalGeneration:
             n0 = _cabi.launch_count()
             with torch.cuda.stream(side):
                 with torch.cuda.graph(g, stream=side, capture_error_mode="thread_local"):
-                    self._native.decode_steps(st, 1, nsplit, sp)
+                    launch(1)
             torch.cuda.current_stream(self.device).wait_stream(side)
             g.lcc_nodes = _cabi.launch_count() - n0
             self._captured_launches += g.lcc_nodes
@@ -419,8 +496,7 @@ class LiveCCB200ForConditionalGeneration:
         for i in range(n_steps):
             g.replay()
             self._replayed_launches += g.lcc_nodes
-            if logits_hist is not None:  # a finished stream replays no-ops and leaves the last logits in place
-                logits_hist[i].copy_(self._raw_logits())
+            copy_logits(i)
 
     def kernel_launches(self) -> int:
         """Kernels of liblivecc_sm100a.so executed so far in this process (counted at the launch sites; launches
@@ -431,6 +507,12 @@ class LiveCCB200ForConditionalGeneration:
         off = self._native.logits_offset
         V = self.config.text_config.vocab_size
         return self._native.workspace[off:off + 4 * V].view(torch.float32)
+
+    def _raw_logits_all(self) -> torch.Tensor:
+        """[8, V] raw logits of the decode-step slots (row b = stream b of a batched step)."""
+        off = self._native.logits_offset
+        V = self.config.text_config.vocab_size
+        return self._native.workspace[off:off + 4 * V * _cabi.MAX_BATCH].view(torch.float32).view(_cabi.MAX_BATCH, V)
 
     def _force_token(self, cache: PagedKVCache, L: int, step: int, forced: List[int], max_new_tokens: int):
         """Teacher forcing (parity tests): replace the token just selected by the oracle's token."""

@@ -336,3 +336,39 @@ def test_op_wrappers_pass_as_many_arguments_as_the_header_declares():
     assert len(calls) == 6
     for name, nargs in calls:
         assert nargs + 1 == declared(name), (name, nargs + 1, declared(name))  # + the ctx argument added by call()
+
+
+def test_model_wrappers_pass_as_many_arguments_as_the_header_declares(monkeypatch):
+    """Same check for the model-level entry points (prefill slot, batched decode, sub-range hook) and embed_gather."""
+    import ctypes as C
+    import re
+    from pathlib import Path
+
+    import torch
+
+    from livecc_b200 import _cabi
+
+    header = (Path(__file__).resolve().parents[1] / "include" / "livecc_b200.h").read_text()
+
+    def declared(fn):
+        return len(re.search(r"\b" + fn + r"\((.*?)\);", header, re.S).group(1).split(","))
+
+    monkeypatch.setattr(_cabi.Context, "stream_ptr", staticmethod(lambda: C.c_void_p(0)))
+    calls = []
+    nm = object.__new__(_cabi.NativeModel)
+    nm._call = lambda name, *args: calls.append((name, len(args)))
+    st, sp = _cabi.StreamState(), _cabi.Sampling()
+    ids, pos3 = torch.zeros(3, dtype=torch.int64), torch.zeros((3, 3), dtype=torch.int32)
+    feats = torch.zeros((2, 8), dtype=torch.bfloat16)
+    nm.prefill(st, ids, pos3, 3, 0, feats, sp, slot=2)
+    nm.decode_steps(st, 1, 1, sp)
+    nm.decode_batch([st, st], 1, sp)
+    nm.decode_mega_debug([st], 0, 1, 31, 1)
+    nm.vit_forward(torch.zeros((4, 1176)), 1, 2, 2, feats)
+    nm.vit_forward_frames(torch.zeros((2, 3, 28, 28), dtype=torch.uint8), [0.0] * 3, [1.0] * 3, feats)
+    ctx = object.__new__(_cabi.Context)
+    ctx.call = lambda name, *args: calls.append((name, len(args)))
+    ctx.embed_gather(ids, torch.zeros((10, 8), dtype=torch.bfloat16), feats, 9)
+    assert len(calls) == 7
+    for name, nargs in calls:
+        assert nargs + 1 == declared(name), (name, nargs + 1, declared(name))  # + the model / ctx handle
