@@ -234,7 +234,8 @@ def time_dominant_kernel(eng, chunks_dev, max_new, iters=20):
 
     t = eng.config.text_config
     _, _, _, kv, cache = run_stream_device(eng, chunks_dev, max_new, keep_cache=True)
-    cache.scalars[_cabi.SC_FINISHED] = 0
+    with torch.inference_mode():
+        cache.scalars[_cabi.SC_FINISHED] = 0
     st = [cache.stream_state()]
     L = t.num_hidden_layers
     stream = torch.cuda.current_stream()

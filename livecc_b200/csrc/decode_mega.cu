@@ -330,10 +330,10 @@ __device__ void consumer_gemv(const MegaParams& p, Cons& c, const Shared& sh, in
             const uint32_t tb = wait_tile(c, tbase + kc);
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
-                if (!XG) {
+                if (!XG) {  // xs holds bpad rows only: columns >= B of the MMA are zero and never read back
                     const bf16* xp = sh.xs + (size_t)g * xpitch + kc * 64 + kk * 16 + 2 * t;
-                    bx[kk][0] = *reinterpret_cast<const uint32_t*>(xp);
-                    bx[kk][1] = *reinterpret_cast<const uint32_t*>(xp + 8);
+                    bx[kk][0] = g < p.B ? *reinterpret_cast<const uint32_t*>(xp) : 0u;
+                    bx[kk][1] = g < p.B ? *reinterpret_cast<const uint32_t*>(xp + 8) : 0u;
                 }
                 const int r = (c.lane & 7) + ((c.lane >> 3) & 1) * 8;
                 const int ch = 2 * kk + (c.lane >> 4);

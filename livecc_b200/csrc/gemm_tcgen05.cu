@@ -408,16 +408,20 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits,
     *reinterpret_cast<uint4*>(C + (size_t)row * ldc + col) = o;
 }
 
-// Split-K for small-M GEMMs whose tile count cannot occupy the SMs (prefill o_proj / down_proj / qkv at M ~ 281).
+// Split-K for small-M GEMMs whose tile count cannot occupy the SMs (prefill down_proj at M ~ 281: 84 tiles on 148 SMs).
 // Returns 1 if it handled the GEMM, 0 if the caller should run the plain path, < 0 on error.
-// UNVALIDATED ON HARDWARE (written at the end of round 1 without GPU time): opt-in through LIVECC_B200_GEMM_SPLITK=1.
+// Validated on B200 in round 2 (bit-exact on integer operands, test_gemm_splitk_exact_integer_operands; whole-model parity
+// with it forced on). Measured (profiles/r02_gemm_shapes.md): it pays only for long K — down_proj (K = 18944) 86.7 -> 60.9 us,
+// while qkv / o_proj (K = 3584) get slower (23 -> 34 us) — so the default applies it for K >= 8192 only.
+// LIVECC_B200_GEMM_SPLITK=1 forces it for every eligible shape, =0 disables it.
 static int try_splitk(const GemmArgs& a, int num_sms, cudaStream_t stream) {
-    static int enabled = -1;
-    if (enabled < 0) {
+    static int mode = -1;  // 0 off, 1 forced, 2 default (long K only)
+    if (mode < 0) {
         const char* e = getenv("LIVECC_B200_GEMM_SPLITK");
-        enabled = (e && e[0] == '1') ? 1 : 0;
+        mode = !e ? 2 : (e[0] == '1' ? 1 : (e[0] == '0' ? 0 : 2));
     }
-    if (!enabled || !a.splitk_ws || a.M > 384) return 0;
+    if (!mode || !a.splitk_ws || a.M > 384) return 0;
+    if (mode == 2 && a.K < 8192) return 0;
     if (a.epi != EPI_NONE && a.epi != EPI_BIAS && a.epi != EPI_RESIDUAL && a.epi != EPI_BIAS_RESIDUAL) return 0;
     const int block_n = a.N >= 256 ? 256 : (a.N >= 128 ? 128 : 64);
     const int m_tiles = (a.M + BLOCK_M - 1) / BLOCK_M, n_tiles = (a.N + block_n - 1) / block_n;

@@ -356,3 +356,37 @@ def test_failed_generate_leaves_the_stream_intact(small):
                      pixel_values_videos=t0.pixel_values_videos, video_grid_thw=t0.video_grid_thw, past_key_values=fresh,
                      max_new_tokens=2)
     assert fresh.get_seq_length() == 0 and fresh.rope_delta is None
+
+
+def test_from_pretrained_round_trip(small, tmp_path):
+    """REF/demo/infer.py:43-47 `from_pretrained(model_path, torch_dtype="auto", device_map=..., attn_implementation=...)`:
+    the synthetic checkpoint written as an HF safetensors directory (pre-5.x names, flat config.json,
+    generation_config.json with the family's two EOS ids) loads into an engine that generates exactly what the
+    from_state_dict engine generates; the second EOS id stops generation like gen/utils.py does."""
+    import sys
+
+    from livecc_b200.engine import LiveCCB200ForConditionalGeneration
+
+    sys.path.insert(0, __import__("os").path.dirname(__file__))
+    from test_checkpoint_cpu import write_dir
+
+    cfg, sd, eng, rs = small
+    d = str(tmp_path / "livecc-small")
+    write_dir(d, cfg, {k: v.cpu() for k, v in sd.items()}, old=True, nested=False, shards=3,
+              gen=dict(do_sample=True, top_k=1, top_p=0.001, temperature=0.01, eos_token_id=[cfg.eos_token_id, cfg.bos_token_id]))
+    m = LiveCCB200ForConditionalGeneration.from_pretrained(d, torch_dtype="auto", device_map="cuda",
+                                                          attn_implementation="flash_attention_2")
+    assert m.config.text_config == cfg.text_config and m.generation_config.eos_token_id == [cfg.eos_token_id, cfg.bos_token_id]
+    inp = make_turn_inputs(StubProcessor(cfg), 0, 2, (112, 112), 5).to(DEV)
+    a = eng.generate(**inp, repetition_penalty=1.05, max_new_tokens=6, do_sample=False, output_logits=True)
+    b = m.generate(**inp, repetition_penalty=1.05, max_new_tokens=6, do_sample=True, output_logits=True)  # top_k = 1: greedy
+    assert torch.equal(a.sequences, b.sequences)
+    assert all(torch.equal(x, y) for x, y in zip(a.logits, b.logits))
+    # second EOS: declare the 3rd generated token to be the family's second stop id -> generation ends there
+    gen = a.sequences[0, inp.input_ids.shape[1]:].tolist()
+    m.generation_config.eos_token_id = [cfg.eos_token_id, gen[2]]
+    c = m.generate(**inp, repetition_penalty=1.05, max_new_tokens=6)
+    assert c.sequences[0, inp.input_ids.shape[1]:].tolist() == gen[:3]
+    assert c.past_key_values.get_seq_length() == inp.input_ids.shape[1] + 2
+    with pytest.raises(NotImplementedError):
+        LiveCCB200ForConditionalGeneration.from_pretrained(d, torch_dtype=torch.float32)

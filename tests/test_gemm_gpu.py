@@ -103,12 +103,12 @@ def test_gemm_strided_views(ctx):
     assert big_c[:, :64].abs().sum().item() == 0 and big_c[:, 64 + N:].abs().sum().item() == 0
 
 
-@pytest.mark.skipif(__import__("os").environ.get("LIVECC_B200_GEMM_SPLITK") != "1",
-                    reason="experimental split-K path: run with LIVECC_B200_GEMM_SPLITK=1 (not yet validated on hardware)")
 @pytest.mark.parametrize("M,N,K", [(281, 3584, 18944), (281, 3584, 3584), (281, 4608, 3584), (64, 256, 2048), (384, 136, 4096)])
 def test_gemm_splitk_exact_integer_operands(ctx, M, N, K):
     """split-K (fp32 partial tiles + reduce kernel with the fused epilogue): integer operands keep every partial sum
-    exact, so the result must be bit-identical to the unsplit reference for all four supported epilogues."""
+    exact, so the result must be bit-identical to the unsplit reference for all four supported epilogues. By default
+    the dispatch splits only K >= 8192 (the first shape); LIVECC_B200_GEMM_SPLITK=1 forces it for all of them (both
+    modes were run on B200 in round 2, profiles/r02_parity_7b.md)."""
     a = _ints((M, K), -2, 2, 11)
     b = _ints((N, K), -1, 1, 12)
     bias = _ints((N,), -8, 8, 13)

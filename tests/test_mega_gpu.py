@@ -99,13 +99,15 @@ def _prefilled_streams(eng, cfg, specs):
                          past_key_values=caches[b]))
     outs = eng.generate_batch(reqs, repetition_penalty=1.05, max_new_tokens=1)   # prefill only, slot = b
     caches = [o.past_key_values for o in outs]
-    for c in caches:
-        c.scalars[A.SC_FINISHED] = 0   # max_new_tokens = 1 finished the call; re-open the stream for the hook below
+    with torch.inference_mode():
+        for c in caches:
+            c.scalars[A.SC_FINISHED] = 0   # max_new_tokens = 1 finished the call; re-open the stream for the hook below
     torch.cuda.synchronize()
     return caches, outs
 
 
 @pytest.mark.parametrize("which", ["small", "wide"])
+@torch.inference_mode()
 def test_phases_match_the_per_op_kernels(which, request, ctx):
     cfg, sd, eng = request.getfixturevalue(which)
     t = cfg.text_config
