@@ -345,6 +345,64 @@ class LiveCCB200ForConditionalGeneration:
         tot["calls"] += B; tot["decode_steps"] += max(max(r["n_gen"] for r in recs) - 1, 0)
         return outs
 
+    @torch.inference_mode()
+    def forward_mcq(self, input_ids: torch.Tensor, attention_mask: torch.Tensor, letter_ids,
+                    pixel_values_videos: Optional[torch.Tensor] = None, video_grid_thw: Optional[torch.Tensor] = None,
+                    mm_token_type_ids=None):
+        """The single-forward multiple-choice scoring of the reference's evaluators
+        (REF/evaluation/distributed_mcq_predictor.py:72-105): a LEFT-padded batch (`padding_side='left'`,
+        REF/evaluation/videomme/distributed_evaluate_videomme.py:39-42), one forward, the logits of the last position
+        restricted to the answer-letter token ids, argmax. No decode loop: ViT + prefill only (BASELINE config #5).
+
+        input_ids / attention_mask: [B, L] (pads on the left, mask 0 there); pixel_values_videos: the processor's rows of
+        all samples concatenated; video_grid_thw: [n_videos, 3], one video per sample that contains <|video_pad|> ids,
+        in batch order. Returns (pred [B] int64 = index into letter_ids, letter_logits [B, len(letter_ids)] fp32).
+        The vision tower runs ONCE over all videos of the batch (frames attend only within themselves, so videos with
+        the same patch grid concatenate into one pass); the decoder prefill runs per sample on a fresh cache."""
+        if input_ids.dim() != 2 or attention_mask.shape != input_ids.shape:
+            raise ValueError("input_ids and attention_mask must both be [B, L]")
+        B = input_ids.shape[0]
+        letters = torch.as_tensor(list(letter_ids), dtype=torch.long, device=self.device)
+        ids_host, mask_host = input_ids.cpu(), attention_mask.cpu().bool()
+        if not bool(mask_host[:, -1].all()):
+            raise ValueError("forward_mcq expects left padding (the last column must be real tokens)")
+        grids = video_grid_thw.tolist() if video_grid_thw is not None else []
+        m2 = self.config.vision_config.spatial_merge_size ** 2
+        feats = None
+        if pixel_values_videos is not None:
+            if len({(h, w) for _, h, w in grids}) == 1:   # one ViT pass for the whole batch
+                t_all, (h, w) = sum(t for t, _, _ in grids), grids[0][1:]
+                feats = self.get_video_features(pixel_values_videos, torch.tensor([[t_all, h, w]]))
+            else:
+                feats = self.get_video_features(pixel_values_videos, video_grid_thw)
+        sp = self._sampling(1.0, None, 1)
+        out = torch.empty((B, letters.numel()), dtype=torch.float32, device=self.device)
+        caches, vid = [], 0
+        row0 = 0
+        for b in range(B):
+            ids_b = ids_host[b][mask_host[b]].view(1, -1)
+            n_vid_tok = int((ids_b == self.config.video_token_id).sum())
+            fe = g = None
+            if n_vid_tok:
+                if vid >= len(grids):
+                    raise ValueError("more samples with video placeholders than rows in video_grid_thw")
+                t, h, w = grids[vid]
+                n = t * h * w // m2
+                fe, g = feats[row0:row0 + n], torch.tensor([grids[vid]])
+                row0 += n
+                vid += 1
+            rec = self._begin_stream(ids_b, None, g, None, None, sp, 1, slot=0, video_embeds=fe)
+            out[b].copy_(self._raw_logits()[letters])
+            caches.append(rec)
+        scal = torch.stack([r["cache"].scalars for r in caches]).tolist()   # one host sync for the batch
+        try:
+            for r, sc in zip(caches, scal):
+                self._finish_stream(r, sc, None, None, False)
+        finally:
+            for r in caches:
+                r["cache"].release()
+        return out.argmax(dim=-1), out
+
     # ------------------------------------------------------------------------------------------
     def _check_common(self, pixel_values, image_grid_thw, do_sample, max_new_tokens):
         if pixel_values is not None or image_grid_thw is not None:
@@ -366,7 +424,7 @@ class LiveCCB200ForConditionalGeneration:
         return self.nsplit
 
     def _begin_stream(self, input_ids, pixel_values_videos, video_grid_thw, past_key_values, video_frames, sp,
-                      max_new_tokens, slot, timed=False):
+                      max_new_tokens, slot, timed=False, video_embeds=None):
         """Everything of one stream's turn up to and including the prefill and the first token selection; the first
         token's embedding and logits land in row `slot` of the decode-step buffers."""
         if input_ids is None or input_ids.dim() != 2 or input_ids.shape[0] != 1:
@@ -398,8 +456,7 @@ class LiveCCB200ForConditionalGeneration:
             pos3_dev = base.view(1, -1).expand(3, -1).contiguous()
 
         # ---- vision tower ----
-        video_embeds = None
-        n_video_expected = -1
+        n_video_expected = -1 if video_embeds is None else video_embeds.shape[0]
         if pixel_values_videos is not None and video_frames is not None:
             raise ValueError("pass either pixel_values_videos (HF processor rows) or video_frames (uint8 frames)")
         if pixel_values_videos is not None:

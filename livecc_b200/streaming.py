@@ -59,12 +59,19 @@ class LiveCCDemoInfer:
 
     @staticmethod
     def _load_processor(model_path, model):
-        try:
-            from transformers import AutoProcessor
+        """`AutoProcessor.from_pretrained(model_path, use_fast=False)` (REF/demo/infer.py:48). Only a checkpoint directory
+        WITHOUT any tokenizer / processor file (weights-only export; nothing can be downloaded offline) falls back to the
+        offline StubProcessor, with a warning; a present-but-broken processor raises like the reference would."""
+        import os
+        import warnings
 
-            return AutoProcessor.from_pretrained(model_path, use_fast=False)
-        except Exception:  # no tokenizer files offline
+        names = ("tokenizer_config.json", "tokenizer.json", "vocab.json", "processor_config.json", "preprocessor_config.json")
+        if model_path and os.path.isdir(model_path) and not any(os.path.exists(os.path.join(model_path, n)) for n in names):
+            warnings.warn(f"{model_path!r} has no tokenizer files: using the offline StubProcessor (synthetic token ids)")
             return StubProcessor(model.config)
+        from transformers import AutoProcessor
+
+        return AutoProcessor.from_pretrained(model_path, use_fast=False)
 
     # ------------------------------------------------------------------------------------------
     # planning steps of live_cc

@@ -390,3 +390,51 @@ def test_from_pretrained_round_trip(small, tmp_path):
     assert c.past_key_values.get_seq_length() == inp.input_ids.shape[1] + 2
     with pytest.raises(NotImplementedError):
         LiveCCB200ForConditionalGeneration.from_pretrained(d, torch_dtype=torch.float32)
+
+
+def test_forward_mcq_left_padded_batch_matches_hf(small):
+    """REF/evaluation/distributed_mcq_predictor.py:72-105: one forward over a LEFT-padded batch, last-position logits over
+    the answer-letter ids, argmax. Oracle: the HF model's own batched forward with attention_mask (bf16, sdpa)."""
+    from oracle.hf_oracle import build_hf_model
+
+    cfg, sd, eng, rs = small
+    hf = build_hf_model(cfg, sd, dtype=torch.bfloat16, device=DEV, attn_implementation="sdpa")
+    proc = StubProcessor(cfg)
+    letters = [proc.tokenizer(f": {c}").input_ids[-1] for c in "ABCD"]   # strict_letter_ids (:92)
+    samples = []
+    for i, (frames, hw, q) in enumerate([(4, (112, 112), "What is shown? A. cat B. dog C. car D. tree"),
+                                         (8, (112, 112), "Which one? A. x B. y C. z D. w and a much longer question text here"),
+                                         (2, (112, 112), "Short? A. a B. b C. c D. d"),
+                                         (4, (84, 140), "Other grid? A. 1 B. 2 C. 3 D. 4")]):
+        g = torch.Generator().manual_seed(500 + i)
+        clip = torch.randint(0, 256, (frames, 3, hw[0], hw[1]), generator=g, dtype=torch.uint8)
+        conv = [{"role": "user", "content": [{"type": "video", "video": clip},
+                                             {"type": "text", "text": q + "\nPlease select the correct answer."}]}]
+        text = proc.apply_chat_template(conv, tokenize=False, add_generation_prompt=True) + "Answer:"
+        samples.append(proc(text=text, videos=[clip], return_attention_mask=False))
+    for group in ([0, 1, 2], [0, 3, 1]):          # same-grid batch (one ViT pass) and mixed grids
+        sub = [samples[i] for i in group]
+        Lmax = max(s.input_ids.shape[1] for s in sub)
+        ids = torch.full((len(sub), Lmax), cfg.pad_token_id, dtype=torch.int64)
+        mask = torch.zeros((len(sub), Lmax), dtype=torch.int64)
+        for b, s in enumerate(sub):
+            n = s.input_ids.shape[1]
+            ids[b, Lmax - n:] = s.input_ids[0]
+            mask[b, Lmax - n:] = 1
+        px = torch.cat([s.pixel_values_videos for s in sub]).to(DEV)
+        grid = torch.cat([s.video_grid_thw for s in sub])
+        pred, ll = eng.forward_mcq(ids.to(DEV), mask.to(DEV), letters, pixel_values_videos=px, video_grid_thw=grid)
+        mm = torch.zeros_like(ids, dtype=torch.int32)
+        mm[ids == cfg.video_token_id] = 2
+        with torch.inference_mode():
+            hf.model.rope_deltas = None
+            out = hf(input_ids=ids.to(DEV), attention_mask=mask.to(DEV), pixel_values_videos=px, video_grid_thw=grid.to(DEV),
+                     mm_token_type_ids=mm.to(DEV))
+        ref = out.logits[:, -1].float()[:, letters]   # preprocess_logits_for_metrics (:72-73): last non-pad position
+        assert (ll - ref).abs().max().item() < LOGIT_ATOL, (ll, ref)
+        for b in range(len(sub)):
+            top2 = ref[b].topk(2).values
+            if float(top2[0] - top2[1]) > 2 * LOGIT_ATOL:
+                assert int(pred[b]) == int(ref[b].argmax())
+    with pytest.raises(ValueError, match="left padding"):
+        eng.forward_mcq(ids.flip(1).to(DEV), mask.flip(1).to(DEV), letters, pixel_values_videos=px, video_grid_thw=grid)
