@@ -24,6 +24,7 @@
 // decoded alone or in a batch.
 // Every wait is bounded: a lost signal sets an error flag (reported through the stream scalars) instead of hanging.
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "../../include/livecc_b200.h"
@@ -728,10 +729,16 @@ int decode_mega_launch(const MegaParams& p_in, const void* k_pool, const void* v
     if (make_tmap_bf16_2d_box(&tk, k_pool, pool_rows, 128, 128, 64, 32, false)) return -10;
     if (make_tmap_bf16_2d_box(&tv, v_pool, pool_rows, 128, 128, 64, 32, false)) return -11;
     static SmemAttrOnce once;
-    if (ensure_dyn_smem(once, decode_mega_kernel, smem)) return -12;
+    if (ensure_dyn_smem(once, decode_mega_kernel, 232448)) return -12;  // the opt-in maximum: the request varies with B
     count_launch();
     decode_mega_kernel<<<num_sms, MG_THREADS, smem, s>>>(tk, tv, p);
-    return cudaGetLastError() == cudaSuccess ? 0 : -13;
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        fprintf(stderr, "[livecc_b200] decode_mega_kernel launch failed: %s (B=%d, smem=%d, nslot=%d)\n", cudaGetErrorString(e),
+                p.B, smem, nslot);
+        return -13;
+    }
+    return 0;
 }
 
 }  // namespace lcc

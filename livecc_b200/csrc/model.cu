@@ -332,7 +332,11 @@ static int mega_step_params(lcc_model* m, const lcc_stream_state* sts, int B, co
 }
 
 static int mega_launch(lcc_model* m, const lcc::MegaParams& p, cudaStream_t s) {
-    if (cudaMemsetAsync(p.bar, 0, sizeof(unsigned), s) != cudaSuccess) return -20;  // grid barrier counter starts at 0
+    const cudaError_t me = cudaMemsetAsync(p.bar, 0, sizeof(unsigned), s);  // grid barrier counter starts at 0
+    if (me != cudaSuccess) {
+        fprintf(stderr, "[livecc_b200] cudaMemsetAsync(barrier) failed: %s\n", cudaGetErrorString(me));
+        return -20;
+    }
     const long long pool_rows = (long long)p.kv_rows_per_layer * p.L;
     return lcc::decode_mega_launch(p, p.k_pool, p.v_pool, pool_rows, m->ctx->num_sms, s);
 }

@@ -326,6 +326,8 @@ class LiveCCB200ForConditionalGeneration:
                                            rq.get("past_key_values"), rq.get("video_frames"), sp, max_new_tokens, slot=b))
         if len({id(r["cache"]) for r in recs}) != len(recs):
             raise ValueError("the same cache object appears in two requests of one batch")
+        for r in recs:   # a later stream's page allocation may have moved the pool: take the pointers after all of them
+            r["st"] = r["cache"].stream_state()
         V = self.config.text_config.vocab_size
         B = len(recs)
         first_logits = self._raw_logits_all()[:B].clone() if output_logits else None

@@ -61,9 +61,11 @@ REPORT = os.environ.get("MEGA_DEBUG_REPORT") == "1"  # print every comparison an
 _failed = []
 
 
-def _close(a, b, ulps=4.0, floor=2e-2, frac=2e-3, what=""):
+def _close(a, b, ulps=2.0, frac=1e-3, what="", **_):
+    """|a - b| <= ulps bf16 ulps of max(|b|, rms(b)): the two paths accumulate in different orders, so elements that
+    are small sums of large terms (residual adds, silu(g)*u near zero) differ by an ulp of the TERMS, not of the element."""
     a, b = a.float(), b.float()
-    tol = ulps * 2.0 ** -8 * b.abs().clamp_min(floor)
+    tol = ulps * 2.0 ** -8 * torch.maximum(b.abs(), b.pow(2).mean().sqrt())
     bad = ((a - b).abs() > tol).float().mean().item()
     if REPORT:
         nan = int(torch.isnan(a).sum())
@@ -181,11 +183,13 @@ def _decode_alone(eng, cfg, specs, max_new):
     return res
 
 
-def test_batched_decode_equals_sequential(small):
+@pytest.mark.parametrize("which,specs", [("small", [[6, 2], [2], [6, 2, 2], [6]]), ("wide", [[6, 2], [2]]),
+                                         ("wide", [[2], [6], [2, 2], [6, 2], [2], [2, 2, 2], [6], [2, 2]])])
+def test_batched_decode_equals_sequential(which, specs, request):
     """B streams with different histories decoded together (one persistent kernel per step, CUDA-graph replay) give
-    bit-identical ids, logits and KV caches to decoding each stream alone."""
-    cfg, sd, eng = small
-    specs = [[6, 2], [2], [6, 2, 2], [6]]
+    bit-identical ids, logits and KV caches to decoding each stream alone (B = 4 small config; B = 2 and B = 8 at the 7B
+    widths)."""
+    cfg, sd, eng = request.getfixturevalue(which)
     alone = _decode_alone(eng, cfg, specs, max_new=6)
     proc = StubProcessor(cfg)
     caches, pasts = [], []
