@@ -5,12 +5,13 @@
 // roofline, and it is what makes multi-stream batching a weight-read-once
 // operation.
 //
-// Structure (grid = #SMs, one CTA per SM, 288 threads):
-//   warp 8 (one lane)  : TMA producer. Walks the whole step's weight/KV tile sequence of this CTA (a pure function of
-//                        the model shape, the streams' KV lengths and the CTA index) and streams it through a shared
-//                        memory ring of 4 KB tiles (cp.async.bulk.tensor, SWIZZLE_128B, mbarrier complete_tx). It never
-//                        waits for a phase boundary: while the consumers sit in a grid barrier the next phase's weights
-//                        keep arriving, so HBM stays busy across the 5 dependent phases of a layer.
+// Structure (grid = #SMs, one CTA per SM, 384 threads):
+//   warps 8-11 (one lane each): TMA producers. Each walks the whole step's weight/KV tile sequence of this CTA (a pure
+//                        function of the model shape, the streams' KV lengths and the CTA index) and issues every 4th
+//                        tile into a shared memory ring of 4 KB tiles (cp.async.bulk.tensor, SWIZZLE_128B, mbarrier
+//                        complete_tx). They never wait for a phase boundary: while the consumers sit in a grid barrier
+//                        the next phase's weights keep arriving, so HBM stays busy across the 5 dependent phases of a
+//                        layer. (One producer thread could not issue 4 KB tiles fast enough: 2.5 TB/s.)
 //   warps 0-7          : consumers. A weight tile is 32 rows x 64 k; `mma.sync.m16n8k16` with the weights as the A
 //                        operand (ldmatrix from the swizzled tile) and the <= 8 stream activations as the 8 columns of
 //                        the B operand, fp32 accumulate. The K range of a row block is split across the 8 warps and
@@ -39,13 +40,14 @@ namespace lcc {
 namespace {
 
 constexpr int NCW = 8;                  // consumer warps
+constexpr int NPW = 4;                  // producer warps (power of two, <= ring slots)
 constexpr int NCT = NCW * 32;           // consumer threads
 constexpr int TILE = 4096;              // bytes per ring slot
 constexpr int QPITCH = 136;             // bf16 elements per staged q row
 constexpr int SCRATCH = 45056;
 // scratch carve-up (bytes)
 constexpr int SC_RED = 0;               // GEMV: float [2][8][32][8]                       (16384)
-constexpr int SC_PART = 16384;          // RMSNorm partial sums float [8] + flags int [8]  (64)
+constexpr int SC_PART = 16384;          // RMSNorm slice sums float [8 streams][8 slices]   (256)
 constexpr int SC_QS = 0;                // attention: bf16 [16][136]                       (4352)
 constexpr int SC_KNEW = 4352;           // bf16 [128]
 constexpr int SC_VNEW = 4608;           // bf16 [128]
@@ -112,7 +114,7 @@ __device__ __forceinline__ bool mbar_wait_bounded(uint64_t* bar, uint32_t parity
             : "r"(a), "r"(parity)
             : "memory");
         if (ok) return true;
-        if (it < 64) continue;
+        if ((it & 0xfff) != 0xfff) continue;   // keep the spin tight: the abort checks cost a global round trip
         if (ld_volatile_i32(err)) return false;
         if (t0 == 0) t0 = globaltimer_ns();
         else if (globaltimer_ns() - t0 > kWaitLimitNs) { atomicExch(err, code); return false; }
@@ -150,19 +152,28 @@ __device__ __forceinline__ PairPlan plan_pair(int T) {
 // ------------------------------------------------------------------------------------------------------------
 // producer
 // ------------------------------------------------------------------------------------------------------------
+// NPW producer warps (one lane each) walk the same tile sequence; producer `which` issues the tiles with
+// tile % NPW == which, so the per-tile cost of a wait + expect_tx + TMA issue (a few hundred cycles for one thread,
+// measured: one producer capped the kernel at 2.5 TB/s) is spread over NPW threads.
 struct Ring {
     uint8_t* base;
     uint64_t *full, *empty;
     int nslot;
-    unsigned tile;  // running tile index of this CTA
+    unsigned tile;   // running tile index of this CTA (all producers count every tile)
     int* err;
+    unsigned which;  // this producer's residue
+    unsigned slot;   // ring slot and phase of this producer's NEXT tile
+    unsigned phase;
 };
 
 __device__ __forceinline__ void produce_tile(Ring& r, const CUtensorMap* tm, int c0, int c1) {
-    const unsigned slot = r.tile % r.nslot, ph = (r.tile / r.nslot) & 1;
-    mbar_wait_bounded(&r.empty[slot], ph ^ 1, r.err, 2);
-    mbar_arrive_expect_tx(&r.full[slot], TILE);
-    tma_load_2d(r.base + (size_t)slot * TILE, tm, &r.full[slot], c0, c1);
+    if ((r.tile & (NPW - 1)) == r.which) {
+        mbar_wait_bounded(&r.empty[r.slot], r.phase ^ 1, r.err, 2);
+        mbar_arrive_expect_tx(&r.full[r.slot], TILE);
+        tma_load_2d(r.base + (size_t)r.slot * TILE, tm, &r.full[r.slot], c0, c1);
+        r.slot += NPW;
+        if (r.slot >= (unsigned)r.nslot) { r.slot -= r.nslot; r.phase ^= 1; }
+    }
     ++r.tile;
 }
 
@@ -233,44 +244,45 @@ __device__ __forceinline__ void grid_sync(const MegaParams& p, const Cons& c, un
         const unsigned target = epoch * (unsigned)G;
         unsigned long long t0 = 0;
         for (int it = 0; ld_acquire_u32(p.bar) < target; ++it) {
-            if (it < 256) continue;
+            if ((it & 0x3ff) != 0x3ff) continue;
             if (ld_volatile_i32(p.err)) break;
             if (t0 == 0) t0 = globaltimer_ns();
             else if (globaltimer_ns() - t0 > kWaitLimitNs) { atomicExch(p.err, 1); break; }
-            __nanosleep(20);
         }
         __threadfence();
     }
     consumer_sync();
 }
 
-// xs[s][k] = (norm_w ? norm_w[k] * bf16(x[s][k] * rsqrt(mean(x^2) + eps)) : x[s][k]) for s < B, zeros for s >= B.
+// xs[s][k] = (norm_w ? norm_w[k] * bf16(x[s][k] * rsqrt(mean(x^2) + eps)) : x[s][k]) for the B live streams.
+// The K range is cut into NCW fixed slices; warp w owns slice w of EVERY stream, and a stream's sum of squares is the
+// sum of its 8 slice sums in slice order — the same arithmetic whether the stream is alone or one of eight.
 __device__ void stage_x(const MegaParams& p, const Cons& c, const Shared& sh, const bf16* src, int K, const bf16* norm_w,
-                        int xpitch, int bpad) {
-    const int s = c.warp % bpad, sl = c.warp / bpad, nsl = NCW / bpad;
+                        int xpitch) {
     const int chunks = K >> 3;
-    const int c0 = (int)((long long)chunks * sl / nsl), c1 = (int)((long long)chunks * (sl + 1) / nsl);
-    float* part = reinterpret_cast<float*>(sh.scratch + SC_PART);
-    const bool live = s < p.B;
-    const bf16* row = src + (size_t)s * K;
+    const int c0 = (int)((long long)chunks * c.warp / NCW), c1 = (int)((long long)chunks * (c.warp + 1) / NCW);
+    float* part = reinterpret_cast<float*>(sh.scratch + SC_PART);  // [MG_MAXB][NCW]
     if (norm_w) {
-        float sq = 0.f;
-        if (live)
+        for (int s = 0; s < p.B; ++s) {
+            const bf16* row = src + (size_t)s * K;
+            float sq = 0.f;
             for (int ch = c0 + c.lane; ch < c1; ch += 32) {
                 const uint4 u = ld_cg_u128(row + ch * 8);
                 const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
                 for (int j = 0; j < 4; ++j) { const float2 f = unpack_bf16x2(uw[j]); sq += f.x * f.x + f.y * f.y; }
             }
-        sq = warp_sum(sq);
-        if (c.lane == 0) part[c.warp] = sq;
+            sq = warp_sum(sq);
+            if (c.lane == 0) part[s * NCW + c.warp] = sq;
+        }
         consumer_sync();
-        float tot = 0.f;
-        for (int j = 0; j < nsl; ++j) tot += part[s + bpad * j];
-        const float rs = rsqrtf(tot / (float)K + p.eps);
-        for (int ch = c0 + c.lane; ch < c1; ch += 32) {
-            uint4 o = make_uint4(0u, 0u, 0u, 0u);
-            if (live) {
+        for (int s = 0; s < p.B; ++s) {
+            const bf16* row = src + (size_t)s * K;
+            float tot = 0.f;
+#pragma unroll
+            for (int j = 0; j < NCW; ++j) tot += part[s * NCW + j];
+            const float rs = rsqrtf(tot / (float)K + p.eps);
+            for (int ch = c0 + c.lane; ch < c1; ch += 32) {
                 const uint4 u = ld_cg_u128(row + ch * 8);
                 const uint4 wv = *reinterpret_cast<const uint4*>(norm_w + ch * 8);
                 const uint32_t uw[4] = {u.x, u.y, u.z, u.w}, ww[4] = {wv.x, wv.y, wv.z, wv.w};
@@ -280,15 +292,13 @@ __device__ void stage_x(const MegaParams& p, const Cons& c, const Shared& sh, co
                     const float2 f = unpack_bf16x2(uw[j]), g = unpack_bf16x2(ww[j]);
                     ov[j] = pack_bf16x2(g.x * rbf(f.x * rs), g.y * rbf(f.y * rs));
                 }
-                o = make_uint4(ov[0], ov[1], ov[2], ov[3]);
+                *reinterpret_cast<uint4*>(sh.xs + (size_t)s * xpitch + ch * 8) = make_uint4(ov[0], ov[1], ov[2], ov[3]);
             }
-            *reinterpret_cast<uint4*>(sh.xs + (size_t)s * xpitch + ch * 8) = o;
         }
     } else {
-        for (int ch = c0 + c.lane; ch < c1; ch += 32) {
-            const uint4 o = live ? ld_cg_u128(row + ch * 8) : make_uint4(0u, 0u, 0u, 0u);
-            *reinterpret_cast<uint4*>(sh.xs + (size_t)s * xpitch + ch * 8) = o;
-        }
+        for (int s = 0; s < p.B; ++s)
+            for (int ch = c0 + c.lane; ch < c1; ch += 32)
+                *reinterpret_cast<uint4*>(sh.xs + (size_t)s * xpitch + ch * 8) = ld_cg_u128(src + (size_t)s * K + ch * 8);
     }
     consumer_sync();
 }
@@ -643,10 +653,10 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_cons
     const bool ph_qkv = p.phase_mask & 1, ph_attn = p.phase_mask & 2, ph_o = p.phase_mask & 4, ph_gu = p.phase_mask & 8,
                ph_down = p.phase_mask & 16;
     unsigned rr = 0;
-    if (warp == NCW) {
-        // ================================= producer =================================
+    if (warp >= NCW) {
+        // ================================= producers =================================
         if (lane == 0) {
-            Ring r{sh.ring, sh.full, sh.empty, p.nslot, 0u, p.err};
+            Ring r{sh.ring, sh.full, sh.empty, p.nslot, 0u, p.err, (unsigned)(warp - NCW), (unsigned)(warp - NCW), 0u};
             for (int l = p.layer_begin; l < p.layer_end; ++l) {
                 const CUtensorMap* wm = p.wmaps + 4 * l;
                 if (ph_qkv) producer_gemv(r, wm + 0, p.qkv_dim, p.H, rr, cta, G);
@@ -665,7 +675,7 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_cons
     for (int l = p.layer_begin; l < p.layer_end; ++l) {
         const MegaLayer& ly = p.layers[l];
         if (ph_qkv) {
-            stage_x(p, c, sh, p.h, p.H, ly.ln1_w, xpitch, bpad);
+            stage_x(p, c, sh, p.h, p.H, ly.ln1_w, xpitch);
             GemvOut o{ly.qkv_b, p.qkv, nullptr, nullptr};
             consumer_gemv<EP_BIAS, false>(p, c, sh, p.qkv_dim, p.H, nullptr, xpitch, o, rr, cta, G);
             grid_sync(p, c, epoch, G);
@@ -675,13 +685,13 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_cons
             grid_sync(p, c, epoch, G);
         }
         if (ph_o) {
-            stage_x(p, c, sh, p.attn, p.Hq * 128, nullptr, xpitch, bpad);
+            stage_x(p, c, sh, p.attn, p.Hq * 128, nullptr, xpitch);
             GemvOut o{nullptr, p.h, nullptr, nullptr};
             consumer_gemv<EP_RESIDUAL, false>(p, c, sh, p.H, p.Hq * 128, nullptr, xpitch, o, rr, cta, G);
             grid_sync(p, c, epoch, G);
         }
         if (ph_gu) {
-            stage_x(p, c, sh, p.h, p.H, ly.ln2_w, xpitch, bpad);
+            stage_x(p, c, sh, p.h, p.H, ly.ln2_w, xpitch);
             GemvOut o{nullptr, p.act, nullptr, nullptr};
             consumer_gemv<EP_SWIGLU, false>(p, c, sh, 2 * p.I, p.H, nullptr, xpitch, o, rr, cta, G);
             grid_sync(p, c, epoch, G);
@@ -693,7 +703,7 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_cons
         }
     }
     if (p.do_head) {
-        stage_x(p, c, sh, p.h, p.H, p.final_norm_w, xpitch, bpad);
+        stage_x(p, c, sh, p.h, p.H, p.final_norm_w, xpitch);
         GemvOut o{nullptr, nullptr, p.logits_raw, p.logits_proc};
         consumer_gemv<EP_LOGITS, false>(p, c, sh, p.V, p.H, nullptr, xpitch, o, rr, cta, G);
     }

@@ -8,7 +8,7 @@
 namespace lcc {
 
 constexpr int MG_MAXB = 8;         // streams per launch (the 8 columns of an m16n8k16 B operand)
-constexpr int MG_THREADS = 288;    // 8 consumer warps + 1 producer warp
+constexpr int MG_THREADS = 384;    // 8 consumer warps + 4 producer warps (one lane each)
 constexpr int MG_MAX_SLOTS = 52;   // ring slots of 4 KB
 constexpr int MG_MAX_ITEMS = 64;   // split-KV items per (stream, kv head)
 
