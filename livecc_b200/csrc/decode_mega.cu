@@ -483,6 +483,7 @@ __device__ void consumer_attn(const MegaParams& p, Cons& c, const Shared& sh, in
                             const uint32_t a = ((ch & 8) ? v_hi : v_lo) + r * 128 + (((ch & 7) ^ (r & 7)) << 4);
                             asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%1};" ::"r"(a), "r"(0u) : "memory");
                         }
+                        fence_proxy_async_smem();  // these generic-proxy stores must be ordered before the slot's next TMA fill
                         __syncwarp();
                     }
                     float s[4][4];
@@ -718,6 +719,10 @@ int mega_smem_bytes(int H, int B, int* nslot_out) {
     const int fixed = 1024 /*align*/ + xs + SCRATCH + MG_MAX_SLOTS * 16 + 128;
     int nslot = (232448 - fixed) / TILE;
     if (nslot > MG_MAX_SLOTS) nslot = MG_MAX_SLOTS;
+    // A multiple of the producer count: slot s is then always armed by producer s % NPW, so two rounds of one slot are
+    // ordered inside one thread. (With nslot % NPW != 0 a producer running a full ring round ahead of its neighbour
+    // passes the parity wait of a slot whose previous round has not even been issued -> double arm -> launch failure.)
+    nslot &= ~(NPW - 1);
     *nslot_out = nslot;
     return fixed + nslot * TILE;
 }

@@ -150,7 +150,9 @@ def test_phases_match_the_per_op_kernels(which, request, ctx):
                 assert nm.mega_error() == 0, f"persistent kernel flagged error {nm.mega_error()} (layer {layer} mask {mask})"
                 got = _ws(eng, off, 8, cols)[:B]
                 for b in range(B):
-                    _close(got[b], ref[key][b], what=f"B={B} layer {layer} phase {key} stream {b}")
+                    # gate rounding flips (1 ulp of the pre-activation) move silu(g)*u by a few ulps of the tensor scale
+                    _close(got[b], ref[key][b], ulps=4.0 if key in ("act", "h_out") else 2.0,
+                           what=f"B={B} layer {layer} phase {key} stream {b}")
             h0 = h_rows[:B].clone()   # output of the full layer feeds the next one
         # lm_head
         lg_ref = [ctx.gemv_norm_logits(eng.weights.lm_head, h0[b].clone(), eng.weights.final_norm_w, t.rms_norm_eps)[0] for b in range(B)]
