@@ -130,6 +130,7 @@ struct Shared {
     int* s_T;           // [8] old tokens in the cache per stream
     int* s_pos;         // [8] rope position of the new token
     int* s_active;      // [8]
+    unsigned* released; // [nslot] number of rounds of each slot that have been consumed (see wait_tile)
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -218,20 +219,40 @@ __device__ void producer_attn(Ring& r, const MegaParams& p, const Shared& sh, co
 struct Cons {
     uint8_t* ring;
     uint64_t *full, *empty;
+    unsigned* released;
     int nslot;
     unsigned tile;  // tile index of the first tile of the current phase for this CTA
     int* err;
     int warp, lane, tid;
 };
 
+// Consecutive rounds of one ring slot are in general consumed by DIFFERENT warps (the tile -> warp map follows the K
+// split / the attention units, not the slot index). A parity wait alone is then ambiguous: a warp that asks for round r
+// while the slot's barrier is still in round r-1 sees "parity differs" and would read the tile a round early. Each slot
+// therefore carries a count of consumed rounds; the consumer of round r first waits until r rounds were released (then
+// the barrier is provably in round r) and only then does the parity wait.
 __device__ __forceinline__ uint32_t wait_tile(const Cons& c, unsigned t) {
-    const unsigned slot = t % c.nslot, ph = (t / c.nslot) & 1;
-    mbar_wait_bounded(&c.full[slot], ph, c.err, 3);
+    const unsigned slot = t % c.nslot, round = t / c.nslot;
+    const volatile unsigned* rel = c.released + slot;
+    if (*rel != round) {
+        unsigned long long t0 = 0;
+        for (int it = 0; *rel != round; ++it) {
+            if ((it & 0xfff) != 0xfff) continue;
+            if (ld_volatile_i32(c.err)) break;
+            if (t0 == 0) t0 = globaltimer_ns();
+            else if (globaltimer_ns() - t0 > kWaitLimitNs) { atomicExch(c.err, 4); break; }
+        }
+    }
+    mbar_wait_bounded(&c.full[slot], round & 1, c.err, 3);
     return smem_u32(c.ring + (size_t)slot * TILE);
 }
 __device__ __forceinline__ void release_tile(const Cons& c, unsigned t) {
     __syncwarp();
-    if (c.lane == 0) mbar_arrive(&c.empty[t % c.nslot]);
+    if (c.lane == 0) {
+        const unsigned slot = t % c.nslot;
+        *(volatile unsigned*)(c.released + slot) = t / c.nslot + 1;
+        mbar_arrive(&c.empty[slot]);   // release.cta: the count above is visible before the slot can be refilled
+    }
 }
 
 // Grid-wide barrier among the consumer halves of all CTAs (the producers never wait here).
@@ -630,11 +651,12 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_cons
     sh.s_T = reinterpret_cast<int*>(sh.empty + MG_MAX_SLOTS);
     sh.s_pos = sh.s_T + 8;
     sh.s_active = sh.s_pos + 8;
+    sh.released = reinterpret_cast<unsigned*>(sh.s_active + 8);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cta = blockIdx.x, G = gridDim.x;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < p.nslot; ++i) { mbar_init(&sh.full[i], 1); mbar_init(&sh.empty[i], 1); }
+        for (int i = 0; i < p.nslot; ++i) { mbar_init(&sh.full[i], 1); mbar_init(&sh.empty[i], 1); sh.released[i] = 0u; }
         fence_barrier_init();
     }
     if (threadIdx.x < 8) {
@@ -671,7 +693,7 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_cons
         return;
     }
     // ================================= consumers =================================
-    Cons c{sh.ring, sh.full, sh.empty, p.nslot, 0u, p.err, warp, lane, (int)threadIdx.x};
+    Cons c{sh.ring, sh.full, sh.empty, sh.released, p.nslot, 0u, p.err, warp, lane, (int)threadIdx.x};
     unsigned epoch = 0;
     for (int l = p.layer_begin; l < p.layer_end; ++l) {
         const MegaLayer& ly = p.layers[l];
@@ -716,7 +738,7 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_cons
 int mega_smem_bytes(int H, int B, int* nslot_out) {
     const int bpad = B <= 1 ? 1 : (B <= 2 ? 2 : (B <= 4 ? 4 : 8));
     const int xs = ((bpad * (H + 8) * 2) + 127) & ~127;
-    const int fixed = 1024 /*align*/ + xs + SCRATCH + MG_MAX_SLOTS * 16 + 128;
+    const int fixed = 1024 /*align*/ + xs + SCRATCH + MG_MAX_SLOTS * 16 + 384;  // barriers, stream scalars, released[]
     int nslot = (232448 - fixed) / TILE;
     if (nslot > MG_MAX_SLOTS) nslot = MG_MAX_SLOTS;
     // A multiple of the producer count: slot s is then always armed by producer s % NPW, so two rounds of one slot are

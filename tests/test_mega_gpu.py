@@ -73,6 +73,9 @@ def _close(a, b, ulps=2.0, frac=1e-3, what="", **_):
               f"ref|max| {b.abs().max().item():.3f}", flush=True)
         if bad > frac or nan:
             _failed.append(what)
+            wrong = ((a - b).abs() > tol).nonzero().flatten()
+            blocks = sorted(set((wrong // 32).tolist()))
+            print(f"[mega]    wrong 32-row blocks ({len(blocks)}): {blocks[:40]}", flush=True)
         return
     assert bad <= frac, f"{what}: {bad:.3e} of elements beyond {ulps} bf16 ulps, max abs err {(a - b).abs().max().item():.4e}"
 
