@@ -28,6 +28,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "../../include/livecc_b200.h"
 #include "common.cuh"
 #include "gemm.h"
@@ -165,27 +167,49 @@ struct Ring {
     unsigned which;  // this producer's residue
     unsigned slot;   // ring slot and phase of this producer's NEXT tile
     unsigned phase;
+    unsigned limit;  // look-ahead mode: stop after this tile index
 };
 
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* tm, int c_inner, int c_outer) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(tm)),
+                 "r"(c_inner), "r"(c_outer)
+                 : "memory");
+}
+
+// PF = false: issue the tile into the ring. PF = true (look-ahead): only ask the L2 for it. When a producer has issued
+// the last tile of a phase, the ring is full of that phase's tail and it would idle until the consumers have crossed the
+// grid barrier, normalised their activations and started to drain the ring (~6 us per phase, longer than the ring is
+// deep). It spends that time pulling the head of the NEXT phase (kLookAhead tiles per CTA, ~38 MB chip-wide) from HBM
+// into L2, so HBM keeps streaming through the dependency bubble and the ring later refills at L2 speed.
+template <bool PF>
 __device__ __forceinline__ void produce_tile(Ring& r, const CUtensorMap* tm, int c0, int c1) {
     if ((r.tile & (NPW - 1)) == r.which) {
-        mbar_wait_bounded(&r.empty[r.slot], r.phase ^ 1, r.err, 2);
-        mbar_arrive_expect_tx(&r.full[r.slot], TILE);
-        tma_load_2d(r.base + (size_t)r.slot * TILE, tm, &r.full[r.slot], c0, c1);
-        r.slot += NPW;
-        if (r.slot >= (unsigned)r.nslot) { r.slot -= r.nslot; r.phase ^= 1; }
+        if (PF) {
+            tma_prefetch_l2_2d(tm, c0, c1);
+        } else {
+            mbar_wait_bounded(&r.empty[r.slot], r.phase ^ 1, r.err, 2);
+            mbar_arrive_expect_tx(&r.full[r.slot], TILE);
+            tma_load_2d(r.base + (size_t)r.slot * TILE, tm, &r.full[r.slot], c0, c1);
+            r.slot += NPW;
+            if (r.slot >= (unsigned)r.nslot) { r.slot -= r.nslot; r.phase ^= 1; }
+        }
     }
     ++r.tile;
 }
 
+template <bool PF>
 __device__ void producer_gemv(Ring& r, const CUtensorMap* tm, int N, int K, unsigned& rr, int cta, int G) {
     const int RB = N >> 5, KC = K >> 6;
     const int first = (int)(((unsigned)cta + (unsigned)G - rr % (unsigned)G) % (unsigned)G);
-    for (int b = first; b < RB; b += G)
-        for (int kc = 0; kc < KC; ++kc) produce_tile(r, tm, kc * 64, b * 32);
     rr += RB;
+    for (int b = first; b < RB; b += G)
+        for (int kc = 0; kc < KC; ++kc) {
+            if (PF && r.tile >= r.limit) return;
+            produce_tile<PF>(r, tm, kc * 64, b * 32);
+        }
 }
 
+template <bool PF>
 __device__ void producer_attn(Ring& r, const MegaParams& p, const Shared& sh, const CUtensorMap* tk, const CUtensorMap* tv,
                               int layer, unsigned& rr, int cta, int G) {
     unsigned gi = 0;
@@ -202,10 +226,11 @@ __device__ void producer_attn(Ring& r, const MegaParams& p, const Shared& sh, co
                     const int t0 = u << 5;
                     const int page = pt[t0 >> 6];
                     const int row = layer * p.kv_rows_per_layer + (page * p.Hkv + g) * 64 + (t0 & 32);
-                    produce_tile(r, tk, 0, row);
-                    produce_tile(r, tk, 64, row);
-                    produce_tile(r, tv, 0, row);
-                    produce_tile(r, tv, 64, row);
+                    if (PF && r.tile >= r.limit) return;
+                    produce_tile<PF>(r, tk, 0, row);
+                    produce_tile<PF>(r, tk, 64, row);
+                    produce_tile<PF>(r, tv, 0, row);
+                    produce_tile<PF>(r, tv, 64, row);
                 }
             }
         }
@@ -231,8 +256,7 @@ struct Cons {
 // while the slot's barrier is still in round r-1 sees "parity differs" and would read the tile a round early. Each slot
 // therefore carries a count of consumed rounds; the consumer of round r first waits until r rounds were released (then
 // the barrier is provably in round r) and only then does the parity wait.
-__device__ __forceinline__ uint32_t wait_tile(const Cons& c, unsigned t) {
-    const unsigned slot = t % c.nslot, round = t / c.nslot;
+__device__ __forceinline__ uint32_t wait_slot(const Cons& c, unsigned slot, unsigned round) {
     const volatile unsigned* rel = c.released + slot;
     if (*rel != round) {
         unsigned long long t0 = 0;
@@ -246,14 +270,15 @@ __device__ __forceinline__ uint32_t wait_tile(const Cons& c, unsigned t) {
     mbar_wait_bounded(&c.full[slot], round & 1, c.err, 3);
     return smem_u32(c.ring + (size_t)slot * TILE);
 }
-__device__ __forceinline__ void release_tile(const Cons& c, unsigned t) {
+__device__ __forceinline__ void release_slot(const Cons& c, unsigned slot, unsigned round) {
     __syncwarp();
     if (c.lane == 0) {
-        const unsigned slot = t % c.nslot;
-        *(volatile unsigned*)(c.released + slot) = t / c.nslot + 1;
+        *(volatile unsigned*)(c.released + slot) = round + 1;
         mbar_arrive(&c.empty[slot]);   // release.cta: the count above is visible before the slot can be refilled
     }
 }
+__device__ __forceinline__ uint32_t wait_tile(const Cons& c, unsigned t) { return wait_slot(c, t % c.nslot, t / c.nslot); }
+__device__ __forceinline__ void release_tile(const Cons& c, unsigned t) { release_slot(c, t % c.nslot, t / c.nslot); }
 
 // Grid-wide barrier among the consumer halves of all CTAs (the producers never wait here).
 __device__ __forceinline__ void grid_sync(const MegaParams& p, const Cons& c, unsigned& epoch, int G) {
@@ -284,11 +309,13 @@ __device__ void stage_x(const MegaParams& p, const Cons& c, const Shared& sh, co
     const int c0 = (int)((long long)chunks * c.warp / NCW), c1 = (int)((long long)chunks * (c.warp + 1) / NCW);
     float* part = reinterpret_cast<float*>(sh.scratch + SC_PART);  // [MG_MAXB][NCW]
     if (norm_w) {
+        // pass 1: global (L2) -> xs raw + this slice's sum of squares; pass 2: normalise in shared memory
         for (int s = 0; s < p.B; ++s) {
             const bf16* row = src + (size_t)s * K;
             float sq = 0.f;
             for (int ch = c0 + c.lane; ch < c1; ch += 32) {
                 const uint4 u = ld_cg_u128(row + ch * 8);
+                *reinterpret_cast<uint4*>(sh.xs + (size_t)s * xpitch + ch * 8) = u;
                 const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
                 for (int j = 0; j < 4; ++j) { const float2 f = unpack_bf16x2(uw[j]); sq += f.x * f.x + f.y * f.y; }
@@ -298,13 +325,13 @@ __device__ void stage_x(const MegaParams& p, const Cons& c, const Shared& sh, co
         }
         consumer_sync();
         for (int s = 0; s < p.B; ++s) {
-            const bf16* row = src + (size_t)s * K;
             float tot = 0.f;
 #pragma unroll
             for (int j = 0; j < NCW; ++j) tot += part[s * NCW + j];
             const float rs = rsqrtf(tot / (float)K + p.eps);
             for (int ch = c0 + c.lane; ch < c1; ch += 32) {
-                const uint4 u = ld_cg_u128(row + ch * 8);
+                uint4* xp = reinterpret_cast<uint4*>(sh.xs + (size_t)s * xpitch + ch * 8);
+                const uint4 u = *xp;
                 const uint4 wv = *reinterpret_cast<const uint4*>(norm_w + ch * 8);
                 const uint32_t uw[4] = {u.x, u.y, u.z, u.w}, ww[4] = {wv.x, wv.y, wv.z, wv.w};
                 uint32_t ov[4];
@@ -313,7 +340,7 @@ __device__ void stage_x(const MegaParams& p, const Cons& c, const Shared& sh, co
                     const float2 f = unpack_bf16x2(uw[j]), g = unpack_bf16x2(ww[j]);
                     ov[j] = pack_bf16x2(g.x * rbf(f.x * rs), g.y * rbf(f.y * rs));
                 }
-                *reinterpret_cast<uint4*>(sh.xs + (size_t)s * xpitch + ch * 8) = make_uint4(ov[0], ov[1], ov[2], ov[3]);
+                *xp = make_uint4(ov[0], ov[1], ov[2], ov[3]);
             }
         }
     } else {
@@ -349,6 +376,7 @@ __device__ void consumer_gemv(const MegaParams& p, Cons& c, const Shared& sh, in
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[m][j] = 0.f;
         const unsigned tbase = c.tile + (unsigned)biter * KC;
+        unsigned slot = (tbase + c.warp) % c.nslot, round = (tbase + c.warp) / c.nslot;  // advanced by NCW per tile below
         for (int kc = c.warp; kc < KC; kc += NCW) {
             uint32_t bx[4][2];
             if (XG) {  // issue the activation loads before waiting for the weight tile
@@ -359,7 +387,7 @@ __device__ void consumer_gemv(const MegaParams& p, Cons& c, const Shared& sh, in
                     bx[kk][1] = g < p.B ? ld_cg_u32(xp + 8) : 0u;
                 }
             }
-            const uint32_t tb = wait_tile(c, tbase + kc);
+            const uint32_t tb = wait_slot(c, slot, round);
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
                 if (!XG) {  // xs holds bpad rows only: columns >= B of the MMA are zero and never read back
@@ -378,7 +406,9 @@ __device__ void consumer_gemv(const MegaParams& p, Cons& c, const Shared& sh, in
                              : "=r"(af[0]), "=r"(af[1]), "=r"(af[2]), "=r"(af[3]) : "r"(a0 + 16 * 128));
                 mma_bf16_16816(acc[1], af, bx[kk][0], bx[kk][1]);
             }
-            release_tile(c, tbase + kc);
+            release_slot(c, slot, round);
+            slot += NCW;
+            if (slot >= (unsigned)c.nslot) { slot -= c.nslot; ++round; }
         }
         // cross-warp K reduction, fixed order
         float* rb = red + (biter & 1) * (NCW * 32 * 8);
@@ -679,16 +709,31 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_cons
     if (warp >= NCW) {
         // ================================= producers =================================
         if (lane == 0) {
-            Ring r{sh.ring, sh.full, sh.empty, p.nslot, 0u, p.err, (unsigned)(warp - NCW), (unsigned)(warp - NCW), 0u};
-            for (int l = p.layer_begin; l < p.layer_end; ++l) {
+            Ring r{sh.ring, sh.full, sh.empty, p.nslot, 0u, p.err, (unsigned)(warp - NCW), (unsigned)(warp - NCW), 0u, 0u};
+            // phase index i -> (layer, kind): kinds 0..4 = qkv, attention, o_proj, gate/up, down; the last index = lm_head
+            const int nl = p.layer_end - p.layer_begin;
+            const int nph = nl * 5 + (p.do_head ? 1 : 0);
+            auto run = [&](auto pf, int i, Ring& rg, unsigned& rrg) {
+                constexpr bool PF = decltype(pf)::value;
+                if (i >= nl * 5) { producer_gemv<PF>(rg, p.wmaps + 4 * p.L, p.V, p.H, rrg, cta, G); return; }
+                const int l = p.layer_begin + i / 5, kind = i % 5;
+                if (!((p.phase_mask >> kind) & 1)) return;
                 const CUtensorMap* wm = p.wmaps + 4 * l;
-                if (ph_qkv) producer_gemv(r, wm + 0, p.qkv_dim, p.H, rr, cta, G);
-                if (ph_attn) producer_attn(r, p, sh, &tmap_k, &tmap_v, l, rr, cta, G);
-                if (ph_o) producer_gemv(r, wm + 1, p.H, p.Hq * 128, rr, cta, G);
-                if (ph_gu) producer_gemv(r, wm + 2, 2 * p.I, p.H, rr, cta, G);
-                if (ph_down) producer_gemv(r, wm + 3, p.H, p.I, rr, cta, G);
+                if (kind == 0) producer_gemv<PF>(rg, wm + 0, p.qkv_dim, p.H, rrg, cta, G);
+                else if (kind == 1) producer_attn<PF>(rg, p, sh, &tmap_k, &tmap_v, l, rrg, cta, G);
+                else if (kind == 2) producer_gemv<PF>(rg, wm + 1, p.H, p.Hq * 128, rrg, cta, G);
+                else if (kind == 3) producer_gemv<PF>(rg, wm + 2, 2 * p.I, p.H, rrg, cta, G);
+                else producer_gemv<PF>(rg, wm + 3, p.H, p.I, rrg, cta, G);
+            };
+            for (int i = 0; i < nph; ++i) {
+                run(std::false_type{}, i, r, rr);
+                if (p.lookahead > 0 && i + 1 < nph) {   // look-ahead into the next phase on copies of the cursors
+                    Ring ra = r;
+                    unsigned rra = rr;
+                    ra.limit = ra.tile + (unsigned)p.lookahead;
+                    run(std::true_type{}, i + 1, ra, rra);
+                }
             }
-            if (p.do_head) producer_gemv(r, p.wmaps + 4 * p.L, p.V, p.H, rr, cta, G);
         }
         return;
     }

@@ -40,6 +40,7 @@ struct MegaParams {
     unsigned* bar;                        // grid barrier counter, zero at launch
     int* err;                             // sticky error flag (bounded waits)
     int nslot;
+    int lookahead;   // tiles per CTA the producers pull into L2 ahead of the ring at each phase end (0 = off)
     int layer_begin, layer_end, phase_mask, do_head;  // sub-range execution (tests); full step = 0, L, 31, 1
     float scale_log2;
 };

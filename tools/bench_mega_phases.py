@@ -18,7 +18,11 @@ H, I, L, V = t.hidden_size, t.intermediate_size, t.num_hidden_layers, t.vocab_si
 qkv_dim = (t.num_attention_heads + 2 * t.num_key_value_heads) * 128
 peak = float(json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"]) \
     if os.path.exists(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")) else 6574.1
-for B, kv in [(1, 1000), (1, 17000), (4, 8000), (8, 8000)]:
+only = os.environ.get("PHASES")  # e.g. "full" -> only the lines whose name contains it
+cases = [(1, 1000), (1, 17000), (4, 8000), (8, 8000)] if not os.environ.get("CASES") else \
+    [tuple(int(x) for x in c.split(":")) for c in os.environ["CASES"].split(",")]
+print("look-ahead tiles:", os.environ.get("LIVECC_B200_MEGA_LOOKAHEAD", "default"))
+for B, kv in cases:
     g = torch.Generator().manual_seed(0)
     reqs = [dict(input_ids=torch.randint(1000, 9000, (1, kv), generator=g).cuda()) for _ in range(B)]
     outs = eng.generate_batch(reqs, max_new_tokens=1)
@@ -33,6 +37,8 @@ for B, kv in [(1, 1000), (1, 17000), (4, 8000), (8, 8000)]:
               ("full step", 31, 1, (qkv_dim * H + H * H + 3 * I * H) * 2 + kvb)]
     print(f"B={B} kv_len={kv}")
     for name, mask, head, per_layer in phases:
+        if only and only not in name:
+            continue
         nl = L if mask else 0
         nbytes = per_layer * nl + (V * H * 2 if head else 0)
         for _ in range(2):
