@@ -42,7 +42,9 @@ namespace lcc {
 namespace {
 
 constexpr int NCW = 8;                  // consumer warps
-constexpr int NPW = 4;                  // producer warps (power of two, <= ring slots)
+constexpr int NPW = 2;                  // producer warps (power of two; ring groups are a multiple of it)
+constexpr int GT = 4;                   // tiles per ring group: one TMA op moves GT tiles (16 KB)
+constexpr int GROUP = 4096 * GT;
 constexpr int NCT = NCW * 32;           // consumer threads
 constexpr int TILE = 4096;              // bytes per ring slot
 constexpr int QPITCH = 136;             // bf16 elements per staged q row
@@ -124,7 +126,7 @@ __device__ __forceinline__ bool mbar_wait_bounded(uint64_t* bar, uint32_t parity
 }
 
 struct Shared {
-    uint8_t* ring;      // nslot x TILE, 1024-aligned
+    uint8_t* ring;      // ngroup x GROUP, 1024-aligned
     bf16* xs;           // [bpad][xpitch]
     uint8_t* scratch;   // SCRATCH bytes
     uint64_t* full;     // [nslot]
@@ -155,61 +157,48 @@ __device__ __forceinline__ PairPlan plan_pair(int T) {
 // ------------------------------------------------------------------------------------------------------------
 // producer
 // ------------------------------------------------------------------------------------------------------------
-// NPW producer warps (one lane each) walk the same tile sequence; producer `which` issues the tiles with
-// tile % NPW == which, so the per-tile cost of a wait + expect_tx + TMA issue (a few hundred cycles for one thread,
-// measured: one producer capped the kernel at 2.5 TB/s) is spread over NPW threads.
+// NPW producer warps (one lane each) walk the same GROUP sequence (a group = GT = 4 consecutive tiles = 16 KB = one TMA
+// op for weights, two for a K/V unit); producer `which` issues the groups with group % NPW == which. Measured on B200:
+// with one 4 KB box per op the TMA path delivered ~40 GB/s per SM whatever the ring depth (per-op cost, not latency) and
+// one producer thread could not even issue that; 16 KB ops cut the op count by four.
 struct Ring {
     uint8_t* base;
     uint64_t *full, *empty;
-    int nslot;
-    unsigned tile;   // running tile index of this CTA (all producers count every tile)
+    int ngroup;
+    unsigned group;  // running group index of this CTA (all producers count every group)
     int* err;
     unsigned which;  // this producer's residue
-    unsigned slot;   // ring slot and phase of this producer's NEXT tile
+    unsigned slot;   // ring slot (group granularity) and phase of this producer's NEXT group
     unsigned phase;
-    unsigned limit;  // look-ahead mode: stop after this tile index
 };
 
-__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* tm, int c_inner, int c_outer) {
-    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(tm)),
-                 "r"(c_inner), "r"(c_outer)
-                 : "memory");
+__device__ __forceinline__ bool producer_begin(Ring& r) {   // true: this producer owns the group; slot is armed
+    const bool mine = (r.group & (NPW - 1)) == r.which;
+    ++r.group;
+    if (!mine) return false;
+    mbar_wait_bounded(&r.empty[r.slot], r.phase ^ 1, r.err, 2);
+    mbar_arrive_expect_tx(&r.full[r.slot], GROUP);
+    return true;
+}
+__device__ __forceinline__ void producer_end(Ring& r) {
+    r.slot += NPW;
+    if (r.slot >= (unsigned)r.ngroup) { r.slot -= r.ngroup; r.phase ^= 1; }
 }
 
-// PF = false: issue the tile into the ring. PF = true (look-ahead): only ask the L2 for it. When a producer has issued
-// the last tile of a phase, the ring is full of that phase's tail and it would idle until the consumers have crossed the
-// grid barrier, normalised their activations and started to drain the ring (~6 us per phase, longer than the ring is
-// deep). It spends that time pulling the head of the NEXT phase (kLookAhead tiles per CTA, ~38 MB chip-wide) from HBM
-// into L2, so HBM keeps streaming through the dependency bubble and the ring later refills at L2 speed.
-template <bool PF>
-__device__ __forceinline__ void produce_tile(Ring& r, const CUtensorMap* tm, int c0, int c1) {
-    if ((r.tile & (NPW - 1)) == r.which) {
-        if (PF) {
-            tma_prefetch_l2_2d(tm, c0, c1);
-        } else {
-            mbar_wait_bounded(&r.empty[r.slot], r.phase ^ 1, r.err, 2);
-            mbar_arrive_expect_tx(&r.full[r.slot], TILE);
-            tma_load_2d(r.base + (size_t)r.slot * TILE, tm, &r.full[r.slot], c0, c1);
-            r.slot += NPW;
-            if (r.slot >= (unsigned)r.nslot) { r.slot -= r.nslot; r.phase ^= 1; }
-        }
-    }
-    ++r.tile;
-}
-
-template <bool PF>
+// weights: 3-D view [k chunk][row][64] of the [N][K] matrix (mega_make_weight_tmap), box = 4 chunks x 32 rows x 64
 __device__ void producer_gemv(Ring& r, const CUtensorMap* tm, int N, int K, unsigned& rr, int cta, int G) {
-    const int RB = N >> 5, KC = K >> 6;
+    const int RB = N >> 5, KG = K >> 8;  // groups of 4 k-chunks
     const int first = (int)(((unsigned)cta + (unsigned)G - rr % (unsigned)G) % (unsigned)G);
     rr += RB;
     for (int b = first; b < RB; b += G)
-        for (int kc = 0; kc < KC; ++kc) {
-            if (PF && r.tile >= r.limit) return;
-            produce_tile<PF>(r, tm, kc * 64, b * 32);
-        }
+        for (int kg = 0; kg < KG; ++kg)
+            if (producer_begin(r)) {
+                tma_load_3d(r.base + (size_t)r.slot * GROUP, tm, &r.full[r.slot], 0, b * 32, kg * GT);
+                producer_end(r);
+            }
 }
 
-template <bool PF>
+// K/V: 3-D view [half][row][64] of a pool (128 dims = 2 halves), box = 2 halves x 32 rows x 64 = 8 KB; a unit = K op + V op
 __device__ void producer_attn(Ring& r, const MegaParams& p, const Shared& sh, const CUtensorMap* tk, const CUtensorMap* tv,
                               int layer, unsigned& rr, int cta, int G) {
     unsigned gi = 0;
@@ -223,14 +212,14 @@ __device__ void producer_attn(Ring& r, const MegaParams& p, const Shared& sh, co
             for (int it = it0; it < pp.nitems; it += G) {
                 const int u1 = min(pp.units, (it + 1) * pp.cu);
                 for (int u = it * pp.cu; u < u1; ++u) {
+                    if (!producer_begin(r)) continue;
                     const int t0 = u << 5;
                     const int page = pt[t0 >> 6];
                     const int row = layer * p.kv_rows_per_layer + (page * p.Hkv + g) * 64 + (t0 & 32);
-                    if (PF && r.tile >= r.limit) return;
-                    produce_tile<PF>(r, tk, 0, row);
-                    produce_tile<PF>(r, tk, 64, row);
-                    produce_tile<PF>(r, tv, 0, row);
-                    produce_tile<PF>(r, tv, 64, row);
+                    uint8_t* dst = r.base + (size_t)r.slot * GROUP;
+                    tma_load_3d(dst, tk, &r.full[r.slot], 0, row, 0);
+                    tma_load_3d(dst + 2 * TILE, tv, &r.full[r.slot], 0, row, 0);
+                    producer_end(r);
                 }
             }
         }
@@ -245,22 +234,23 @@ struct Cons {
     uint8_t* ring;
     uint64_t *full, *empty;
     unsigned* released;
-    int nslot;
-    unsigned tile;  // tile index of the first tile of the current phase for this CTA
+    int ngroup;
+    unsigned tile;  // tile index of the first tile of the current phase for this CTA (a multiple of GT)
     int* err;
     int warp, lane, tid;
 };
 
-// Consecutive rounds of one ring slot are in general consumed by DIFFERENT warps (the tile -> warp map follows the K
-// split / the attention units, not the slot index). A parity wait alone is then ambiguous: a warp that asks for round r
-// while the slot's barrier is still in round r-1 sees "parity differs" and would read the tile a round early. Each slot
-// therefore carries a count of consumed rounds; the consumer of round r first waits until r rounds were released (then
-// the barrier is provably in round r) and only then does the parity wait.
-__device__ __forceinline__ uint32_t wait_slot(const Cons& c, unsigned slot, unsigned round) {
+// The GT tiles of a ring group are in general consumed by DIFFERENT warps, and so are consecutive rounds of a group. A
+// parity wait alone is then ambiguous: a warp that asks for round r while the group's barrier is still in round r-1
+// sees "parity differs" and would read its tile a round early. Each group therefore counts its released tiles; the
+// consumer of a tile of round r first waits until GT*r tiles were released (then the barrier is provably in round r)
+// and only then does the parity wait.
+__device__ __forceinline__ uint32_t wait_tile(const Cons& c, unsigned t) {
+    const unsigned grp = t / GT, slot = grp % c.ngroup, round = grp / c.ngroup;
     const volatile unsigned* rel = c.released + slot;
-    if (*rel != round) {
+    if (*rel < GT * round) {
         unsigned long long t0 = 0;
-        for (int it = 0; *rel != round; ++it) {
+        for (int it = 0; *rel < GT * round; ++it) {
             if ((it & 0xfff) != 0xfff) continue;
             if (ld_volatile_i32(c.err)) break;
             if (t0 == 0) t0 = globaltimer_ns();
@@ -268,17 +258,16 @@ __device__ __forceinline__ uint32_t wait_slot(const Cons& c, unsigned slot, unsi
         }
     }
     mbar_wait_bounded(&c.full[slot], round & 1, c.err, 3);
-    return smem_u32(c.ring + (size_t)slot * TILE);
+    return smem_u32(c.ring + (size_t)slot * GROUP + (size_t)(t % GT) * TILE);
 }
-__device__ __forceinline__ void release_slot(const Cons& c, unsigned slot, unsigned round) {
+__device__ __forceinline__ void release_tile(const Cons& c, unsigned t) {
     __syncwarp();
     if (c.lane == 0) {
-        *(volatile unsigned*)(c.released + slot) = round + 1;
-        mbar_arrive(&c.empty[slot]);   // release.cta: the count above is visible before the slot can be refilled
+        const unsigned slot = (t / GT) % c.ngroup;
+        atomicAdd(c.released + slot, 1u);
+        mbar_arrive(&c.empty[slot]);   // GT arrivals free the group; release.cta orders the count before any refill
     }
 }
-__device__ __forceinline__ uint32_t wait_tile(const Cons& c, unsigned t) { return wait_slot(c, t % c.nslot, t / c.nslot); }
-__device__ __forceinline__ void release_tile(const Cons& c, unsigned t) { release_slot(c, t % c.nslot, t / c.nslot); }
 
 // Grid-wide barrier among the consumer halves of all CTAs (the producers never wait here).
 __device__ __forceinline__ void grid_sync(const MegaParams& p, const Cons& c, unsigned& epoch, int G) {
@@ -376,7 +365,6 @@ __device__ void consumer_gemv(const MegaParams& p, Cons& c, const Shared& sh, in
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[m][j] = 0.f;
         const unsigned tbase = c.tile + (unsigned)biter * KC;
-        unsigned slot = (tbase + c.warp) % c.nslot, round = (tbase + c.warp) / c.nslot;  // advanced by NCW per tile below
         for (int kc = c.warp; kc < KC; kc += NCW) {
             uint32_t bx[4][2];
             if (XG) {  // issue the activation loads before waiting for the weight tile
@@ -387,7 +375,7 @@ __device__ void consumer_gemv(const MegaParams& p, Cons& c, const Shared& sh, in
                     bx[kk][1] = g < p.B ? ld_cg_u32(xp + 8) : 0u;
                 }
             }
-            const uint32_t tb = wait_slot(c, slot, round);
+            const uint32_t tb = wait_tile(c, tbase + kc);
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
                 if (!XG) {  // xs holds bpad rows only: columns >= B of the MMA are zero and never read back
@@ -406,9 +394,7 @@ __device__ void consumer_gemv(const MegaParams& p, Cons& c, const Shared& sh, in
                              : "=r"(af[0]), "=r"(af[1]), "=r"(af[2]), "=r"(af[3]) : "r"(a0 + 16 * 128));
                 mma_bf16_16816(acc[1], af, bx[kk][0], bx[kk][1]);
             }
-            release_slot(c, slot, round);
-            slot += NCW;
-            if (slot >= (unsigned)c.nslot) { slot -= c.nslot; ++round; }
+            release_tile(c, tbase + kc);
         }
         // cross-warp K reduction, fixed order
         float* rb = red + (biter & 1) * (NCW * 32 * 8);
@@ -674,7 +660,7 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_cons
     const int xpitch = p.H + 8;
     Shared sh;
     sh.ring = sm;
-    sh.xs = reinterpret_cast<bf16*>(sm + (size_t)p.nslot * TILE);
+    sh.xs = reinterpret_cast<bf16*>(sm + (size_t)p.ngroup * GROUP);
     sh.scratch = reinterpret_cast<uint8_t*>(sh.xs) + (((size_t)bpad * xpitch * 2 + 127) & ~size_t(127));
     sh.full = reinterpret_cast<uint64_t*>(sh.scratch + SCRATCH);
     sh.empty = sh.full + MG_MAX_SLOTS;
@@ -686,7 +672,7 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_cons
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cta = blockIdx.x, G = gridDim.x;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < p.nslot; ++i) { mbar_init(&sh.full[i], 1); mbar_init(&sh.empty[i], 1); sh.released[i] = 0u; }
+        for (int i = 0; i < p.ngroup; ++i) { mbar_init(&sh.full[i], 1); mbar_init(&sh.empty[i], GT); sh.released[i] = 0u; }
         fence_barrier_init();
     }
     if (threadIdx.x < 8) {
@@ -709,36 +695,21 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_cons
     if (warp >= NCW) {
         // ================================= producers =================================
         if (lane == 0) {
-            Ring r{sh.ring, sh.full, sh.empty, p.nslot, 0u, p.err, (unsigned)(warp - NCW), (unsigned)(warp - NCW), 0u, 0u};
-            // phase index i -> (layer, kind): kinds 0..4 = qkv, attention, o_proj, gate/up, down; the last index = lm_head
-            const int nl = p.layer_end - p.layer_begin;
-            const int nph = nl * 5 + (p.do_head ? 1 : 0);
-            auto run = [&](auto pf, int i, Ring& rg, unsigned& rrg) {
-                constexpr bool PF = decltype(pf)::value;
-                if (i >= nl * 5) { producer_gemv<PF>(rg, p.wmaps + 4 * p.L, p.V, p.H, rrg, cta, G); return; }
-                const int l = p.layer_begin + i / 5, kind = i % 5;
-                if (!((p.phase_mask >> kind) & 1)) return;
+            Ring r{sh.ring, sh.full, sh.empty, p.ngroup, 0u, p.err, (unsigned)(warp - NCW), (unsigned)(warp - NCW), 0u};
+            for (int l = p.layer_begin; l < p.layer_end; ++l) {
                 const CUtensorMap* wm = p.wmaps + 4 * l;
-                if (kind == 0) producer_gemv<PF>(rg, wm + 0, p.qkv_dim, p.H, rrg, cta, G);
-                else if (kind == 1) producer_attn<PF>(rg, p, sh, &tmap_k, &tmap_v, l, rrg, cta, G);
-                else if (kind == 2) producer_gemv<PF>(rg, wm + 1, p.H, p.Hq * 128, rrg, cta, G);
-                else if (kind == 3) producer_gemv<PF>(rg, wm + 2, 2 * p.I, p.H, rrg, cta, G);
-                else producer_gemv<PF>(rg, wm + 3, p.H, p.I, rrg, cta, G);
-            };
-            for (int i = 0; i < nph; ++i) {
-                run(std::false_type{}, i, r, rr);
-                if (p.lookahead > 0 && i + 1 < nph) {   // look-ahead into the next phase on copies of the cursors
-                    Ring ra = r;
-                    unsigned rra = rr;
-                    ra.limit = ra.tile + (unsigned)p.lookahead;
-                    run(std::true_type{}, i + 1, ra, rra);
-                }
+                if (ph_qkv) producer_gemv(r, wm + 0, p.qkv_dim, p.H, rr, cta, G);
+                if (ph_attn) producer_attn(r, p, sh, &tmap_k, &tmap_v, l, rr, cta, G);
+                if (ph_o) producer_gemv(r, wm + 1, p.H, p.Hq * 128, rr, cta, G);
+                if (ph_gu) producer_gemv(r, wm + 2, 2 * p.I, p.H, rr, cta, G);
+                if (ph_down) producer_gemv(r, wm + 3, p.H, p.I, rr, cta, G);
             }
+            if (p.do_head) producer_gemv(r, p.wmaps + 4 * p.L, p.V, p.H, rr, cta, G);
         }
         return;
     }
     // ================================= consumers =================================
-    Cons c{sh.ring, sh.full, sh.empty, sh.released, p.nslot, 0u, p.err, warp, lane, (int)threadIdx.x};
+    Cons c{sh.ring, sh.full, sh.empty, sh.released, p.ngroup, 0u, p.err, warp, lane, (int)threadIdx.x};
     unsigned epoch = 0;
     for (int l = p.layer_begin; l < p.layer_end; ++l) {
         const MegaLayer& ly = p.layers[l];
@@ -780,44 +751,48 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_cons
 // ------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------
-int mega_smem_bytes(int H, int B, int* nslot_out) {
+int mega_smem_bytes(int H, int B, int* ngroup_out) {
     const int bpad = B <= 1 ? 1 : (B <= 2 ? 2 : (B <= 4 ? 4 : 8));
     const int xs = ((bpad * (H + 8) * 2) + 127) & ~127;
     const int fixed = 1024 /*align*/ + xs + SCRATCH + MG_MAX_SLOTS * 16 + 384;  // barriers, stream scalars, released[]
-    int nslot = (232448 - fixed) / TILE;
-    if (nslot > MG_MAX_SLOTS) nslot = MG_MAX_SLOTS;
-    // A multiple of the producer count: slot s is then always armed by producer s % NPW, so two rounds of one slot are
-    // ordered inside one thread. (With nslot % NPW != 0 a producer running a full ring round ahead of its neighbour
-    // passes the parity wait of a slot whose previous round has not even been issued -> double arm -> launch failure.)
-    nslot &= ~(NPW - 1);
-    *nslot_out = nslot;
-    return fixed + nslot * TILE;
+    int ngroup = (232448 - fixed) / GROUP;
+    if (ngroup > MG_MAX_SLOTS) ngroup = MG_MAX_SLOTS;
+    // A multiple of the producer count: group slot s is then always armed by producer s % NPW, so two rounds of one slot
+    // are ordered inside one thread (a producer a full ring round ahead of its neighbour would otherwise pass the parity
+    // wait of a slot whose previous round has not even been issued -> double arm -> launch failure).
+    ngroup &= ~(NPW - 1);
+    *ngroup_out = ngroup;
+    return fixed + ngroup * GROUP;
 }
 
+// [N][K] bf16 weights as a 3-D tensor {64 cols, N rows, K/64 chunks}: one box = 4 consecutive k-chunks of 32 rows, landing
+// in shared memory as 4 consecutive 4 KB tiles [32 rows][128 B], each in the SWIZZLE_128B layout ldmatrix expects.
 int mega_make_weight_tmap(CUtensorMap* tm, const void* w, int N, int K) {
-    return make_tmap_bf16_2d_box(tm, w, N, K, K, 64, 32, false);
+    if (K % 256) return -1;
+    return make_tmap_bf16_3d_sw128(tm, w, 64, N, K / 64, K, 64, 32, GT);
 }
 
 int decode_mega_launch(const MegaParams& p_in, const void* k_pool, const void* v_pool, long long pool_rows, int num_sms,
                        cudaStream_t s) {
     MegaParams p = p_in;
     if (p.B < 1 || p.B > MG_MAXB || p.Hq % p.Hkv || p.Hq / p.Hkv > 8) return -1;
-    if ((p.qkv_dim % 32) || (p.H % 64) || (p.I % 64) || ((2 * p.I) % 32) || (p.V % 32) || ((p.Hq * 128) % 64)) return -2;
-    int nslot = 0;
-    const int smem = mega_smem_bytes(p.H, p.B, &nslot);
-    if (nslot < 16) return -3;
-    p.nslot = nslot;
+    if ((p.qkv_dim % 32) || (p.H % 256) || (p.I % 256) || ((2 * p.I) % 32) || (p.V % 32)) return -2;
+    int ngroup = 0;
+    const int smem = mega_smem_bytes(p.H, p.B, &ngroup);
+    if (ngroup < 4) return -3;
+    p.ngroup = ngroup;
+    // pools viewed as {64 cols, rows, 2 halves}: one box = both 64-dim halves of 32 tokens -> tiles (lo, hi)
     CUtensorMap tk, tv;
-    if (make_tmap_bf16_2d_box(&tk, k_pool, pool_rows, 128, 128, 64, 32, false)) return -10;
-    if (make_tmap_bf16_2d_box(&tv, v_pool, pool_rows, 128, 128, 64, 32, false)) return -11;
+    if (make_tmap_bf16_3d_sw128(&tk, k_pool, 64, pool_rows, 2, 128, 64, 32, 2)) return -10;
+    if (make_tmap_bf16_3d_sw128(&tv, v_pool, 64, pool_rows, 2, 128, 64, 32, 2)) return -11;
     static SmemAttrOnce once;
     if (ensure_dyn_smem(once, decode_mega_kernel, 232448)) return -12;  // the opt-in maximum: the request varies with B
     count_launch();
     decode_mega_kernel<<<num_sms, MG_THREADS, smem, s>>>(tk, tv, p);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
-        fprintf(stderr, "[livecc_b200] decode_mega_kernel launch failed: %s (B=%d, smem=%d, nslot=%d)\n", cudaGetErrorString(e),
-                p.B, smem, nslot);
+        fprintf(stderr, "[livecc_b200] decode_mega_kernel launch failed: %s (B=%d, smem=%d, ngroup=%d)\n", cudaGetErrorString(e),
+                p.B, smem, ngroup);
         return -13;
     }
     return 0;

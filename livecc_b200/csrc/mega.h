@@ -8,8 +8,8 @@
 namespace lcc {
 
 constexpr int MG_MAXB = 8;         // streams per launch (the 8 columns of an m16n8k16 B operand)
-constexpr int MG_THREADS = 384;    // 8 consumer warps + 4 producer warps (one lane each)
-constexpr int MG_MAX_SLOTS = 52;   // ring slots of 4 KB
+constexpr int MG_THREADS = 320;    // 8 consumer warps + 2 producer warps (one lane each)
+constexpr int MG_MAX_SLOTS = 16;   // ring groups of 16 KB
 constexpr int MG_MAX_ITEMS = 64;   // split-KV items per (stream, kv head)
 
 struct MegaLayer {
@@ -39,13 +39,12 @@ struct MegaParams {
     int* pair_cnt;                        // [8*Hkv], zero between launches
     unsigned* bar;                        // grid barrier counter, zero at launch
     int* err;                             // sticky error flag (bounded waits)
-    int nslot;
-    int lookahead;   // tiles per CTA the producers pull into L2 ahead of the ring at each phase end (0 = off)
+    int ngroup;      // ring depth in 16 KB groups
     int layer_begin, layer_end, phase_mask, do_head;  // sub-range execution (tests); full step = 0, L, 31, 1
     float scale_log2;
 };
 
-int mega_smem_bytes(int H, int B, int* nslot_out);
+int mega_smem_bytes(int H, int B, int* ngroup_out);
 int mega_make_weight_tmap(CUtensorMap* tm, const void* w, int N, int K);
 // k_pool/v_pool: whole pools viewed as [pool_rows, 128] bf16. Enqueues the kernel on `s` (p.bar must be zero).
 int decode_mega_launch(const MegaParams& p, const void* k_pool, const void* v_pool, long long pool_rows, int num_sms,

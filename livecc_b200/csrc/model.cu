@@ -26,7 +26,6 @@ struct lcc_model {
     uint8_t* ws = nullptr;
     size_t ws_bytes = 0;
     int cap_patches = 0, cap_tokens = 0;
-    int mega_lookahead = 64;  // LIVECC_B200_MEGA_LOOKAHEAD: L2 look-ahead tiles (4 KB) per CTA at each phase end
     bool use_mega = true;   // persistent decode-step kernel (decode_mega.cu); LIVECC_B200_MEGA=0 selects the per-op kernels
     bool mega_ok = false;   // geometry supported by the persistent kernel and its tables are uploaded
     bool fuse_attn_oproj = false;  // LIVECC_B200_FUSE=1: one launch for decode attention + o_proj (flag-synchronised roles)
@@ -161,7 +160,6 @@ lcc_model* lcc_model_create(lcc_ctx* ctx, const lcc_model_config* cfg, const lcc
     m->w.layers = m->layers.data();
     const char* mega_env = getenv("LIVECC_B200_MEGA");
     m->use_mega = !(mega_env && mega_env[0] == '0');
-    if (const char* la = getenv("LIVECC_B200_MEGA_LOOKAHEAD")) m->mega_lookahead = atoi(la) < 0 ? 0 : atoi(la);
     const char* fuse_env = getenv("LIVECC_B200_FUSE");
     m->fuse_attn_oproj = fuse_env && fuse_env[0] == '1';
 #ifdef LCC_ENABLE_PDL
@@ -328,7 +326,6 @@ static int mega_step_params(lcc_model* m, const lcc_stream_state* sts, int B, co
     int* cnt = (int*)(ws + L.mg_cnt);
     p.pair_cnt = cnt; p.bar = (unsigned*)(cnt + 96); p.err = cnt + 97;
     p.layer_begin = 0; p.layer_end = c.layers; p.phase_mask = 31; p.do_head = 1;
-    p.lookahead = m->mega_lookahead;
     p.scale_log2 = 1.4426950408889634f / sqrtf(128.f);
     *out = p;
     return 0;
@@ -468,7 +465,7 @@ extern "C" int lcc_model_bind_workspace(lcc_model* m, void* ws, size_t ws_bytes,
     const WsLayout L = make_layout(c, max_patches, max_tokens);
     const int qkv_dim = (c.q_heads + 2 * c.kv_heads) * 128;
     m->mega_ok = false;
-    if (!(qkv_dim % 32) && !(c.hidden % 64) && !(c.inter % 64) && !(c.vocab % 32) && c.q_heads / c.kv_heads <= 8) {
+    if (!(qkv_dim % 32) && !(c.hidden % 256) && !(c.inter % 256) && !(c.vocab % 32) && c.q_heads / c.kv_heads <= 8) {
         std::vector<CUtensorMap> maps(4 * c.layers + 1);
         std::vector<lcc::MegaLayer> lays(c.layers);
         bool ok = true;
