@@ -134,7 +134,8 @@ struct Shared {
     int* s_T;           // [8] old tokens in the cache per stream
     int* s_pos;         // [8] rope position of the new token
     int* s_active;      // [8]
-    unsigned* released; // [nslot] number of rounds of each slot that have been consumed (see wait_tile)
+    unsigned* released; // [ngroup] tiles of each group slot released so far (see wait_tile)
+    unsigned* prog;     // [NPW] groups walked so far by each TMA producer (paces the L2 prefetcher)
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -170,11 +171,42 @@ struct Ring {
     unsigned which;  // this producer's residue
     unsigned slot;   // ring slot (group granularity) and phase of this producer's NEXT group
     unsigned phase;
+    volatile unsigned* prog;  // [NPW] progress counters in shared memory
+    unsigned lookahead;       // prefetcher: groups it may run ahead of the slowest TMA producer
 };
 
-__device__ __forceinline__ bool producer_begin(Ring& r) {   // true: this producer owns the group; slot is armed
+__device__ __forceinline__ void tma_prefetch_l2_3d(const CUtensorMap* tm, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(reinterpret_cast<uint64_t>(tm)),
+                 "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+
+// PF = false (TMA producers): true if this producer owns the group; its slot is then armed.
+// PF = true (the L2 prefetcher, one extra thread walking the same sequence): every group is its own; it only waits until
+// it is at most `lookahead` groups ahead of the slowest TMA producer. The ring (160 KB/SM) is exactly what the TMA path
+// needs in flight for full bandwidth, so any stall of the consumers (grid barrier, RMSNorm staging, split-K reduction:
+// ~4 us per phase, measured) used to stop HBM. The prefetcher keeps pulling the stream into L2 (lookahead x 16 KB per SM,
+// ~38 MB chip-wide) through those bubbles, and the ring then refills from L2.
+template <bool PF>
+__device__ __forceinline__ bool producer_begin(Ring& r) {
+    if (PF) {
+        unsigned long long t0 = 0;
+        for (int it = 0;; ++it) {
+            unsigned m = r.prog[0];
+#pragma unroll
+            for (int j = 1; j < NPW; ++j) m = min(m, r.prog[j]);
+            if (r.group < m + r.lookahead) break;
+            if ((it & 0xfff) != 0xfff) continue;
+            if (ld_volatile_i32(r.err)) break;
+            if (t0 == 0) t0 = globaltimer_ns();
+            else if (globaltimer_ns() - t0 > kWaitLimitNs) break;   // pacing only: giving up is harmless
+        }
+        ++r.group;
+        return true;
+    }
     const bool mine = (r.group & (NPW - 1)) == r.which;
     ++r.group;
+    r.prog[r.which] = r.group;
     if (!mine) return false;
     mbar_wait_bounded(&r.empty[r.slot], r.phase ^ 1, r.err, 2);
     mbar_arrive_expect_tx(&r.full[r.slot], GROUP);
@@ -186,19 +218,25 @@ __device__ __forceinline__ void producer_end(Ring& r) {
 }
 
 // weights: 3-D view [k chunk][row][64] of the [N][K] matrix (mega_make_weight_tmap), box = 4 chunks x 32 rows x 64
+template <bool PF>
 __device__ void producer_gemv(Ring& r, const CUtensorMap* tm, int N, int K, unsigned& rr, int cta, int G) {
     const int RB = N >> 5, KG = K >> 8;  // groups of 4 k-chunks
     const int first = (int)(((unsigned)cta + (unsigned)G - rr % (unsigned)G) % (unsigned)G);
     rr += RB;
     for (int b = first; b < RB; b += G)
         for (int kg = 0; kg < KG; ++kg)
-            if (producer_begin(r)) {
-                tma_load_3d(r.base + (size_t)r.slot * GROUP, tm, &r.full[r.slot], 0, b * 32, kg * GT);
-                producer_end(r);
+            if (producer_begin<PF>(r)) {
+                if (PF) {
+                    tma_prefetch_l2_3d(tm, 0, b * 32, kg * GT);
+                } else {
+                    tma_load_3d(r.base + (size_t)r.slot * GROUP, tm, &r.full[r.slot], 0, b * 32, kg * GT);
+                    producer_end(r);
+                }
             }
 }
 
 // K/V: 3-D view [half][row][64] of a pool (128 dims = 2 halves), box = 2 halves x 32 rows x 64 = 8 KB; a unit = K op + V op
+template <bool PF>
 __device__ void producer_attn(Ring& r, const MegaParams& p, const Shared& sh, const CUtensorMap* tk, const CUtensorMap* tv,
                               int layer, unsigned& rr, int cta, int G) {
     unsigned gi = 0;
@@ -212,14 +250,19 @@ __device__ void producer_attn(Ring& r, const MegaParams& p, const Shared& sh, co
             for (int it = it0; it < pp.nitems; it += G) {
                 const int u1 = min(pp.units, (it + 1) * pp.cu);
                 for (int u = it * pp.cu; u < u1; ++u) {
-                    if (!producer_begin(r)) continue;
+                    if (!producer_begin<PF>(r)) continue;
                     const int t0 = u << 5;
                     const int page = pt[t0 >> 6];
                     const int row = layer * p.kv_rows_per_layer + (page * p.Hkv + g) * 64 + (t0 & 32);
-                    uint8_t* dst = r.base + (size_t)r.slot * GROUP;
-                    tma_load_3d(dst, tk, &r.full[r.slot], 0, row, 0);
-                    tma_load_3d(dst + 2 * TILE, tv, &r.full[r.slot], 0, row, 0);
-                    producer_end(r);
+                    if (PF) {
+                        tma_prefetch_l2_3d(tk, 0, row, 0);
+                        tma_prefetch_l2_3d(tv, 0, row, 0);
+                    } else {
+                        uint8_t* dst = r.base + (size_t)r.slot * GROUP;
+                        tma_load_3d(dst, tk, &r.full[r.slot], 0, row, 0);
+                        tma_load_3d(dst + 2 * TILE, tv, &r.full[r.slot], 0, row, 0);
+                        producer_end(r);
+                    }
                 }
             }
         }
@@ -668,11 +711,13 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_cons
     sh.s_pos = sh.s_T + 8;
     sh.s_active = sh.s_pos + 8;
     sh.released = reinterpret_cast<unsigned*>(sh.s_active + 8);
+    sh.prog = sh.released + MG_MAX_SLOTS;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cta = blockIdx.x, G = gridDim.x;
     if (threadIdx.x == 0) {
         for (int i = 0; i < p.ngroup; ++i) { mbar_init(&sh.full[i], 1); mbar_init(&sh.empty[i], GT); sh.released[i] = 0u; }
+        for (int i = 0; i < NPW; ++i) sh.prog[i] = 0u;
         fence_barrier_init();
     }
     if (threadIdx.x < 8) {
@@ -694,17 +739,27 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_cons
     unsigned rr = 0;
     if (warp >= NCW) {
         // ================================= producers =================================
-        if (lane == 0) {
-            Ring r{sh.ring, sh.full, sh.empty, p.ngroup, 0u, p.err, (unsigned)(warp - NCW), (unsigned)(warp - NCW), 0u};
-            for (int l = p.layer_begin; l < p.layer_end; ++l) {
-                const CUtensorMap* wm = p.wmaps + 4 * l;
-                if (ph_qkv) producer_gemv(r, wm + 0, p.qkv_dim, p.H, rr, cta, G);
-                if (ph_attn) producer_attn(r, p, sh, &tmap_k, &tmap_v, l, rr, cta, G);
-                if (ph_o) producer_gemv(r, wm + 1, p.H, p.Hq * 128, rr, cta, G);
-                if (ph_gu) producer_gemv(r, wm + 2, 2 * p.I, p.H, rr, cta, G);
-                if (ph_down) producer_gemv(r, wm + 3, p.H, p.I, rr, cta, G);
+        if (lane == 0 && (warp < NCW + NPW || p.lookahead > 0)) {
+            const bool pf = warp == NCW + NPW;   // the last warp is the L2 prefetcher
+            Ring r{sh.ring, sh.full, sh.empty, p.ngroup, 0u, p.err, (unsigned)(warp - NCW), (unsigned)(warp - NCW), 0u, sh.prog,
+                   (unsigned)(p.ngroup + p.lookahead)};
+            auto walk = [&](auto tag) {
+                constexpr bool PF = decltype(tag)::value;
+                for (int l = p.layer_begin; l < p.layer_end; ++l) {
+                    const CUtensorMap* wm = p.wmaps + 4 * l;
+                    if (ph_qkv) producer_gemv<PF>(r, wm + 0, p.qkv_dim, p.H, rr, cta, G);
+                    if (ph_attn) producer_attn<PF>(r, p, sh, &tmap_k, &tmap_v, l, rr, cta, G);
+                    if (ph_o) producer_gemv<PF>(r, wm + 1, p.H, p.Hq * 128, rr, cta, G);
+                    if (ph_gu) producer_gemv<PF>(r, wm + 2, 2 * p.I, p.H, rr, cta, G);
+                    if (ph_down) producer_gemv<PF>(r, wm + 3, p.H, p.I, rr, cta, G);
+                }
+                if (p.do_head) producer_gemv<PF>(r, p.wmaps + 4 * p.L, p.V, p.H, rr, cta, G);
+            };
+            if (pf) walk(std::true_type{});
+            else {
+                walk(std::false_type{});
+                sh.prog[warp - NCW] = 0x7fffffffu;   // done: never hold the prefetcher back
             }
-            if (p.do_head) producer_gemv(r, p.wmaps + 4 * p.L, p.V, p.H, rr, cta, G);
         }
         return;
     }
@@ -754,7 +809,7 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_cons
 int mega_smem_bytes(int H, int B, int* ngroup_out) {
     const int bpad = B <= 1 ? 1 : (B <= 2 ? 2 : (B <= 4 ? 4 : 8));
     const int xs = ((bpad * (H + 8) * 2) + 127) & ~127;
-    const int fixed = 1024 /*align*/ + xs + SCRATCH + MG_MAX_SLOTS * 16 + 384;  // barriers, stream scalars, released[]
+    const int fixed = 1024 /*align*/ + xs + SCRATCH + MG_MAX_SLOTS * 16 + 384;  // barriers, stream scalars, released[], prog[]
     int ngroup = (232448 - fixed) / GROUP;
     if (ngroup > MG_MAX_SLOTS) ngroup = MG_MAX_SLOTS;
     // A multiple of the producer count: group slot s is then always armed by producer s % NPW, so two rounds of one slot

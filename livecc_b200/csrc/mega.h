@@ -8,7 +8,7 @@
 namespace lcc {
 
 constexpr int MG_MAXB = 8;         // streams per launch (the 8 columns of an m16n8k16 B operand)
-constexpr int MG_THREADS = 320;    // 8 consumer warps + 2 producer warps (one lane each)
+constexpr int MG_THREADS = 352;    // 8 consumer warps + 2 TMA producer warps + 1 L2 prefetch warp (one lane each)
 constexpr int MG_MAX_SLOTS = 16;   // ring groups of 16 KB
 constexpr int MG_MAX_ITEMS = 64;   // split-KV items per (stream, kv head)
 
@@ -40,6 +40,7 @@ struct MegaParams {
     unsigned* bar;                        // grid barrier counter, zero at launch
     int* err;                             // sticky error flag (bounded waits)
     int ngroup;      // ring depth in 16 KB groups
+    int lookahead;   // groups (16 KB) per CTA the L2 prefetcher may run ahead of the ring (0 = no prefetcher)
     int layer_begin, layer_end, phase_mask, do_head;  // sub-range execution (tests); full step = 0, L, 31, 1
     float scale_log2;
 };

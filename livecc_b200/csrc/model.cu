@@ -26,6 +26,7 @@ struct lcc_model {
     uint8_t* ws = nullptr;
     size_t ws_bytes = 0;
     int cap_patches = 0, cap_tokens = 0;
+    int mega_lookahead = 16;  // LIVECC_B200_MEGA_LOOKAHEAD: 16 KB groups per CTA the L2 prefetcher runs ahead of the ring
     bool use_mega = true;   // persistent decode-step kernel (decode_mega.cu); LIVECC_B200_MEGA=0 selects the per-op kernels
     bool mega_ok = false;   // geometry supported by the persistent kernel and its tables are uploaded
     bool fuse_attn_oproj = false;  // LIVECC_B200_FUSE=1: one launch for decode attention + o_proj (flag-synchronised roles)
@@ -160,6 +161,7 @@ lcc_model* lcc_model_create(lcc_ctx* ctx, const lcc_model_config* cfg, const lcc
     m->w.layers = m->layers.data();
     const char* mega_env = getenv("LIVECC_B200_MEGA");
     m->use_mega = !(mega_env && mega_env[0] == '0');
+    if (const char* la = getenv("LIVECC_B200_MEGA_LOOKAHEAD")) m->mega_lookahead = atoi(la) < 0 ? 0 : atoi(la);
     const char* fuse_env = getenv("LIVECC_B200_FUSE");
     m->fuse_attn_oproj = fuse_env && fuse_env[0] == '1';
 #ifdef LCC_ENABLE_PDL
@@ -326,6 +328,7 @@ static int mega_step_params(lcc_model* m, const lcc_stream_state* sts, int B, co
     int* cnt = (int*)(ws + L.mg_cnt);
     p.pair_cnt = cnt; p.bar = (unsigned*)(cnt + 96); p.err = cnt + 97;
     p.layer_begin = 0; p.layer_end = c.layers; p.phase_mask = 31; p.do_head = 1;
+    p.lookahead = m->mega_lookahead;
     p.scale_log2 = 1.4426950408889634f / sqrtf(128.f);
     *out = p;
     return 0;
