@@ -280,6 +280,7 @@ int lcc_decode_mega_debug(lcc_model* m, const lcc_stream_state* states, int n_st
 #define LCC_WS_DECODE_ACT 5     /* bf16 [8][inter] */
 #define LCC_WS_LOGITS_PROC 6    /* f32 [8][vocab] processed logits */
 #define LCC_WS_MEGA_ERROR 7     /* int32: sticky error flag of the persistent decode kernel (0 = ok) */
+#define LCC_WS_MEGA_TRACE 8     /* u64 [256][64]: per-CTA globaltimer stamps when LIVECC_B200_MEGA_TRACE=1 */
 size_t lcc_ws_offset(const lcc_model* m, int which);
 
 #ifdef __cplusplus

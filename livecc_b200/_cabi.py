@@ -349,6 +349,7 @@ class NativeModel:
         self.decode_act_offset = self.lib.lcc_ws_offset(C.c_void_p(self.handle), 5)
         self.logits_proc_offset = self.lib.lcc_ws_offset(C.c_void_p(self.handle), 6)
         self.mega_error_offset = self.lib.lcc_ws_offset(C.c_void_p(self.handle), 7)
+        self.mega_trace_offset = self.lib.lcc_ws_offset(C.c_void_p(self.handle), 8)
 
     def mega_error(self) -> int:
         """Sticky error flag of the persistent decode kernel (synchronises the device)."""

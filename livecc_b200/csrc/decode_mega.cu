@@ -766,34 +766,53 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_cons
     // ================================= consumers =================================
     Cons c{sh.ring, sh.full, sh.empty, sh.released, p.ngroup, 0u, p.err, warp, lane, (int)threadIdx.x};
     unsigned epoch = 0;
+    int tr_n = 0;   // optional timeline (LIVECC_B200_MEGA_TRACE=1): globaltimer stamps of consumer thread 0, 64 per CTA
+#define MG_TRACE()                                                                                       \
+    do {                                                                                                 \
+        if (p.trace && c.tid == 0 && tr_n < 64) p.trace[(size_t)cta * 64 + tr_n++] = globaltimer_ns();  \
+    } while (0)
+    MG_TRACE();
     for (int l = p.layer_begin; l < p.layer_end; ++l) {
         const MegaLayer& ly = p.layers[l];
         if (ph_qkv) {
             stage_x(p, c, sh, p.h, p.H, ly.ln1_w, xpitch);
+            MG_TRACE();
             GemvOut o{ly.qkv_b, p.qkv, nullptr, nullptr};
             consumer_gemv<EP_BIAS, false>(p, c, sh, p.qkv_dim, p.H, nullptr, xpitch, o, rr, cta, G);
+            MG_TRACE();
             grid_sync(p, c, epoch, G);
+            MG_TRACE();
         }
         if (ph_attn) {
             consumer_attn(p, c, sh, l, rr, cta, G);
+            MG_TRACE();
             grid_sync(p, c, epoch, G);
+            MG_TRACE();
         }
         if (ph_o) {
             stage_x(p, c, sh, p.attn, p.Hq * 128, nullptr, xpitch);
+            MG_TRACE();
             GemvOut o{nullptr, p.h, nullptr, nullptr};
             consumer_gemv<EP_RESIDUAL, false>(p, c, sh, p.H, p.Hq * 128, nullptr, xpitch, o, rr, cta, G);
+            MG_TRACE();
             grid_sync(p, c, epoch, G);
+            MG_TRACE();
         }
         if (ph_gu) {
             stage_x(p, c, sh, p.h, p.H, ly.ln2_w, xpitch);
+            MG_TRACE();
             GemvOut o{nullptr, p.act, nullptr, nullptr};
             consumer_gemv<EP_SWIGLU, false>(p, c, sh, 2 * p.I, p.H, nullptr, xpitch, o, rr, cta, G);
+            MG_TRACE();
             grid_sync(p, c, epoch, G);
+            MG_TRACE();
         }
         if (ph_down) {
             GemvOut o{nullptr, p.h, nullptr, nullptr};
             consumer_gemv<EP_RESIDUAL, true>(p, c, sh, p.H, p.I, p.act, xpitch, o, rr, cta, G);
+            MG_TRACE();
             grid_sync(p, c, epoch, G);
+            MG_TRACE();
         }
     }
     if (p.do_head) {

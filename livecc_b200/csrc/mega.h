@@ -39,6 +39,7 @@ struct MegaParams {
     int* pair_cnt;                        // [8*Hkv], zero between launches
     unsigned* bar;                        // grid barrier counter, zero at launch
     int* err;                             // sticky error flag (bounded waits)
+    unsigned long long* trace;            // optional [grid][64] globaltimer stamps (bring-up/profiling aid), or null
     int ngroup;      // ring depth in 16 KB groups
     int lookahead;   // groups (16 KB) per CTA the L2 prefetcher may run ahead of the ring (0 = no prefetcher)
     int layer_begin, layer_end, phase_mask, do_head;  // sub-range execution (tests); full step = 0, L, 31, 1

@@ -26,7 +26,8 @@ struct lcc_model {
     uint8_t* ws = nullptr;
     size_t ws_bytes = 0;
     int cap_patches = 0, cap_tokens = 0;
-    int mega_lookahead = 16;  // LIVECC_B200_MEGA_LOOKAHEAD: 16 KB groups per CTA the L2 prefetcher runs ahead of the ring
+    int mega_lookahead = 0;  // LIVECC_B200_MEGA_LOOKAHEAD: 16 KB groups per CTA an L2 prefetcher thread runs ahead of the ring (measured slower: off)
+    bool mega_trace = false;  // LIVECC_B200_MEGA_TRACE=1: per-CTA phase timeline in the workspace (LCC_WS_MEGA_TRACE)
     bool use_mega = true;   // persistent decode-step kernel (decode_mega.cu); LIVECC_B200_MEGA=0 selects the per-op kernels
     bool mega_ok = false;   // geometry supported by the persistent kernel and its tables are uploaded
     bool fuse_attn_oproj = false;  // LIVECC_B200_FUSE=1: one launch for decode attention + o_proj (flag-synchronised roles)
@@ -45,7 +46,7 @@ struct WsLayout {
     size_t vx, vh, vn, vqkv, vattn, vmlp, vcos, vsin, vcu;  // ViT
     size_t hid, normed, qkv, attn, act, rank, pf_part_o, pf_part_ml, pf_splitk;  // prefill
     size_t h1, qkv1, attn1, act1, logits_raw, logits_proc, part_o, part_ml, attn_cnt;  // decode (8 stream rows each)
-    size_t mg_part_o, mg_part_ml, mg_cnt, mg_tmaps, mg_layers;  // persistent decode kernel
+    size_t mg_part_o, mg_part_ml, mg_cnt, mg_tmaps, mg_layers, mg_trace;  // persistent decode kernel
     size_t total;
 };
 
@@ -92,6 +93,7 @@ WsLayout make_layout(const lcc_model_config& c, int NP, int NT) {
     L.mg_cnt = take(128 * 4);  // [0, 8*kv_heads): pair counters; [96]: grid barrier; [97]: sticky error flag
     L.mg_tmaps = take((size_t)(4 * c.layers + 1) * sizeof(CUtensorMap));
     L.mg_layers = take((size_t)c.layers * sizeof(lcc::MegaLayer));
+    L.mg_trace = take((size_t)256 * 64 * 8);
     L.total = off;
     return L;
 }
@@ -161,6 +163,7 @@ lcc_model* lcc_model_create(lcc_ctx* ctx, const lcc_model_config* cfg, const lcc
     m->w.layers = m->layers.data();
     const char* mega_env = getenv("LIVECC_B200_MEGA");
     m->use_mega = !(mega_env && mega_env[0] == '0');
+    if (const char* te = getenv("LIVECC_B200_MEGA_TRACE")) m->mega_trace = te[0] == '1';
     if (const char* la = getenv("LIVECC_B200_MEGA_LOOKAHEAD")) m->mega_lookahead = atoi(la) < 0 ? 0 : atoi(la);
     const char* fuse_env = getenv("LIVECC_B200_FUSE");
     m->fuse_attn_oproj = fuse_env && fuse_env[0] == '1';
@@ -190,6 +193,7 @@ size_t lcc_ws_offset(const lcc_model* m, int which) {
         case LCC_WS_DECODE_ACT: return L.act1;
         case LCC_WS_LOGITS_PROC: return L.logits_proc;
         case LCC_WS_MEGA_ERROR: return L.mg_cnt + 97 * 4;
+        case LCC_WS_MEGA_TRACE: return L.mg_trace;
     }
     return 0;
 }
@@ -327,6 +331,7 @@ static int mega_step_params(lcc_model* m, const lcc_stream_state* sts, int B, co
     p.part_o = (float*)(ws + L.mg_part_o); p.part_ml = (float*)(ws + L.mg_part_ml);
     int* cnt = (int*)(ws + L.mg_cnt);
     p.pair_cnt = cnt; p.bar = (unsigned*)(cnt + 96); p.err = cnt + 97;
+    p.trace = m->mega_trace ? (unsigned long long*)(ws + L.mg_trace) : nullptr;
     p.layer_begin = 0; p.layer_end = c.layers; p.phase_mask = 31; p.do_head = 1;
     p.lookahead = m->mega_lookahead;
     p.scale_log2 = 1.4426950408889634f / sqrtf(128.f);
