@@ -79,11 +79,6 @@ __device__ __forceinline__ float ld_cg_f32(const float* p) {
     asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p));
     return v;
 }
-__device__ __forceinline__ float4 ld_cg_f32x4(const float* p) {
-    float4 r;
-    asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
-    return r;
-}
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
     unsigned v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -317,8 +312,8 @@ __device__ __forceinline__ void grid_sync(const MegaParams& p, const Cons& c, un
     consumer_sync();
     ++epoch;
     if (c.tid == 0) {
-        __threadfence();
-        atomicAdd(p.bar, 1u);
+        // release at gpu scope: cumulative over everything the other consumer threads wrote before the bar.sync above
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.bar) : "memory");
         const unsigned target = epoch * (unsigned)G;
         unsigned long long t0 = 0;
         for (int it = 0; ld_acquire_u32(p.bar) < target; ++it) {
@@ -327,7 +322,6 @@ __device__ __forceinline__ void grid_sync(const MegaParams& p, const Cons& c, un
             if (t0 == 0) t0 = globaltimer_ns();
             else if (globaltimer_ns() - t0 > kWaitLimitNs) { atomicExch(p.err, 1); break; }
         }
-        __threadfence();
     }
     consumer_sync();
 }
@@ -341,6 +335,13 @@ __device__ void stage_x(const MegaParams& p, const Cons& c, const Shared& sh, co
     const int c0 = (int)((long long)chunks * c.warp / NCW), c1 = (int)((long long)chunks * (c.warp + 1) / NCW);
     float* part = reinterpret_cast<float*>(sh.scratch + SC_PART);  // [MG_MAXB][NCW]
     if (norm_w) {
+        // the norm weights of this lane's chunks (static data): in flight together with the activation loads below
+        uint4 nw[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int ch = c0 + c.lane + 32 * j;
+            nw[j] = ch < c1 ? *reinterpret_cast<const uint4*>(norm_w + ch * 8) : make_uint4(0u, 0u, 0u, 0u);
+        }
         // pass 1: global (L2) -> xs raw + this slice's sum of squares; pass 2: normalise in shared memory
         for (int s = 0; s < p.B; ++s) {
             const bf16* row = src + (size_t)s * K;
@@ -361,10 +362,11 @@ __device__ void stage_x(const MegaParams& p, const Cons& c, const Shared& sh, co
 #pragma unroll
             for (int j = 0; j < NCW; ++j) tot += part[s * NCW + j];
             const float rs = rsqrtf(tot / (float)K + p.eps);
-            for (int ch = c0 + c.lane; ch < c1; ch += 32) {
+            int jn = 0;
+            for (int ch = c0 + c.lane; ch < c1; ch += 32, ++jn) {
                 uint4* xp = reinterpret_cast<uint4*>(sh.xs + (size_t)s * xpitch + ch * 8);
                 const uint4 u = *xp;
-                const uint4 wv = *reinterpret_cast<const uint4*>(norm_w + ch * 8);
+                const uint4 wv = jn < 2 ? nw[jn] : *reinterpret_cast<const uint4*>(norm_w + ch * 8);
                 const uint32_t uw[4] = {u.x, u.y, u.z, u.w}, ww[4] = {wv.x, wv.y, wv.z, wv.w};
                 uint32_t ov[4];
 #pragma unroll
@@ -653,29 +655,40 @@ __device__ void consumer_attn(const MegaParams& p, Cons& c, const Shared& sh, in
                     p.part_o[(pbase + r) * D + d] = acc;
                     if (d == 0) { p.part_ml[(pbase + r) * 2] = M; p.part_ml[(pbase + r) * 2 + 1] = L; }
                 }
-                __threadfence();
                 consumer_sync();
                 if (c.tid == 0) {
-                    const int prev = atomicAdd(&p.pair_cnt[b * p.Hkv + g], 1);
+                    int prev;   // acq_rel at gpu scope: publishes this item's partials, and the last arriver sees all of them
+                    asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], 1;" : "=r"(prev) : "l"(&p.pair_cnt[b * p.Hkv + g]) : "memory");
                     flag[0] = (prev == pp.nitems - 1) ? 1 : 0;
                     if (flag[0]) p.pair_cnt[b * p.Hkv + g] = 0;  // re-armed for the next layer
                 }
                 consumer_sync();
                 if (flag[0]) {  // last item of this (stream, kv head) to finish: merge the items in index order
-                    __threadfence();
+                    // (m, l) of every item first, in parallel, into shared memory (the accumulators `so` are free now);
+                    // then each thread folds the items' float4 partials with the loads of several items in flight
                     const size_t pb = ((size_t)b * p.Hkv + g) * MG_MAX_ITEMS * 8;
+                    float* sm_m = so;                       // [MG_MAX_ITEMS][8]
+                    float* sm_l = so + MG_MAX_ITEMS * 8;    // [MG_MAX_ITEMS][8]
+                    for (int i = c.tid; i < pp.nitems * 8; i += NCT) {
+                        const float2 ml = __ldcg(reinterpret_cast<const float2*>(p.part_ml + (pb + i) * 2));
+                        sm_m[i] = ml.x;
+                        sm_l[i] = ml.y;
+                    }
+                    consumer_sync();
                     for (int i = c.tid; i < Gq * (D / 4); i += NCT) {
                         const int r = i / (D / 4), d4 = (i % (D / 4)) * 4;
                         float M = -INFINITY;
-                        for (int q = 0; q < pp.nitems; ++q) M = fmaxf(M, ld_cg_f32(p.part_ml + (pb + (size_t)q * 8 + r) * 2));
+                        for (int q = 0; q < pp.nitems; ++q) M = fmaxf(M, sm_m[q * 8 + r]);
                         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
                         float L = 0.f;
+                        const float* src = p.part_o + (pb + r) * D + d4;
+#pragma unroll 4
                         for (int q = 0; q < pp.nitems; ++q) {
-                            const float mq = ld_cg_f32(p.part_ml + (pb + (size_t)q * 8 + r) * 2);
+                            const float mq = sm_m[q * 8 + r];
                             const float f = (mq == -INFINITY) ? 0.f : exp2f((mq - M) * p.scale_log2);
-                            const float4 v = ld_cg_f32x4(p.part_o + (pb + (size_t)q * 8 + r) * D + d4);
+                            const float4 v = __ldcg(reinterpret_cast<const float4*>(src + (size_t)q * 8 * D));
                             acc.x += f * v.x; acc.y += f * v.y; acc.z += f * v.z; acc.w += f * v.w;
-                            L += f * ld_cg_f32(p.part_ml + (pb + (size_t)q * 8 + r) * 2 + 1);
+                            L += f * sm_l[q * 8 + r];
                         }
                         const float inv = L > 0.f ? 1.f / L : 0.f;
                         uint2 o;
