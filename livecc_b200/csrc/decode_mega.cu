@@ -58,6 +58,7 @@ constexpr int SC_VNEW = 4608;           // bf16 [128]
 constexpr int SC_SML = 4864;            // float [9][8][2]                                 (576)
 constexpr int SC_SO = 5632;             // float [9][8][128]                               (36864) -> 42496
 constexpr int SC_FLAG = 42496;          // int [4]
+constexpr int SC_FAC = 42512;           // float [MG_MAX_ITEMS * 8] merge weights (2048 B) -> 44560
 
 __device__ __forceinline__ uint32_t ld_cg_u32(const void* p) {
     uint32_t v;
@@ -73,11 +74,6 @@ __device__ __forceinline__ uint4 ld_cg_u128(const void* p) {
     uint4 r;
     asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
-}
-__device__ __forceinline__ float ld_cg_f32(const float* p) {
-    float v;
-    asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p));
-    return v;
 }
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
     unsigned v;
@@ -131,6 +127,7 @@ struct Shared {
     int* s_active;      // [8]
     unsigned* released; // [ngroup] tiles of each group slot released so far (see wait_tile)
     unsigned* prog;     // [NPW] groups walked so far by each TMA producer (paces the L2 prefetcher)
+    float2* rope;       // [8 streams][64] (cos, sin) of this step's position, already rounded to bf16 (mq2vl.py:201)
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -276,7 +273,12 @@ struct Cons {
     unsigned tile;  // tile index of the first tile of the current phase for this CTA (a multiple of GT)
     int* err;
     int warp, lane, tid;
+    unsigned long long* trace;  // this CTA's 64 stamps or null
+    int tr_n;
 };
+__device__ __forceinline__ void trace_stamp(Cons& c) {
+    if (c.trace && c.tid == 0 && c.tr_n < 64) c.trace[c.tr_n++] = globaltimer_ns();
+}
 
 // The GT tiles of a ring group are in general consumed by DIFFERENT warps, and so are consecutive rounds of a group. A
 // parity wait alone is then ambiguous: a warp that asks for round r while the group's barrier is still in round r-1
@@ -482,13 +484,21 @@ __device__ void consumer_gemv(const MegaParams& p, Cons& c, const Shared& sh, in
     c.tile += (unsigned)biter * KC;
 }
 
-__device__ __forceinline__ void rope_pair(const bf16* src, bf16* dst, int j, float pos, const float* inv_freq) {
-    // one (j, j+64) pair; torch bf16 semantics (each product and the sum rounded to bf16), as attention.cu::rope1d_row
-    const float ang = __fmul_rn(pos, inv_freq[j]);
-    const float cs = rbf(cosf(ang)), sn = rbf(sinf(ang));
-    const float x1 = ld_cg_bf16(src + j), x2 = ld_cg_bf16(src + j + 64);  // written by other CTAs in this launch: L2, not L1
-    dst[j] = f2bf(rbf(rbf(x1 * cs) + rbf(-x2 * sn)));
-    dst[j + 64] = f2bf(rbf(rbf(x2 * cs) + rbf(x1 * sn)));
+// Rotates 8 consecutive (j, j+64) pairs of one head: two 16-byte loads from L2 (the qkv vector was written by other CTAs
+// in this launch), torch bf16 semantics (each product and the sum rounded to bf16, as attention.cu::rope1d_row).
+__device__ __forceinline__ void rope_chunk(const bf16* src, bf16* dst, int j0, const float2* tab) {
+    const uint4 lo = ld_cg_u128(src + j0), hi = ld_cg_u128(src + j0 + 64);
+    const uint32_t lw[4] = {lo.x, lo.y, lo.z, lo.w}, hw[4] = {hi.x, hi.y, hi.z, hi.w};
+    uint32_t ol[4], oh[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 x1 = unpack_bf16x2(lw[i]), x2 = unpack_bf16x2(hw[i]);
+        const float2 c0 = tab[j0 + 2 * i], c1 = tab[j0 + 2 * i + 1];
+        ol[i] = pack_bf16x2(rbf(rbf(x1.x * c0.x) + rbf(-x2.x * c0.y)), rbf(rbf(x1.y * c1.x) + rbf(-x2.y * c1.y)));
+        oh[i] = pack_bf16x2(rbf(rbf(x2.x * c0.x) + rbf(x1.x * c0.y)), rbf(rbf(x2.y * c1.x) + rbf(x1.y * c1.y)));
+    }
+    *reinterpret_cast<uint4*>(dst + j0) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+    *reinterpret_cast<uint4*>(dst + j0 + 64) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
 }
 
 // Attention phase: this CTA's items.
@@ -507,7 +517,6 @@ __device__ void consumer_attn(const MegaParams& p, Cons& c, const Shared& sh, in
         if (!sh.s_active[b]) continue;
         const int T = sh.s_T[b];
         const PairPlan pp = plan_pair(T);
-        const float pos = (float)sh.s_pos[b];
         const bf16* qkv = p.qkv + (size_t)b * p.qkv_dim;
         for (int g = 0; g < p.Hkv; ++g, gi += pp.nitems) {
             const int it0 = (int)(((unsigned)cta + (unsigned)G - (rr + gi) % (unsigned)G) % (unsigned)G);
@@ -516,20 +525,25 @@ __device__ void consumer_attn(const MegaParams& p, Cons& c, const Shared& sh, in
                 const bool last_item = it == pp.nitems - 1;
                 // ---- stage the rotated q heads of this KV group (rows >= Gq zero); the owner of the pair's last
                 //      item also rotates + appends the new token's k and v ----
-                for (int i = c.tid; i < 16 * 64; i += NCT) {
-                    const int r = i >> 6, j = i & 63;
-                    if (r < Gq) rope_pair(qkv + (size_t)(g * Gq + r) * D, qs + r * QPITCH, j, pos, p.inv_freq);
-                    else { qs[r * QPITCH + j] = f2bf(0.f); qs[r * QPITCH + j + 64] = f2bf(0.f); }
+                const float2* tab = sh.rope + b * 64;
+                if (c.tid < 128) {   // 16 rows x 8 chunks of 8 pairs
+                    const int r = c.tid >> 3, j0 = (c.tid & 7) * 8;
+                    if (r < Gq) rope_chunk(qkv + (size_t)(g * Gq + r) * D, qs + r * QPITCH, j0, tab);
+                    else {
+                        *reinterpret_cast<uint4*>(qs + r * QPITCH + j0) = make_uint4(0u, 0u, 0u, 0u);
+                        *reinterpret_cast<uint4*>(qs + r * QPITCH + j0 + 64) = make_uint4(0u, 0u, 0u, 0u);
+                    }
                 }
                 if (last_item) {
                     const int page = p.st[b].page_table[T >> 6], slot = T & 63;
                     const size_t base = (size_t)layer * p.layer_stride + (((size_t)page * p.Hkv + g) * 64 + slot) * D;
-                    if (c.tid < 64) {
-                        rope_pair(qkv + (size_t)(p.Hq + g) * D, knew, c.tid, pos, p.inv_freq);
-                        p.k_pool[base + c.tid] = knew[c.tid];
-                        p.k_pool[base + c.tid + 64] = knew[c.tid + 64];
-                    } else if (c.tid < 80) {
-                        const int ch = c.tid - 64;
+                    if (c.tid >= 128 && c.tid < 136) {
+                        const int j0 = (c.tid - 128) * 8;
+                        rope_chunk(qkv + (size_t)(p.Hq + g) * D, knew, j0, tab);
+                        *reinterpret_cast<uint4*>(p.k_pool + base + j0) = *reinterpret_cast<const uint4*>(knew + j0);
+                        *reinterpret_cast<uint4*>(p.k_pool + base + j0 + 64) = *reinterpret_cast<const uint4*>(knew + j0 + 64);
+                    } else if (c.tid >= 136 && c.tid < 152) {
+                        const int ch = c.tid - 136;
                         const uint4 v = ld_cg_u128(qkv + (size_t)(p.Hq + p.Hkv + g) * D + ch * 8);
                         *reinterpret_cast<uint4*>(vnew + ch * 8) = v;
                         *reinterpret_cast<uint4*>(p.v_pool + base + ch * 8) = v;
@@ -540,6 +554,7 @@ __device__ void consumer_attn(const MegaParams& p, Cons& c, const Shared& sh, in
                     }
                 }
                 consumer_sync();
+                if (p.phase_mask & 32) trace_stamp(c);   // deep trace: staged
                 // ---- per warp: flash pass over its 32-token units ----
                 uint32_t qf[D / 16][4];
 #pragma unroll
@@ -620,7 +635,8 @@ __device__ void consumer_attn(const MegaParams& p, Cons& c, const Shared& sh, in
                 l[0] += __shfl_xor_sync(0xffffffffu, l[0], 1);
                 l[0] += __shfl_xor_sync(0xffffffffu, l[0], 2);
                 // ---- merge the warps (+ the new token) of this item through shared memory; rows g4 < 8 only ----
-                consumer_sync();  // everybody is done with qs (SC_SO overlaps nothing, but SC_QS is re-staged next item)
+                consumer_sync();  // everybody is done with qs
+                if (p.phase_mask & 32) trace_stamp(c);   // deep trace: units done (SC_SO overlaps nothing, but SC_QS is re-staged next item)
                 {
                     float* dst = so + ((size_t)c.warp * 8 + g4) * D + 2 * t4;
 #pragma unroll
@@ -641,21 +657,29 @@ __device__ void consumer_attn(const MegaParams& p, Cons& c, const Shared& sh, in
                 consumer_sync();
                 const int nsrc = last_item ? 9 : 8;
                 const size_t pbase = (((size_t)b * p.Hkv + g) * MG_MAX_ITEMS + it) * 8;
-                for (int i = c.tid; i < Gq * D; i += NCT) {
-                    const int r = i / D, d = i % D;
+                float* fac = reinterpret_cast<float*>(sh.scratch + SC_FAC);   // [9][8] weights of the contributors
+                if (c.tid < nsrc * 8) {
+                    const int r = c.tid & 7;
                     float M = -INFINITY;
                     for (int w = 0; w < nsrc; ++w) M = fmaxf(M, sml[(w * 8 + r) * 2]);
-                    float acc = 0.f, L = 0.f;
-                    for (int w = 0; w < nsrc; ++w) {
-                        const float mw = sml[(w * 8 + r) * 2];
-                        const float f = (mw == -INFINITY) ? 0.f : exp2f((mw - M) * p.scale_log2);
-                        acc += f * so[((size_t)w * 8 + r) * D + d];
-                        L += f * sml[(w * 8 + r) * 2 + 1];
-                    }
-                    p.part_o[(pbase + r) * D + d] = acc;
-                    if (d == 0) { p.part_ml[(pbase + r) * 2] = M; p.part_ml[(pbase + r) * 2 + 1] = L; }
+                    const float mw = sml[c.tid * 2];
+                    fac[c.tid] = (mw == -INFINITY) ? 0.f : exp2f((mw - M) * p.scale_log2);
+                    if (c.tid < 8 && r < Gq) p.part_ml[(pbase + r) * 2] = M;
                 }
                 consumer_sync();
+                for (int i = c.tid; i < Gq * D; i += NCT) {
+                    const int r = i / D, d = i % D;
+                    float acc = 0.f;
+                    for (int w = 0; w < nsrc; ++w) acc += fac[w * 8 + r] * so[((size_t)w * 8 + r) * D + d];
+                    p.part_o[(pbase + r) * D + d] = acc;
+                    if (d == 0) {
+                        float L = 0.f;
+                        for (int w = 0; w < nsrc; ++w) L += fac[w * 8 + r] * sml[(w * 8 + r) * 2 + 1];
+                        p.part_ml[(pbase + r) * 2 + 1] = L;
+                    }
+                }
+                consumer_sync();
+                if (p.phase_mask & 32) trace_stamp(c);   // deep trace: partial written
                 if (c.tid == 0) {
                     int prev;   // acq_rel at gpu scope: publishes this item's partials, and the last arriver sees all of them
                     asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], 1;" : "=r"(prev) : "l"(&p.pair_cnt[b * p.Hkv + g]) : "memory");
@@ -663,6 +687,7 @@ __device__ void consumer_attn(const MegaParams& p, Cons& c, const Shared& sh, in
                     if (flag[0]) p.pair_cnt[b * p.Hkv + g] = 0;  // re-armed for the next layer
                 }
                 consumer_sync();
+                if (p.phase_mask & 32) trace_stamp(c);   // deep trace: counted
                 if (flag[0]) {  // last item of this (stream, kv head) to finish: merge the items in index order
                     // (m, l) of every item first, in parallel, into shared memory (the accumulators `so` are free now);
                     // then each thread folds the items' float4 partials with the loads of several items in flight
@@ -675,17 +700,23 @@ __device__ void consumer_attn(const MegaParams& p, Cons& c, const Shared& sh, in
                         sm_l[i] = ml.y;
                     }
                     consumer_sync();
-                    for (int i = c.tid; i < Gq * (D / 4); i += NCT) {
-                        const int r = i / (D / 4), d4 = (i % (D / 4)) * 4;
+                    float* wq = reinterpret_cast<float*>(sh.scratch + SC_FAC);   // [nitems][8] weight of item q for row r
+                    for (int i = c.tid; i < pp.nitems * 8; i += NCT) {
+                        const int r = i & 7;
                         float M = -INFINITY;
                         for (int q = 0; q < pp.nitems; ++q) M = fmaxf(M, sm_m[q * 8 + r]);
+                        const float mq = sm_m[i];
+                        wq[i] = (mq == -INFINITY) ? 0.f : exp2f((mq - M) * p.scale_log2);
+                    }
+                    consumer_sync();
+                    for (int i = c.tid; i < Gq * (D / 4); i += NCT) {
+                        const int r = i / (D / 4), d4 = (i % (D / 4)) * 4;
                         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
                         float L = 0.f;
                         const float* src = p.part_o + (pb + r) * D + d4;
-#pragma unroll 4
+#pragma unroll 8
                         for (int q = 0; q < pp.nitems; ++q) {
-                            const float mq = sm_m[q * 8 + r];
-                            const float f = (mq == -INFINITY) ? 0.f : exp2f((mq - M) * p.scale_log2);
+                            const float f = wq[q * 8 + r];
                             const float4 v = __ldcg(reinterpret_cast<const float4*>(src + (size_t)q * 8 * D));
                             acc.x += f * v.x; acc.y += f * v.y; acc.z += f * v.z; acc.w += f * v.w;
                             L += f * sm_l[q * 8 + r];
@@ -725,6 +756,7 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_cons
     sh.s_active = sh.s_pos + 8;
     sh.released = reinterpret_cast<unsigned*>(sh.s_active + 8);
     sh.prog = sh.released + MG_MAX_SLOTS;
+    sh.rope = reinterpret_cast<float2*>(sh.prog + 8);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cta = blockIdx.x, G = gridDim.x;
@@ -746,6 +778,13 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_cons
     int any = 0;
     for (int b = 0; b < p.B; ++b) any |= sh.s_active[b];
     if (!any) return;  // every stream is finished: the step is a no-op (graph replay after EOS)
+    // The position of the new token is fixed for the whole step: its 64 (cos, sin) pairs per stream are computed once
+    // (fp32 angle, cos/sin rounded to bf16 as the reference does) instead of by every attention item of every layer.
+    for (int i = threadIdx.x; i < p.B * 64; i += blockDim.x) {
+        const float ang = __fmul_rn((float)sh.s_pos[i >> 6], p.inv_freq[i & 63]);
+        sh.rope[i] = make_float2(rbf(cosf(ang)), rbf(sinf(ang)));
+    }
+    __syncthreads();
 
     const bool ph_qkv = p.phase_mask & 1, ph_attn = p.phase_mask & 2, ph_o = p.phase_mask & 4, ph_gu = p.phase_mask & 8,
                ph_down = p.phase_mask & 16;
@@ -777,13 +816,11 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_cons
         return;
     }
     // ================================= consumers =================================
-    Cons c{sh.ring, sh.full, sh.empty, sh.released, p.ngroup, 0u, p.err, warp, lane, (int)threadIdx.x};
+    Cons c{sh.ring, sh.full, sh.empty, sh.released, p.ngroup, 0u, p.err, warp, lane, (int)threadIdx.x,
+           p.trace ? p.trace + (size_t)cta * 64 : nullptr, 0};
     unsigned epoch = 0;
-    int tr_n = 0;   // optional timeline (LIVECC_B200_MEGA_TRACE=1): globaltimer stamps of consumer thread 0, 64 per CTA
-#define MG_TRACE()                                                                                       \
-    do {                                                                                                 \
-        if (p.trace && c.tid == 0 && tr_n < 64) p.trace[(size_t)cta * 64 + tr_n++] = globaltimer_ns();  \
-    } while (0)
+    // optional timeline (LIVECC_B200_MEGA_TRACE=1): globaltimer stamps of consumer thread 0, 64 per CTA
+#define MG_TRACE() trace_stamp(c)
     MG_TRACE();
     for (int l = p.layer_begin; l < p.layer_end; ++l) {
         const MegaLayer& ly = p.layers[l];
@@ -841,7 +878,7 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_cons
 int mega_smem_bytes(int H, int B, int* ngroup_out) {
     const int bpad = B <= 1 ? 1 : (B <= 2 ? 2 : (B <= 4 ? 4 : 8));
     const int xs = ((bpad * (H + 8) * 2) + 127) & ~127;
-    const int fixed = 1024 /*align*/ + xs + SCRATCH + MG_MAX_SLOTS * 16 + 384;  // barriers, stream scalars, released[], prog[]
+    const int fixed = 1024 /*align*/ + xs + SCRATCH + MG_MAX_SLOTS * 16 + 384 + 4096;  // barriers, scalars, released[], prog[], rope table
     int ngroup = (232448 - fixed) / GROUP;
     if (ngroup > MG_MAX_SLOTS) ngroup = MG_MAX_SLOTS;
     // A multiple of the producer count: group slot s is then always armed by producer s % NPW, so two rounds of one slot
