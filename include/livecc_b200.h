@@ -263,7 +263,8 @@ int lcc_decode_steps(lcc_model* m, const lcc_stream_state* st, int n_steps, int 
  * REF/demo/app.py:178): n_steps x (one persistent kernel = every decoder layer + lm_head for all n_streams <= 8 streams,
  * each weight byte read once per step, then one token selection per stream). states[b] must have been prefilled with
  * slot = b and share one page pool. A stream's ids and logits are bit-identical to decoding it alone (same kernel,
- * same reduction order). lcc_decode_steps routes through this with n_streams = 1 unless LIVECC_B200_MEGA=0. */
+ * same reduction order). lcc_decode_steps (one stream) uses the per-op kernels unless LIVECC_B200_MEGA=1: they are ~5 % faster
+ * for a single stream (measured); with 2..8 streams the persistent kernel reads every weight byte once per step for all. */
 int lcc_decode_batch(lcc_model* m, const lcc_stream_state* states, int n_streams, int n_steps, const lcc_sampling* sp,
                      lcc_stream_t stream);
 /* Test hook: run layers [layer_begin, layer_end) and the phases in phase_mask (1 qkv, 2 attention, 4 o_proj,

@@ -28,7 +28,7 @@ struct lcc_model {
     int cap_patches = 0, cap_tokens = 0;
     int mega_lookahead = 0;  // LIVECC_B200_MEGA_LOOKAHEAD: 16 KB groups per CTA an L2 prefetcher thread runs ahead of the ring (measured slower: off)
     bool mega_trace = false;  // LIVECC_B200_MEGA_TRACE=1: per-CTA phase timeline in the workspace (LCC_WS_MEGA_TRACE)
-    bool use_mega = true;   // persistent decode-step kernel (decode_mega.cu); LIVECC_B200_MEGA=0 selects the per-op kernels
+    bool use_mega = false;  // one-stream decode through the persistent kernel (LIVECC_B200_MEGA=1); batched decode always uses it
     bool mega_ok = false;   // geometry supported by the persistent kernel and its tables are uploaded
     bool fuse_attn_oproj = false;  // LIVECC_B200_FUSE=1: one launch for decode attention + o_proj (flag-synchronised roles)
     bool use_pdl = false;  // programmatic dependent launch between the decode-step kernels (LIVECC_B200_PDL=1 enables)
@@ -162,7 +162,10 @@ lcc_model* lcc_model_create(lcc_ctx* ctx, const lcc_model_config* cfg, const lcc
     m->w.vit_blocks = m->vit_blocks.data();
     m->w.layers = m->layers.data();
     const char* mega_env = getenv("LIVECC_B200_MEGA");
-    m->use_mega = !(mega_env && mega_env[0] == '0');
+    // Measured on B200 (profiles/r02_decode_paths.md): for ONE stream the per-op kernels are 5 % faster than the persistent
+    // kernel (3.21 vs 3.37 ms/step in situ), so lcc_decode_steps keeps them by default; lcc_decode_batch (2..8 streams) is
+    // always the persistent kernel.
+    m->use_mega = mega_env && mega_env[0] == '1';
     if (const char* te = getenv("LIVECC_B200_MEGA_TRACE")) m->mega_trace = te[0] == '1';
     if (const char* la = getenv("LIVECC_B200_MEGA_LOOKAHEAD")) m->mega_lookahead = atoi(la) < 0 ? 0 : atoi(la);
     const char* fuse_env = getenv("LIVECC_B200_FUSE");

@@ -29,14 +29,22 @@ def _turn_inputs(proc, turn, frames, seed, hw=(112, 112)):
     return proc(text=text, videos=[clip], return_attention_mask=False)
 
 
-@pytest.fixture(scope="module")
-def small():
+def _mega_engine(cfg, sd):
+    """Engine whose one-stream decode also runs the persistent kernel, so that "alone" and "batched" are the same code."""
     from livecc_b200.engine import LiveCCB200ForConditionalGeneration
 
+    os.environ["LIVECC_B200_MEGA"] = "1"
+    try:
+        return LiveCCB200ForConditionalGeneration.from_state_dict(cfg, sd, DEV)
+    finally:
+        del os.environ["LIVECC_B200_MEGA"]
+
+
+@pytest.fixture(scope="module")
+def small():
     cfg = LiveCCConfig.small()
     sd = synthetic_state_dict(cfg, dtype=torch.bfloat16, device=DEV, gen_device=DEV)
-    eng = LiveCCB200ForConditionalGeneration.from_state_dict(cfg, sd, DEV)
-    return cfg, sd, eng
+    return cfg, sd, _mega_engine(cfg, sd)
 
 
 @pytest.fixture(scope="module")
@@ -44,12 +52,10 @@ def wide():
     """LiveCC-7B widths (hidden 3584, inter 18944, vocab 152064, 28:4 heads) with 2 decoder layers and a 1-block ViT: the
     tile counts, K splits and row-block rotation of the real model at a fraction of the memory."""
     from livecc_b200.config import TextConfig, VisionConfig
-    from livecc_b200.engine import LiveCCB200ForConditionalGeneration
 
     cfg = LiveCCConfig(text_config=TextConfig(num_hidden_layers=2), vision_config=VisionConfig(depth=1), name="livecc-7b-wide-l2")
     sd = synthetic_state_dict(cfg, dtype=torch.bfloat16, device=DEV, gen_device=DEV)
-    eng = LiveCCB200ForConditionalGeneration.from_state_dict(cfg, sd, DEV)
-    return cfg, sd, eng
+    return cfg, sd, _mega_engine(cfg, sd)
 
 
 def _ws(eng, off, rows, cols, dtype=torch.bfloat16):
@@ -226,21 +232,18 @@ def test_batched_decode_equals_sequential(which, specs, request):
 
 
 def test_persistent_kernel_vs_per_op_path(small):
-    """Same stream through the persistent kernel (default) and through the per-op kernels (LIVECC_B200_MEGA=0):
-    logits within bf16 tolerance, cache lengths equal."""
+    """Same stream through the persistent kernel (`small` engines are built with LIVECC_B200_MEGA=1; every batched step
+    uses it) and through the per-op decode kernels (the one-stream default): logits within bf16 tolerance, cache lengths
+    equal."""
     from livecc_b200.engine import LiveCCB200ForConditionalGeneration
 
-    cfg, sd, eng = small
-    os.environ["LIVECC_B200_MEGA"] = "0"
-    try:
-        legacy = LiveCCB200ForConditionalGeneration.from_state_dict(cfg, sd, DEV)
-    finally:
-        del os.environ["LIVECC_B200_MEGA"]
+    cfg, sd, mega = small
+    perop = LiveCCB200ForConditionalGeneration.from_state_dict(cfg, sd, DEV)
     proc = StubProcessor(cfg)
     inp = _turn_inputs(proc, 0, 6, 77).to(DEV)
-    a = eng.generate(**inp, repetition_penalty=1.05, max_new_tokens=6, output_logits=True)
+    a = mega.generate(**inp, repetition_penalty=1.05, max_new_tokens=6, output_logits=True)
     gen = a.sequences[0, inp.input_ids.shape[1]:].tolist()
-    b = legacy.generate(**inp, repetition_penalty=1.05, max_new_tokens=len(gen), output_logits=True, _forced_ids=gen)
+    b = perop.generate(**inp, repetition_penalty=1.05, max_new_tokens=len(gen), output_logits=True, _forced_ids=gen)
     assert a.past_key_values.get_seq_length() == b.past_key_values.get_seq_length()
     worst = max((x - y).abs().max().item() for x, y in zip(a.logits, b.logits))
     assert worst < 0.06, worst
