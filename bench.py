@@ -224,8 +224,35 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def time_dominant_kernel(eng, chunks_dev, max_new, iters=20):
-    """The dominant kernel = decode_mega_kernel: one launch = one decode step of one stream (28 layers + lm_head).
+def time_gateup_kernel(eng, iters=5):
+    """decode gate/up GEMV (gemv_rows_kernel<2,true,SWIGLU>): fused RMSNorm + [2I,H] weight stream + SwiGLU.
+    Algorithmic bytes/launch = 2I*H*2 (weights) + H*2 (x) + H*2 (norm w) + I*2 (out). Cycles through all layers
+    so every launch streams a different 271 MB (7B) weight, i.e. inputs >> L2."""
+    t = eng.config.text_config
+    H, I = t.hidden_size, t.intermediate_size
+    x = torch.randn(H, device=eng.device).to(torch.bfloat16)
+    stream = torch.cuda.current_stream()
+    for lw in eng.weights.layers:  # warm-up
+        eng.ctx.gemv_norm_swiglu(lw.gate_up_w, x, lw.ln2_w, t.rms_norm_eps)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 0
+    e0.record(stream)
+    for _ in range(iters):
+        for lw in eng.weights.layers:
+            eng.ctx.gemv_norm_swiglu(lw.gate_up_w, x, lw.ln2_w, t.rms_norm_eps)
+            n += 1
+    e1.record(stream)
+    torch.cuda.synchronize()
+    sec = e0.elapsed_time(e1) / 1e3 / n
+    nbytes = 2 * I * H * 2 + 2 * H * 2 + I * 2
+    return nbytes, sec
+
+
+
+def time_persistent_kernel(eng, chunks_dev, max_new, iters=20):
+    """The persistent decode kernel (decode_mega_kernel; what every batched step runs): one launch = one decode step of one
+    stream (28 layers + lm_head).
     Timed alone with CUDA events on its launch stream (the sub-range hook of the C ABI launches exactly the kernel the
     CUDA-graph step contains, without the token selection, so the stream state does not advance and every launch
     re-reads the same bytes): algorithmic bytes per launch = all decoder weights + lm_head + the stream's KV at the
@@ -525,14 +552,14 @@ def main():
     lat_sorted = sorted(lat)
     p50 = lat_sorted[len(lat_sorted) // 2] * 1e3
     peak, peak_src = load_peaks()
-    kbytes, ksec, k_kv, k_err = time_dominant_kernel(eng, chunks_dev, args.max_new_tokens)
+    kbytes, ksec = time_gateup_kernel(eng)
+    pk_bytes, pk_sec, pk_kv, pk_err = time_persistent_kernel(eng, chunks_dev, args.max_new_tokens)
     traffic, traffic_src = None, None
     try:  # dram bytes of the same kernel from the committed `ncu --set full` capture (7B dims only)
         if args.model == "7b":
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r02_mega_ncu.json")))
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_gateup_ncu.json")))
             traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
-            traffic_src = ("static: one `ncu --set full` capture of this kernel at kv_len %d (profiles/r02_mega_ncu.json), "
-                           "not measured in this run" % tr.get("kv_len", -1))
+            traffic_src = "static: one `ncu --set full` capture of this kernel (profiles/r01_gateup_ncu.json), not measured in this run"
     except Exception:
         traffic = None
     t = cfg.text_config
@@ -546,13 +573,17 @@ def main():
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic (hash-filled checkpoint, synthetic frames and token ids)",
         "config": config, "frames_per_s": tot_frames / max_sec, "p50_frame_latency_ms": p50,
         "kv_len_end": kv_end, "clocks": clocks, "gpu_launches": int(gpu_launches),
-        "roofline": {"kernel": "decode_mega_kernel (persistent decode step: 28 layers + lm_head, 1 stream, kv_len %d)" % k_kv,
-                     "bound": "hbm", "native_error": k_err,
+        "roofline": {"kernel": "gemv_rows_kernel<2,NORM,SWIGLU> (decode gate/up + RMSNorm + SwiGLU; largest share of the decode step)",
+                     "bound": "hbm",
                      "achieved": kbytes / ksec / 1e9, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                      "frac": kbytes / ksec / 1e9 / peak, "traffic": traffic, "traffic_source": traffic_src,
                      "bytes_per_launch": kbytes,
                      "us_per_launch": ksec * 1e6},
     }
+    line["persistent_kernel"] = {"kernel": "decode_mega_kernel (one launch = 28 layers + lm_head; the batched-decode kernel), 1 stream, "
+                                           "kv_len %d" % pk_kv, "bytes_per_launch": pk_bytes, "us_per_launch": pk_sec * 1e6,
+                                 "achieved": pk_bytes / pk_sec / 1e9, "unit": "GB/s", "frac": pk_bytes / pk_sec / 1e9 / peak,
+                                 "native_error": pk_err}
     if e2e:
         tot_e_tok, tot_e_frames = allst[:, 3].sum().item(), allst[:, 4].sum().item()
         max_e_sec = allst[:, 5].max().item()

@@ -23,7 +23,7 @@ SHAPES = {
 }
 
 
-def run(name, iters=20, copies=8):
+def run(name, iters=20, copies=8, block_n=0):
     M, N, K, epi = SHAPES[name]
     g = torch.Generator(device="cuda").manual_seed(1)
     a = (torch.randn((M, K), device="cuda", generator=g) * 0.5).to(torch.bfloat16)
@@ -34,7 +34,7 @@ def run(name, iters=20, copies=8):
     out = torch.empty((M, n_out), dtype=torch.bfloat16, device="cuda")
     skw = torch.empty(8 * 384 * max(N, 8) * 4 // 4, dtype=torch.float32, device="cuda") if M <= 384 and N <= 8192 else None
     kw = dict(bias=bias if epi in (A.EPI_BIAS, A.EPI_BIAS_QUICKGELU, A.EPI_BIAS_GELU, A.EPI_BIAS_RESIDUAL) else None,
-              residual=res if epi in (A.EPI_RESIDUAL, A.EPI_BIAS_RESIDUAL) else None, epilogue=epi, splitk_ws=skw)
+              residual=res if epi in (A.EPI_RESIDUAL, A.EPI_BIAS_RESIDUAL) else None, epilogue=epi, splitk_ws=skw, block_n=block_n)
     for w in ws:
         ctx.gemm(a, w, out=out, **kw)
     torch.cuda.synchronize()
@@ -47,7 +47,7 @@ def run(name, iters=20, copies=8):
     us = e0.elapsed_time(e1) * 1e3 / iters
     flops = 2.0 * M * N * K
     wbytes = N * K * 2
-    print(f"{name:16s} M={M:5d} N={N:6d} K={K:6d}: {us:8.1f} us  {flops / us / 1e6:7.1f} TFLOP/s  weights {wbytes / us / 1e3:7.1f} GB/s",
+    print(f"{name:16s} bn={block_n:3d} M={M:5d} N={N:6d} K={K:6d}: {us:8.1f} us  {flops / us / 1e6:7.1f} TFLOP/s  weights {wbytes / us / 1e3:7.1f} GB/s",
           flush=True)
 
 
@@ -55,6 +55,10 @@ if __name__ == "__main__":
     case = os.environ.get("CASE")
     if case:
         run(case, iters=2, copies=2)
+    elif os.environ.get("SWEEP_BN"):
+        for n in SHAPES:
+            for bn in (0, 64, 128, 256):
+                run(n, block_n=bn)
     else:
         for n in SHAPES:
             run(n)
