@@ -331,7 +331,7 @@ __device__ __forceinline__ void grid_sync(const MegaParams& p, const Cons& c, un
 // xs[s][k] = (norm_w ? norm_w[k] * bf16(x[s][k] * rsqrt(mean(x^2) + eps)) : x[s][k]) for the B live streams.
 // The K range is cut into NCW fixed slices; warp w owns slice w of EVERY stream, and a stream's sum of squares is the
 // sum of its 8 slice sums in slice order — the same arithmetic whether the stream is alone or one of eight.
-__device__ void stage_x(const MegaParams& p, const Cons& c, const Shared& sh, const bf16* src, int K, const bf16* norm_w,
+__device__ void stage_x(const MegaParams& p, Cons& c, const Shared& sh, const bf16* src, int K, const bf16* norm_w,
                         int xpitch) {
     const int chunks = K >> 3;
     const int c0 = (int)((long long)chunks * c.warp / NCW), c1 = (int)((long long)chunks * (c.warp + 1) / NCW);
@@ -358,7 +358,9 @@ __device__ void stage_x(const MegaParams& p, const Cons& c, const Shared& sh, co
             sq = warp_sum(sq);
             if (c.lane == 0) part[s * NCW + c.warp] = sq;
         }
+        if (p.phase_mask & 64) trace_stamp(c);   // deep trace: activation loads done (thread 0's view)
         consumer_sync();
+        if (p.phase_mask & 64) trace_stamp(c);   // deep trace: all warps' slices summed
         for (int s = 0; s < p.B; ++s) {
             float tot = 0.f;
 #pragma unroll

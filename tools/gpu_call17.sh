@@ -9,3 +9,4 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:
 cat $O/rc.txt; tail -n 4 $O/tests_all.log | cut -c1-300; tail -2 $O/smoke.log | cut -c1-300
 cat $O/gemm_bn_sweep.txt | grep -v "^$" | head -40
 tail -c 2500 $O/bench_native.json
+MASK=$((1|64)) KV=8000 timeout 300 python tools/trace_attn.py > $O/trace_stage.txt 2>&1; tail -8 $O/trace_stage.txt | cut -c1-200

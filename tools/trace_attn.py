@@ -17,7 +17,7 @@ with torch.inference_mode():
     cache.scalars[_cabi.SC_FINISHED] = 0
 st = [cache.stream_state()]
 for _ in range(3):
-    eng._native.decode_mega_debug(st, 0, 4, 2 | 32, 0)
+    eng._native.decode_mega_debug(st, 0, 4, int(os.environ.get("MASK", str(2 | 32))), 0)
 torch.cuda.synchronize()
 off = eng._native.mega_trace_offset
 G = eng.ctx.num_sms
