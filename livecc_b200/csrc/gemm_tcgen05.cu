@@ -464,15 +464,18 @@ int gemm_bf16_tn(const GemmArgs& a, int num_sms, cudaStream_t stream) {
     if ((a.epi == EPI_BIAS || a.epi == EPI_BIAS_QUICKGELU || a.epi == EPI_BIAS_GELU ||
          a.epi == EPI_BIAS_RESIDUAL) && !a.bias) return -5;
     if (int r = try_splitk(a, num_sms, stream)) return r < 0 ? r : 0;
-    // Tile-shape heuristic. Narrow tiles re-read the A tile from L2 once per N tile and are L2->SM
-    // bandwidth bound (128x64 tiles need ~190 B/clk/SM; the L2 delivers ~40), so prefer the widest
-    // tile that still occupies at least half of the SMs.
+    // Tile-shape heuristic, fitted to the B200 sweep in profiles/r02_gemm_shapes.md: 64-wide tiles are L2->SM bound and
+    // never win; between 128 and 256 the cost is (waves over the SMs) x (fixed fill/epilogue + mainloop ~ 128 + block_n),
+    // ties go to the narrower tile (more CTAs overlap epilogue and mainloop). Examples: ViT fc1 (1024, 5120): 256 -> 2 waves
+    // x 384 = 768, 128 -> 3 x 256 = 768 -> 128 (28.0 vs 31.4 us); prefill gate/up (281, 37888): 256 (82 vs 102 us).
     int block_n = a.block_n;
     if (block_n == 0) {
-        const int m_tiles = (a.M + BLOCK_M - 1) / BLOCK_M;
-        if (m_tiles * ((a.N + 255) / 256) * 2 >= num_sms) block_n = 256;
-        else if (m_tiles * ((a.N + 127) / 128) * 2 >= num_sms) block_n = 128;
-        else block_n = (a.N >= 1024) ? 128 : 64;
+        const long long m_tiles = (a.M + BLOCK_M - 1) / BLOCK_M;
+        auto cost = [&](int bn) {
+            const long long tiles = m_tiles * ((a.N + bn - 1) / bn);
+            return ((tiles + num_sms - 1) / num_sms) * (long long)(128 + bn);
+        };
+        block_n = cost(128) <= cost(256) ? 128 : 256;
         if (a.N <= 64) block_n = 64;
     }
     switch (block_n) {
