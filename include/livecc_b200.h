@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define LCC_ABI_VERSION 7
+#define LCC_ABI_VERSION 8
 #define LCC_PAGE_SIZE 64
 
 typedef struct lcc_ctx lcc_ctx;
@@ -271,6 +271,24 @@ int lcc_decode_batch(lcc_model* m, const lcc_stream_state* states, int n_streams
  * 8 gate/up, 16 down_proj) of the persistent decode kernel, optionally the lm_head, without token selection. */
 int lcc_decode_mega_debug(lcc_model* m, const lcc_stream_state* states, int n_streams, int layer_begin, int layer_end,
                           int phase_mask, int do_head, lcc_stream_t stream);
+
+/* ---- frame ingest ------------------------------------------------------------------------------
+ * transforms.functional.resize(clip, [H, W], interpolation=BICUBIC, antialias=True) on a uint8 TCHW clip
+ * (REF/livecc-utils/src/livecc_utils/video_process_patch.py:101-106 and :150-155), bit-identical to torchvision 0.26 /
+ * ATen's CPU kernel: float32 width pass, float32 height pass, clamp, round half to even, uint8. */
+/* Window/weight table of one axis (ATen _compute_indices_min_size_weights_aa<float>, Keys cubic a = -0.5), host only:
+ * lcc_resize_aa_taps = max window length; xmin/xsize: int32[out_size]; weights: float[taps][out_size] (tap-major). */
+int lcc_resize_aa_taps(int in_size, int out_size);
+int lcc_resize_aa_table(int in_size, int out_size, int32_t* xmin, int32_t* xsize, float* weights);
+/* A plan owns the device copy of both axes' tables for (h, w) -> (H, W). rows_per_cta: 0 = choose (tuning hook).
+ * NULL (and lcc_last_error) when a window does not fit in shared memory or a size is out of range. */
+typedef struct lcc_resize_plan lcc_resize_plan;
+lcc_resize_plan* lcc_resize_plan_create(lcc_ctx* ctx, int h, int w, int H, int W, int rows_per_cta);
+void lcc_resize_plan_destroy(lcc_resize_plan* plan);
+int lcc_resize_plan_info(const lcc_resize_plan* plan, int* rows_per_cta, int* max_rows, int64_t* smem_bytes);
+/* src: device uint8 [planes, h, w] (planes = T*C), dst: device uint8 [planes, H, W]. One kernel. */
+int lcc_resize_bicubic_aa_u8(lcc_ctx* ctx, const lcc_resize_plan* plan, const uint8_t* src, int planes, uint8_t* dst,
+                             lcc_stream_t stream);
 
 /* Debug/parity hooks: byte offsets of buffers inside the bound workspace. */
 #define LCC_WS_PREFILL_HIDDEN 0 /* bf16 [S, hidden] residual stream of the last prefill */

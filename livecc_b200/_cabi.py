@@ -13,7 +13,7 @@ PKG_DIR = Path(__file__).resolve().parent
 LIB_PATH = PKG_DIR / "liblivecc_sm100a.so"
 HEADER_PATH = PKG_DIR.parent / "include" / "livecc_b200.h"
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 PAGE_SIZE = 64
 
 # epilogue codes (LCC_EPI_*)
@@ -102,6 +102,12 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     lib.lcc_workspace_bytes.argtypes = [C.c_void_p, C.c_int, C.c_int]
     lib.lcc_ws_offset.restype = C.c_size_t
     lib.lcc_ws_offset.argtypes = [C.c_void_p, C.c_int]
+    lib.lcc_resize_aa_taps.argtypes = [C.c_int, C.c_int]
+    lib.lcc_resize_aa_table.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.lcc_resize_plan_create.restype = C.c_void_p
+    lib.lcc_resize_plan_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.lcc_resize_plan_destroy.argtypes = [C.c_void_p]
+    lib.lcc_resize_plan_info.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int64)]
     _lib = lib
     return lib
 
@@ -109,6 +115,25 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
 def launch_count() -> int:
     """Kernel launches issued by the library so far (graph-captured launches count once, at capture)."""
     return int(load_library().lcc_launch_count())
+
+
+def resize_aa_table(in_size: int, out_size: int):
+    """Host-only: (xmin int32[out], xsize int32[out], weights float32[taps, out]) of one axis of the antialiased bicubic
+    resize (lcc_resize_aa_table; ATen _compute_indices_min_size_weights_aa<float>). Needs no GPU."""
+    import numpy as np
+
+    lib = load_library()
+    taps = lib.lcc_resize_aa_taps(int(in_size), int(out_size))
+    if taps <= 0:
+        raise LiveCCNativeError(f"lcc_resize_aa_taps({in_size}, {out_size}) failed")
+    xmin = np.zeros(out_size, np.int32)
+    xsize = np.zeros(out_size, np.int32)
+    w = np.zeros((taps, out_size), np.float32)
+    rc = lib.lcc_resize_aa_table(int(in_size), int(out_size), xmin.ctypes.data_as(C.c_void_p),
+                                 xsize.ctypes.data_as(C.c_void_p), w.ctypes.data_as(C.c_void_p))
+    if rc:
+        raise LiveCCNativeError(f"lcc_resize_aa_table({in_size}, {out_size}) failed ({rc})")
+    return xmin, xsize, w
 
 
 def _ptr(t):
@@ -134,6 +159,9 @@ class Context:
         self.num_sms = self.lib.lcc_num_sms(C.c_void_p(self.handle))
 
     def close(self):
+        for plan in getattr(self, "_resize_plans", {}).values():
+            self.lib.lcc_resize_plan_destroy(C.c_void_p(plan))
+        self._resize_plans = {}
         if getattr(self, "handle", None):
             self.lib.lcc_destroy(C.c_void_p(self.handle))
             self.handle = None
@@ -184,6 +212,38 @@ class Context:
 
         out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
         self.call("lcc_cast_f32_bf16", _ptr(x), _ptr(out), C.c_int64(x.numel()), self.stream_ptr())
+        return out
+
+    def resize_plan(self, h, w, H, W, rows_per_cta=0):
+        """Device tables for (h, w) -> (H, W), created once per size and owned by this context."""
+        plans = self.__dict__.setdefault("_resize_plans", {})
+        key = (int(h), int(w), int(H), int(W), int(rows_per_cta))
+        if key not in plans:
+            plan = self.lib.lcc_resize_plan_create(C.c_void_p(self.handle), *map(int, key))
+            if not plan:
+                raise LiveCCNativeError("lcc_resize_plan_create failed: " + self.lib.lcc_last_error(C.c_void_p(self.handle)).decode())
+            plans[key] = plan
+        return plans[key]
+
+    def resize_plan_info(self, plan):
+        th, rows, smem = C.c_int(0), C.c_int(0), C.c_int64(0)
+        self.lib.lcc_resize_plan_info(C.c_void_p(plan), C.byref(th), C.byref(rows), C.byref(smem))
+        return {"rows_per_cta": th.value, "max_rows": rows.value, "smem_bytes": smem.value}
+
+    def resize_bicubic_aa_u8(self, clip, size, out=None, rows_per_cta=0):
+        """torchvision F.resize(clip, size, BICUBIC, antialias=True) of a contiguous uint8 CUDA tensor [..., h, w]
+        (video_process_patch.py:101-106,150-155), bit-identical, in one kernel."""
+        import torch
+
+        if clip.dtype != torch.uint8 or not clip.is_cuda or not clip.is_contiguous() or clip.dim() < 2:
+            raise ValueError("resize_bicubic_aa_u8 takes a contiguous uint8 CUDA tensor [..., h, w]")
+        h, w = clip.shape[-2:]
+        H, W = int(size[0]), int(size[1])
+        planes = clip.numel() // (h * w)
+        if out is None:
+            out = torch.empty(clip.shape[:-2] + (H, W), dtype=torch.uint8, device=clip.device)
+        plan = self.resize_plan(h, w, H, W, rows_per_cta)
+        self.call("lcc_resize_bicubic_aa_u8", C.c_void_p(plan), _ptr(clip), _i(planes), _ptr(out), self.stream_ptr())
         return out
 
     def layernorm(self, x, w, b, eps=1e-6):

@@ -5,6 +5,7 @@
 #include "gemm.h"
 #include "launch.h"
 #include "ops.h"
+#include "resize.h"
 
 using lcc::bf16;
 
@@ -171,6 +172,50 @@ int lcc_sample_greedy(lcc_ctx* ctx, const float* logits_raw, float* logits_proc,
     a.max_new_tokens = sp->max_new_tokens;
     a.advance_kv = advance_kv; a.embed = (const bf16*)embed; a.h = (bf16*)h; a.H = H;
     OP_RET(ctx, lcc::sample_greedy(a, (cudaStream_t)stream), "lcc_sample_greedy");
+}
+
+// ---- frame ingest: antialiased bicubic uint8 resize (resize.cu) ----
+struct lcc_resize_plan {
+    lcc::ResizePlan* impl;
+};
+
+int lcc_resize_aa_taps(int in_size, int out_size) { return lcc::resize_aa_taps(in_size, out_size); }
+
+int lcc_resize_aa_table(int in_size, int out_size, int32_t* xmin, int32_t* xsize, float* weights) {
+    if (!xmin || !xsize || !weights) return -1;
+    return lcc::resize_aa_table(in_size, out_size, xmin, xsize, weights);
+}
+
+lcc_resize_plan* lcc_resize_plan_create(lcc_ctx* ctx, int h, int w, int H, int W, int rows_per_cta) {
+    if (!ctx) return nullptr;
+    lcc::ResizePlan* impl = lcc::resize_plan_create(h, w, H, W, rows_per_cta);
+    if (!impl) {
+        snprintf(ctx->err, sizeof(ctx->err),
+                 "lcc_resize_plan_create(%dx%d -> %dx%d): size out of range, window larger than shared memory, or "
+                 "device allocation failed: %s", h, w, H, W, cudaGetErrorString(cudaGetLastError()));
+        return nullptr;
+    }
+    lcc_resize_plan* p = new lcc_resize_plan();
+    p->impl = impl;
+    return p;
+}
+
+void lcc_resize_plan_destroy(lcc_resize_plan* plan) {
+    if (!plan) return;
+    lcc::resize_plan_destroy(plan->impl);
+    delete plan;
+}
+
+int lcc_resize_plan_info(const lcc_resize_plan* plan, int* rows_per_cta, int* max_rows, int64_t* smem_bytes) {
+    if (!plan) return -1;
+    lcc::resize_plan_info(plan->impl, rows_per_cta, max_rows, smem_bytes);
+    return 0;
+}
+
+int lcc_resize_bicubic_aa_u8(lcc_ctx* ctx, const lcc_resize_plan* plan, const uint8_t* src, int planes, uint8_t* dst,
+                             lcc_stream_t stream) {
+    if (!plan) LCC_FAIL(ctx, -1, "lcc_resize_bicubic_aa_u8: null plan");
+    OP_RET(ctx, lcc::resize_bicubic_aa_u8(plan->impl, src, planes, dst, (cudaStream_t)stream), "lcc_resize_bicubic_aa_u8");
 }
 
 }  // extern "C"

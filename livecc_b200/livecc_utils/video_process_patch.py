@@ -184,10 +184,30 @@ def _open_reader(video_path: str, num_threads: int = 0):
     return Cv2VideoReader(video_path, num_threads)
 
 
+_NATIVE_CTX = {}
+
+
+def _native_ctx(device: torch.device):
+    """One C-ABI context per CUDA device for the ingest kernels (created on first use)."""
+    from .. import _cabi
+
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _NATIVE_CTX:
+        _NATIVE_CTX[idx] = _cabi.Context(idx)
+    return _NATIVE_CTX[idx]
+
+
 def _resize_bicubic_antialias(video: torch.Tensor, size):
-    """transforms.functional.resize(video, size, BICUBIC, antialias=True) (video_process_patch.py:101-106,150-155)."""
+    """transforms.functional.resize(video, size, BICUBIC, antialias=True) (video_process_patch.py:101-106,150-155).
+    A uint8 CUDA clip is resized by the native kernel (csrc/resize.cu: bit-identical to torchvision's CPU result, both
+    passes in one kernel); a host tensor goes through torchvision exactly as in the reference."""
     if tuple(video.shape[-2:]) == tuple(size):
         return video
+    if video.is_cuda:
+        if video.dtype != torch.uint8:
+            raise ValueError("GPU frame ingest resizes uint8 clips (decoded frames); got " + str(video.dtype))
+        with torch.cuda.device(video.device):
+            return _native_ctx(video.device).resize_bicubic_aa_u8(video.contiguous(), size)
     from torchvision.transforms import InterpolationMode
     from torchvision.transforms import functional as TF
 
@@ -284,11 +304,13 @@ def get_smart_resized_video_reader(video_path: str, max_pixels: int = None):
 
 
 def get_smart_resized_clip(video_reader, resized_height: int, resized_width: int, timestamps: torch.Tensor,
-                           video_pts: np.ndarray, video_pts_index_from: int = 0):
+                           video_pts: np.ndarray, video_pts_index_from: int = 0, device=None):
     """Frames for the given timestamps (video_process_patch.py:126-156): timestamps are padded to a multiple of
     FRAME_FACTOR by extrapolation, each maps to the first not-yet-passed frame whose pts reaches it, timestamps
     beyond the last frame are dropped and the result is trimmed back to a multiple of FRAME_FACTOR.
-    Returns (uint8 TCHW clip resized to (resized_height, resized_width), timestamps, frame indices)."""
+    Returns (uint8 TCHW clip resized to (resized_height, resized_width), timestamps, frame indices).
+    `device` (extension): a CUDA device moves the DECODED frames there (pinned staging, async copy)
+    and resizes them on the GPU; the returned clip lives on that device and is bit-identical to the host result."""
     extra = -len(timestamps) % FRAME_FACTOR
     if extra:
         tail = timestamps[-1] + torch.arange(1, extra + 1, dtype=timestamps.dtype) / FPS
@@ -301,7 +323,11 @@ def get_smart_resized_clip(video_reader, resized_height: int, resized_width: int
     clip_idxs = idx[: n_found - odd].tolist()
     if odd:  # the reference trims the timestamps only by the frames dropped for evenness (not to the clip length)
         timestamps = timestamps[:-odd]
-    clip = torch.from_numpy(video_reader.get_batch(clip_idxs).asnumpy()).permute(0, 3, 1, 2)  # THWC -> TCHW
+    clip = torch.from_numpy(video_reader.get_batch(clip_idxs).asnumpy())
+    if device is not None and torch.device(device).type == "cuda" and clip.numel() and \
+            tuple(clip.shape[1:3]) != (resized_height, resized_width):
+        clip = clip.pin_memory().to(device, non_blocking=True)
+    clip = clip.permute(0, 3, 1, 2)  # THWC -> TCHW
     if clip.shape[0] == 3 and clip.shape[1] == len(clip_idxs):  # a reader that returns channel-first batches
         clip = clip.transpose(0, 1)
     return _resize_bicubic_antialias(clip, (resized_height, resized_width)), timestamps, clip_idxs

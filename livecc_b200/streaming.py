@@ -38,9 +38,11 @@ class LiveCCDemoInfer:
     streaming_time_interval = streaming_fps_frames / fps
     frame_time_interval = 1 / fps
 
-    def __init__(self, model_path: str = None, device: str = None, model=None, processor=None):
+    def __init__(self, model_path: str = None, device: str = None, model=None, processor=None, gpu_ingest: bool = None):
         """Builds (or adopts) the model and processor (REF/demo/infer.py:35-59). `model=` / `processor=` reuse
-        existing objects (synthetic checkpoint); otherwise `model_path` must be a local HF checkpoint directory."""
+        existing objects (synthetic checkpoint); otherwise `model_path` must be a local HF checkpoint directory.
+        `gpu_ingest` (extension): decoded frames that need resizing are uploaded as uint8 and resized on the GPU
+        (bit-identical to the host resize); default = on whenever the processor hands uint8 frames to the engine."""
         if model is None:
             device = device or ("cuda" if torch.cuda.is_available() else "cpu")
             model = LiveCCB200ForConditionalGeneration.from_pretrained(model_path, torch_dtype="auto", device_map=device)
@@ -55,6 +57,9 @@ class LiveCCDemoInfer:
                                               tokenize=False)
         self.system_prompt_offset = probe.index("<|im_start|>user")  # later turns drop the system header
         self._cached_video_readers_with_hw = {}
+        if gpu_ingest is None:
+            gpu_ingest = bool(getattr(processor, "emit_frames", False)) and torch.device(model.device).type == "cuda"
+        self.ingest_device = model.device if gpu_ingest else None
         self.timings = []  # one record per chunk: frames, new_tokens, ingest_s, preprocess_s, generate_s, kv_len
 
     @staticmethod
@@ -153,7 +158,8 @@ class LiveCCDemoInfer:
         reader, height, width = source
         opening = state.get("last_timestamp", -1) < 0
         clip, stamps, frame_idxs = get_smart_resized_clip(reader, height, width, stamps, state["video_pts"],
-                                                          video_pts_index_from=state["last_video_pts_index"] + 1)
+                                                          video_pts_index_from=state["last_video_pts_index"] + 1,
+                                                          device=self.ingest_device)
         if len(frame_idxs) == 0:
             return
         state["last_video_pts_index"], state["last_timestamp"] = frame_idxs[-1], stamps[-1]

@@ -333,7 +333,18 @@ def test_op_wrappers_pass_as_many_arguments_as_the_header_declares():
     pt = torch.zeros(2, dtype=torch.int32)
     ctx.attn_prefill(q, kv, kv, pt, 4, 2, 0)
     ctx.attn_prefill(q, kv, kv, pt, 4, 2, 0, impl=1, split=True)
-    assert len(calls) == 6
+
+    class _FakeCudaU8:  # resize_bicubic_aa_u8 insists on a CUDA tensor; the arity check needs no device
+        dtype, is_cuda, shape = torch.uint8, True, (2, 3, 8, 10)
+
+        def is_contiguous(self): return True
+        def dim(self): return 4
+        def numel(self): return 2 * 3 * 8 * 10
+        def data_ptr(self): return 0
+
+    ctx.resize_plan = lambda *a: 1
+    ctx.resize_bicubic_aa_u8(_FakeCudaU8(), (4, 6), out=_FakeCudaU8())
+    assert len(calls) == 7
     for name, nargs in calls:
         assert nargs + 1 == declared(name), (name, nargs + 1, declared(name))  # + the ctx argument added by call()
 
