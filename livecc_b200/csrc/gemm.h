@@ -28,7 +28,7 @@ struct GemmArgs {
     const void* residual;  // [M, N] bf16, row stride ldr, or null
     int ldr;
     int epi;
-    int block_n;  // 0 = heuristic, else 64 / 128 / 256
+    int block_n;  // N tile: 0 = cost model, else a multiple of 16 in [32, 256] (EPI_SWIGLU: multiple of 32)
     // optional split-K scratch (fp32, >= splits*M*N*4 bytes); null = never split. `splits` is set internally.
     void* splitk_ws = nullptr;
     size_t splitk_ws_bytes = 0;

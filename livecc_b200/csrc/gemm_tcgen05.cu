@@ -28,15 +28,32 @@ static constexpr int BLOCK_M = 128;
 static constexpr int BLOCK_K = 64;   // 64 bf16 = 128 B = one SWIZZLE_128B row
 static constexpr int UMMA_K = 16;
 
-template <int BLOCK_N>
-struct GemmCfg {
-    static constexpr int STAGES = (BLOCK_N == 256) ? 4 : ((BLOCK_N == 128) ? 6 : 8);
-    static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
-    static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
-    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : 2 * BLOCK_N;  // power of two >= 32
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+// The N tile is a RUN-TIME value (multiple of 16, 32..256): the 148 SMs are filled by choosing the tile width per
+// shape (e.g. ViT qkv (1024 x 3840): 224 -> 8 x 18 = 144 tiles = one full wave; 256 or 128 leave a mostly empty
+// second wave). Everything that depended on BLOCK_N (stage size, ring depth, TMEM columns, instruction descriptor,
+// epilogue chunking) is derived from it on the host and passed in.
+static constexpr int MAX_STAGES = 8;
+static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+struct GemmTile {
+    int bn;          // N tile
+    int stages;      // smem ring depth
+    int tmem_cols;   // power of two >= two accumulators (+16 when the last 32-column epilogue chunk is half used)
+    uint32_t idesc;  // tcgen05 instruction descriptor (M = 128, N = bn)
+    int smem_bytes;
 };
+static GemmTile make_tile(int bn) {
+    GemmTile t;
+    t.bn = bn;
+    const int stage_bytes = A_BYTES + bn * BLOCK_K * 2;
+    t.stages = (227 * 1024 - 1024 - 256) / stage_bytes;
+    if (t.stages > MAX_STAGES) t.stages = MAX_STAGES;
+    int cols = 2 * bn + ((bn & 31) ? 16 : 0);
+    t.tmem_cols = 32;
+    while (t.tmem_cols < cols) t.tmem_cols <<= 1;
+    t.idesc = make_idesc_bf16(BLOCK_M, bn);
+    t.smem_bytes = t.stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    return t;
+}
 
 __device__ __forceinline__ float quick_gelu_bf16(float x) {
     // ACT2FN["quick_gelu"]: input * sigmoid(1.702 * input), every op rounded to bf16
@@ -50,24 +67,106 @@ __device__ __forceinline__ float gelu_erf_bf16(float x) {
 }
 __device__ __forceinline__ float silu_bf16(float x) { return rbf(__fdividef(x, 1.0f + __expf(-x))); }
 
-template <int BLOCK_N, int EPI>
+// Fused epilogue of one 32-column chunk of one accumulator row: v = the fp32 bits of columns [col0, col0 + 32) of output row
+// `row` (one thread per row); columns >= tile_end belong to the next tile (or are padding) and are dropped.
+template <int EPI>
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], bf16* C, int ldc, int M, int row, bool row_ok, int col0,
+                                               int tile_end, int ks, const bf16* __restrict__ bias, const bf16* residual,
+                                               int ldr) {
+    if (EPI == EPI_PARTIAL_F32) {
+        // fp32 partial tile of split ks: P[ks][row][col] (C is the partial buffer, ldc == N)
+        if (row_ok) {
+            float* dst = reinterpret_cast<float*>(C) + ((size_t)ks * M + row) * (size_t)ldc + col0;
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+                if (col0 + g * 4 < tile_end)
+                    *reinterpret_cast<uint4*>(dst + g * 4) =
+                        make_uint4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+        }
+    } else if (EPI == EPI_SWIGLU) {
+        // Weight rows are interleaved in 32-row groups: 16 gate rows then the 16
+        // matching up rows. out[j] = bf16(silu_bf16(bf16 gate) * bf16 up)  (mq2vl.py:503)
+        if (row_ok && col0 < tile_end) {  // BLOCK_N % 32 == 0 for this epilogue: whole chunks only
+            const int ocol0 = (col0 >> 5) << 4;
+            uint32_t o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float g0 = rbf(__uint_as_float(v[2 * j])), g1 = rbf(__uint_as_float(v[2 * j + 1]));
+                float u0 = rbf(__uint_as_float(v[16 + 2 * j])), u1 = rbf(__uint_as_float(v[16 + 2 * j + 1]));
+                o[j] = pack_bf16x2(silu_bf16(g0) * u0, silu_bf16(g1) * u1);
+            }
+            uint4* dst = reinterpret_cast<uint4*>(C + (size_t)row * ldc + ocol0);
+            dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+            dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+        }
+    } else {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {  // 4 groups of 8 columns (16 B of bf16 each)
+            const int col = col0 + g * 8;
+            if (row_ok && col < tile_end) {
+                float x[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v[g * 8 + j]);
+                if (EPI == EPI_BIAS || EPI == EPI_BIAS_QUICKGELU || EPI == EPI_BIAS_GELU ||
+                    EPI == EPI_BIAS_RESIDUAL) {
+                    const uint4 bb = *reinterpret_cast<const uint4*>(bias + col);
+                    const uint32_t bw[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float2 f = unpack_bf16x2(bw[j]);
+                        x[2 * j] += f.x;
+                        x[2 * j + 1] += f.y;
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) x[j] = rbf(x[j]);
+                if (EPI == EPI_BIAS_QUICKGELU) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) x[j] = quick_gelu_bf16(x[j]);
+                } else if (EPI == EPI_BIAS_GELU) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) x[j] = gelu_erf_bf16(x[j]);
+                } else if (EPI == EPI_RESIDUAL || EPI == EPI_BIAS_RESIDUAL) {
+                    const uint4 rr =
+                        *reinterpret_cast<const uint4*>(residual + (size_t)row * ldr + col);
+                    const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float2 f = unpack_bf16x2(rw[j]);
+                        x[2 * j] += f.x;
+                        x[2 * j + 1] += f.y;
+                    }
+                }
+                uint4 o;
+                o.x = pack_bf16x2(x[0], x[1]);
+                o.y = pack_bf16x2(x[2], x[3]);
+                o.z = pack_bf16x2(x[4], x[5]);
+                o.w = pack_bf16x2(x[6], x[7]);
+                *reinterpret_cast<uint4*>(C + (size_t)row * ldc + col) = o;
+            }
+        }
+    }
+}
+
+template <int EPI>
 __global__ void __launch_bounds__(384, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     const __grid_constant__ CUtensorMap tmap_b, bf16* C, int M, int N,
                     int K, int ldc, const bf16* __restrict__ bias,
-                    const bf16* residual /* may alias C */, int ldr, int splits_arg /* >= 1 */) {
-    using Cfg = GemmCfg<BLOCK_N>;
+                    const bf16* residual /* may alias C */, int ldr, int splits_arg /* >= 1 */, const GemmTile cfg) {
+    const int BLOCK_N = cfg.bn;
+    const int STAGE_BYTES = A_BYTES + BLOCK_N * BLOCK_K * 2;
     // split-K exists only in the EPI_PARTIAL_F32 instantiations; everywhere else splits is the constant 1 and the
     // unit arithmetic below folds back to the plain (m tile, n tile) loop.
     const int splits = (EPI == EPI_PARTIAL_F32) ? splits_arg : 1;
-    constexpr int STAGES = Cfg::STAGES;
+    const int STAGES = cfg.stages;
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte alignment.
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                                ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
-    uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* tmem_full = empty_bar + STAGES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + MAX_STAGES;
+    uint64_t* tmem_full = empty_bar + MAX_STAGES;
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
@@ -99,7 +198,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
         fence_barrier_init();
     }
     if (warp == 2) {
-        tmem_alloc(tmem_holder, Cfg::TMEM_COLS);
+        tmem_alloc(tmem_holder, cfg.tmem_cols);
         tmem_relinquish();
     }
     tc_fence_before();
@@ -117,9 +216,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 const int kb0 = ks * kbps, kb1 = min(kb0 + kbps, num_k_blocks);
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-                    uint8_t* sb = sa + Cfg::A_BYTES;
-                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                    uint8_t* sa = smem + stage * STAGE_BYTES;
+                    uint8_t* sb = sa + A_BYTES;
+                    mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
                     tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
                     tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -128,7 +227,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N);
+        const uint32_t idesc = cfg.idesc;
         int stage = 0;
         uint32_t phase = 0;
         int acc = 0;
@@ -143,8 +242,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
                 if (lane == 0) {
-                    const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-                    const uint32_t sb = sa + Cfg::A_BYTES;
+                    const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+                    const uint32_t sb = sa + A_BYTES;
                     const uint64_t da = make_sw128_kmajor_desc(sa);
                     const uint64_t db = make_sw128_kmajor_desc(sb);
 #pragma unroll
@@ -165,7 +264,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
         // ===================== Epilogue =====================
         const int q = warp & 3;          // TMEM lane quarter this warp may access (warp id mod 4)
         const int half = (warp - 4) >> 2;  // which half of the tile's columns this warp converts
-        constexpr int CHUNKS_PER_HALF = BLOCK_N / 64;
+        const int chunks = (BLOCK_N + 31) >> 5;  // 32-column epilogue chunks; the last one may be half used (BLOCK_N % 32 == 16)
+        const int chunks_h0 = (chunks + 1) >> 1;
+        const int c_begin = half ? chunks_h0 : 0, c_end = half ? chunks : chunks_h0;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -174,87 +275,16 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
             tc_fence_after();
             const int row = m_blk * BLOCK_M + q * 32 + lane;
             const bool row_ok = row < M;
+            const int tile_end = min(N, (n_blk + 1) * BLOCK_N);  // columns past it belong to the next tile (or are padding)
 #pragma unroll 1
-            for (int c = half * CHUNKS_PER_HALF; c < (half + 1) * CHUNKS_PER_HALF; ++c) {
+            for (int c = c_begin; c < c_end; ++c) {
                 uint32_t v[32];
                 const uint32_t taddr =
                     tmem_base + (uint32_t)(acc * BLOCK_N + c * 32) + ((uint32_t)(q * 32) << 16);
                 tmem_ld_32x32b_x32(taddr, v);
                 tmem_ld_wait();
                 const int col0 = n_blk * BLOCK_N + c * 32;
-                if (EPI == EPI_PARTIAL_F32) {
-                    // fp32 partial tile of split ks: P[ks][row][col] (C is the partial buffer, ldc == N)
-                    if (row_ok) {
-                        float* dst = reinterpret_cast<float*>(C) + ((size_t)ks * M + row) * (size_t)ldc + col0;
-#pragma unroll
-                        for (int g = 0; g < 8; ++g)
-                            if (col0 + g * 4 < N)
-                                *reinterpret_cast<uint4*>(dst + g * 4) =
-                                    make_uint4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
-                    }
-                } else if (EPI == EPI_SWIGLU) {
-                    // Weight rows are interleaved in 32-row groups: 16 gate rows then the 16
-                    // matching up rows. out[j] = bf16(silu_bf16(bf16 gate) * bf16 up)  (mq2vl.py:503)
-                    if (row_ok && col0 < N) {
-                        const int ocol0 = (col0 >> 5) << 4;
-                        uint32_t o[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            float g0 = rbf(__uint_as_float(v[2 * j])), g1 = rbf(__uint_as_float(v[2 * j + 1]));
-                            float u0 = rbf(__uint_as_float(v[16 + 2 * j])), u1 = rbf(__uint_as_float(v[16 + 2 * j + 1]));
-                            o[j] = pack_bf16x2(silu_bf16(g0) * u0, silu_bf16(g1) * u1);
-                        }
-                        uint4* dst = reinterpret_cast<uint4*>(C + (size_t)row * ldc + ocol0);
-                        dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
-                        dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
-                    }
-                } else {
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {  // 4 groups of 8 columns (16 B of bf16 each)
-                        const int col = col0 + g * 8;
-                        if (row_ok && col < N) {
-                            float x[8];
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v[g * 8 + j]);
-                            if (EPI == EPI_BIAS || EPI == EPI_BIAS_QUICKGELU || EPI == EPI_BIAS_GELU ||
-                                EPI == EPI_BIAS_RESIDUAL) {
-                                const uint4 bb = *reinterpret_cast<const uint4*>(bias + col);
-                                const uint32_t bw[4] = {bb.x, bb.y, bb.z, bb.w};
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    float2 f = unpack_bf16x2(bw[j]);
-                                    x[2 * j] += f.x;
-                                    x[2 * j + 1] += f.y;
-                                }
-                            }
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) x[j] = rbf(x[j]);
-                            if (EPI == EPI_BIAS_QUICKGELU) {
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) x[j] = quick_gelu_bf16(x[j]);
-                            } else if (EPI == EPI_BIAS_GELU) {
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) x[j] = gelu_erf_bf16(x[j]);
-                            } else if (EPI == EPI_RESIDUAL || EPI == EPI_BIAS_RESIDUAL) {
-                                const uint4 rr =
-                                    *reinterpret_cast<const uint4*>(residual + (size_t)row * ldr + col);
-                                const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    float2 f = unpack_bf16x2(rw[j]);
-                                    x[2 * j] += f.x;
-                                    x[2 * j + 1] += f.y;
-                                }
-                            }
-                            uint4 o;
-                            o.x = pack_bf16x2(x[0], x[1]);
-                            o.y = pack_bf16x2(x[2], x[3]);
-                            o.z = pack_bf16x2(x[4], x[5]);
-                            o.w = pack_bf16x2(x[6], x[7]);
-                            *reinterpret_cast<uint4*>(C + (size_t)row * ldc + col) = o;
-                        }
-                    }
-                }
+                epilogue_chunk<EPI>(v, C, ldc, M, row, row_ok, col0, tile_end, ks, bias, residual, ldr);
             }
             tc_fence_before();
             __syncwarp();
@@ -267,7 +297,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
     __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+        tmem_dealloc(tmem_base, cfg.tmem_cols);
     }
 }
 
@@ -328,38 +358,57 @@ int make_tmap_bf16_2d(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t co
     return make_tmap_bf16_2d_box(tm, ptr, rows, cols, ld, BLOCK_K, box_rows, false);
 }
 
-template <int BLOCK_N, int EPI>
-static int launch_cfg(const GemmArgs& a, int num_sms, cudaStream_t stream) {
-    using Cfg = GemmCfg<BLOCK_N>;
+template <int EPI>
+static int launch_cfg(const GemmArgs& a, int bn, int num_sms, cudaStream_t stream) {
+    const GemmTile cfg = make_tile(bn);
     CUtensorMap ta, tb;
     if (make_tmap_bf16_2d(&ta, a.A, a.M, a.K, a.lda, BLOCK_M)) return -10;
-    if (make_tmap_bf16_2d(&tb, a.B, a.N, a.K, a.ldb, BLOCK_N)) return -11;
-    auto kern = gemm_bf16_tn_kernel<BLOCK_N, EPI>;
+    if (make_tmap_bf16_2d(&tb, a.B, a.N, a.K, a.ldb, bn)) return -11;
+    auto kern = gemm_bf16_tn_kernel<EPI>;
     static SmemAttrOnce once;  // per template instantiation
-    if (ensure_dyn_smem(once, kern, Cfg::SMEM_BYTES)) return -12;
-    const int m_tiles = (a.M + BLOCK_M - 1) / BLOCK_M, n_tiles = (a.N + BLOCK_N - 1) / BLOCK_N;
+    if (ensure_dyn_smem(once, kern, 227 * 1024)) return -12;
+    const int m_tiles = (a.M + BLOCK_M - 1) / BLOCK_M, n_tiles = (a.N + bn - 1) / bn;
     const int splits = (EPI == EPI_PARTIAL_F32 && a.splits > 1) ? a.splits : 1;
     const int tiles = m_tiles * n_tiles * splits;
     const int grid = tiles < num_sms ? tiles : num_sms;
     lcc::count_launch();
-    kern<<<grid, 384, Cfg::SMEM_BYTES, stream>>>(ta, tb, (bf16*)a.C, a.M, a.N, a.K, a.ldc,
-                                                 (const bf16*)a.bias, (const bf16*)a.residual,
-                                                 a.ldr, splits);
+    kern<<<grid, 384, cfg.smem_bytes, stream>>>(ta, tb, (bf16*)a.C, a.M, a.N, a.K, a.ldc,
+                                                (const bf16*)a.bias, (const bf16*)a.residual,
+                                                a.ldr, splits, cfg);
     return cudaGetLastError() == cudaSuccess ? 0 : -13;
 }
 
-template <int BLOCK_N>
-static int launch_epi(const GemmArgs& a, int num_sms, cudaStream_t stream) {
+static int launch_epi(const GemmArgs& a, int bn, int num_sms, cudaStream_t stream) {
     switch (a.epi) {
-        case EPI_NONE: return launch_cfg<BLOCK_N, EPI_NONE>(a, num_sms, stream);
-        case EPI_BIAS: return launch_cfg<BLOCK_N, EPI_BIAS>(a, num_sms, stream);
-        case EPI_BIAS_QUICKGELU: return launch_cfg<BLOCK_N, EPI_BIAS_QUICKGELU>(a, num_sms, stream);
-        case EPI_BIAS_GELU: return launch_cfg<BLOCK_N, EPI_BIAS_GELU>(a, num_sms, stream);
-        case EPI_RESIDUAL: return launch_cfg<BLOCK_N, EPI_RESIDUAL>(a, num_sms, stream);
-        case EPI_BIAS_RESIDUAL: return launch_cfg<BLOCK_N, EPI_BIAS_RESIDUAL>(a, num_sms, stream);
-        case EPI_SWIGLU: return launch_cfg<BLOCK_N, EPI_SWIGLU>(a, num_sms, stream);
+        case EPI_NONE: return launch_cfg<EPI_NONE>(a, bn, num_sms, stream);
+        case EPI_BIAS: return launch_cfg<EPI_BIAS>(a, bn, num_sms, stream);
+        case EPI_BIAS_QUICKGELU: return launch_cfg<EPI_BIAS_QUICKGELU>(a, bn, num_sms, stream);
+        case EPI_BIAS_GELU: return launch_cfg<EPI_BIAS_GELU>(a, bn, num_sms, stream);
+        case EPI_RESIDUAL: return launch_cfg<EPI_RESIDUAL>(a, bn, num_sms, stream);
+        case EPI_BIAS_RESIDUAL: return launch_cfg<EPI_BIAS_RESIDUAL>(a, bn, num_sms, stream);
+        case EPI_SWIGLU: return launch_cfg<EPI_SWIGLU>(a, bn, num_sms, stream);
     }
     return -14;
+}
+
+// Tile-width choice. What the B200 measurements say (profiles/r02_gemm_shapes.md, r02_gemm_vs_cublas.md):
+//  * with one CTA per SM the main loop is bound by SHARED-MEMORY bandwidth, not by the tensor pipe: per 64-deep k-block the
+//    TMA writes 16 KB (A) + bn*128 B (B) into shared memory and the four MMAs read the same bytes back: 2*(16384 + 128*bn) B
+//    at 128 B/clk = 256 + 2*bn clocks against the tensor floor of 2*bn (bn = 256: 67 %, 128: 50 %, 64: 33 % — the measured
+//    per-k-block times of every shape in the sweep fit this at the ~1.4 GHz the SMs run under tensor load);
+//  * every launch carries ~8 us that does not depend on the tile (launch gap, barrier/TMEM set-up, first TMA round trip,
+//    the un-overlapped epilogue of the last tile), which is 30-60 % of the M = 281 / 1024 GEMMs of the streaming path;
+//  * because of that fixed part, filling the last wave exactly (widths like 224 or 144, which the run-time width allows)
+//    measured within noise of the simple rule below (prefill qkv: 96 -> 24.3 us, 128 -> 23.5, 192 -> 25.3, 256 -> 29.5).
+// So: 64-wide tiles never win; between 128 and 256 the cost is (waves over the SMs) x (128 + bn), ties to the narrower tile.
+static int choose_bn(int M, int N, int num_sms) {
+    if (N <= 64) return 64;
+    const long long m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
+    auto cost = [&](int bn) {
+        const long long tiles = m_tiles * ((N + bn - 1) / bn);
+        return ((tiles + num_sms - 1) / num_sms) * (long long)(128 + bn);
+    };
+    return cost(128) <= cost(256) ? 128 : 256;
 }
 
 // Sum of the split-K partials + the fused epilogue (same rounding points as the in-kernel epilogues):
@@ -423,7 +472,7 @@ static int try_splitk(const GemmArgs& a, int num_sms, cudaStream_t stream) {
     if (!mode || !a.splitk_ws || a.M > 384) return 0;
     if (mode == 2 && a.K < 8192) return 0;
     if (a.epi != EPI_NONE && a.epi != EPI_BIAS && a.epi != EPI_RESIDUAL && a.epi != EPI_BIAS_RESIDUAL) return 0;
-    const int block_n = a.N >= 256 ? 256 : (a.N >= 128 ? 128 : 64);
+    const int block_n = a.block_n ? a.block_n : (a.N >= 256 ? 256 : (a.N >= 128 ? 128 : 64));
     const int m_tiles = (a.M + BLOCK_M - 1) / BLOCK_M, n_tiles = (a.N + block_n - 1) / block_n;
     const int tiles = m_tiles * n_tiles;
     const int nkb = (a.K + BLOCK_K - 1) / BLOCK_K;
@@ -441,13 +490,7 @@ static int try_splitk(const GemmArgs& a, int num_sms, cudaStream_t stream) {
     p.splits = splits;
     p.bias = nullptr;
     p.residual = nullptr;
-    int r;
-    switch (block_n) {
-        case 256: r = launch_cfg<256, EPI_PARTIAL_F32>(p, num_sms, stream); break;
-        case 128: r = launch_cfg<128, EPI_PARTIAL_F32>(p, num_sms, stream); break;
-        default: r = launch_cfg<64, EPI_PARTIAL_F32>(p, num_sms, stream); break;
-    }
-    if (r) return r;
+    if (int r = launch_cfg<EPI_PARTIAL_F32>(p, block_n, num_sms, stream)) return r;
     const int64_t threads = (int64_t)a.M * (a.N / 8);
     lcc::count_launch();
     splitk_reduce_kernel<<<(int)((threads + 255) / 256), 256, 0, stream>>>(
@@ -464,26 +507,17 @@ int gemm_bf16_tn(const GemmArgs& a, int num_sms, cudaStream_t stream) {
     if ((a.epi == EPI_BIAS || a.epi == EPI_BIAS_QUICKGELU || a.epi == EPI_BIAS_GELU ||
          a.epi == EPI_BIAS_RESIDUAL) && !a.bias) return -5;
     if (int r = try_splitk(a, num_sms, stream)) return r < 0 ? r : 0;
-    // Tile-shape heuristic, fitted to the B200 sweep in profiles/r02_gemm_shapes.md: 64-wide tiles are L2->SM bound and
-    // never win; between 128 and 256 the cost is (waves over the SMs) x (fixed fill/epilogue + mainloop ~ 128 + block_n),
-    // ties go to the narrower tile (more CTAs overlap epilogue and mainloop). Examples: ViT fc1 (1024, 5120): 256 -> 2 waves
-    // x 384 = 768, 128 -> 3 x 256 = 768 -> 128 (28.0 vs 31.4 us); prefill gate/up (281, 37888): 256 (82 vs 102 us).
     int block_n = a.block_n;
     if (block_n == 0) {
-        const long long m_tiles = (a.M + BLOCK_M - 1) / BLOCK_M;
-        auto cost = [&](int bn) {
-            const long long tiles = m_tiles * ((a.N + bn - 1) / bn);
-            return ((tiles + num_sms - 1) / num_sms) * (long long)(128 + bn);
-        };
-        block_n = cost(128) <= cost(256) ? 128 : 256;
-        if (a.N <= 64) block_n = 64;
+        static int forced = -1;
+        if (forced < 0) {
+            const char* e = getenv("LIVECC_B200_GEMM_BN");  // tuning hook: force one width (0/unset = model)
+            forced = e ? atoi(e) : 0;
+        }
+        block_n = forced > 0 ? forced : choose_bn(a.M, a.N, num_sms);
     }
-    switch (block_n) {
-        case 256: return launch_epi<256>(a, num_sms, stream);
-        case 128: return launch_epi<128>(a, num_sms, stream);
-        case 64: return launch_epi<64>(a, num_sms, stream);
-    }
-    return -6;
+    if (block_n < 32 || block_n > 256 || (block_n % 16) || (a.epi == EPI_SWIGLU && (block_n % 32))) return -6;
+    return launch_epi(a, block_n, num_sms, stream);
 }
 
 }  // namespace lcc

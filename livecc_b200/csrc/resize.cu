@@ -8,10 +8,8 @@
 // (FMA-contracted polynomial; tap sums with 4-wide unfused groups and a fused remainder) is stated in
 // oracle/resize_aa.py and pinned by tests/test_resize_cpu.py / tests/golden/resize_aa_golden.json.
 //
-// One kernel, both passes: a CTA owns TH output rows of one plane. It copies the source rows its vertical windows cover
-// (contiguous in HBM, 16-byte loads) into shared memory, runs the width pass from shared memory into a float tile
-// [rows][W] in shared memory, then the height pass, clamp, round, and writes 4 output bytes per thread. The float
-// intermediate never leaves the SM; HBM traffic = source (re-read of window overlap is served by L2) + output.
+// One kernel, both passes (tiling described at the kernel). HBM traffic = source + output; the work is fp32-issue bound
+// (22 taps per output pixel on the 1080p -> 448 shape), not bandwidth bound.
 #include <string.h>
 
 #include <algorithm>
@@ -85,91 +83,164 @@ int resize_aa_table(int in_size, int out_size, int32_t* xmin_out, int32_t* xsize
 }
 
 // ---- device ----------------------------------------------------------------------------------------------------------
+// Tiling: a CTA owns TH output rows x TW output columns of one plane. It stages the source window its taps cover
+// (nr rows x seg bytes, 16-byte loads; each row keeps its global 16-byte phase), runs the width pass from shared memory into a
+// float tile [nr][TW] in shared memory, then the height pass, clamp, round, and stores 4 output bytes per thread. Both
+// weight tables of the tile live in shared memory. The float intermediate never leaves the SM; every source byte is read from
+// HBM once (window overlaps between neighbouring CTAs are L2 hits).
 struct ResizeParams {
     const uint8_t* src;
     uint8_t* dst;
+    size_t src_bytes;
     int h, w, H, W;
+    int taps_w, taps_h;
     const int32_t* xmin_w; const int32_t* n_w; const float* wt_w;  // [W], [W], [taps_w][W]
     const int32_t* xmin_h; const int32_t* n_h; const float* wt_h;  // [H], [H], [taps_h][H]
-    int th;        // output rows per CTA
-    int max_rows;  // source rows a CTA may stage
+    const int32_t* col_c0; const int32_t* col_len;                 // per column tile: first source column, window length
+    const int32_t* row_r0; const int32_t* row_nr;                  // per row tile: first source row, window rows
+    int th, tw;        // output rows / columns per CTA
+    int max_rows;      // source rows a CTA may stage
+    int stride;        // bytes between staged rows (multiple of 16, >= longest window + 30)
 };
 
-// t = s0*w0; then 4*floor((n-1)/4) separate multiply/add steps; the remaining (n-1) mod 4 steps fused (oracle/resize_aa.py)
-template <typename LoadS, typename LoadW>
-__device__ __forceinline__ float tap_sum(int n, LoadS s, LoadW w) {
-    if (n <= 0) return 0.f;
-    float acc = __fmul_rn(s(0), w(0));
-    const int unfused = ((n - 1) >> 2) << 2;
-    int j = 1;
-    for (; j <= unfused; ++j) acc = __fadd_rn(acc, __fmul_rn(s(j), w(j)));
-    for (; j < n; ++j) acc = __fmaf_rn(s(j), w(j), acc);
-    return acc;
-}
+// float(u8) without the quarter-rate I2F: 0x4B000000 | u is the float 2^23 + u (exact), minus 2^23.
+__device__ __forceinline__ float u8_to_float(uint32_t u) { return __fsub_rn(__uint_as_float(0x4B000000u | u), 8388608.0f); }
 
 __device__ __forceinline__ uint32_t to_u8(float v) {  // clamp(0, 255), round half to even (torch.round), cast
     return (uint32_t)__float2int_rn(fminf(fmaxf(v, 0.f), 255.f));
 }
 
-__global__ void __launch_bounds__(256) resize_bicubic_aa_u8_kernel(const ResizeParams p) {
+constexpr int RS_THREADS = 256;
+constexpr int RS_RB = 4;  // source rows per thread and iteration in the width pass (independent accumulators)
+
+__global__ void __launch_bounds__(RS_THREADS) resize_bicubic_aa_u8_kernel(const ResizeParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
-    const int plane = blockIdx.y;
-    const int y0 = blockIdx.x * p.th, y1 = min(y0 + p.th, p.H);
-    const int r0 = p.xmin_h[y0];
-    int r1 = r0;
-    for (int y = y0; y < y1; ++y) r1 = max(r1, p.xmin_h[y] + p.n_h[y]);
-    const int nr = min(r1 - r0, p.max_rows);
-    float* tile = reinterpret_cast<float*>(smem);                                  // [max_rows][W]
-    uint8_t* rows = smem + (((size_t)p.max_rows * p.W * sizeof(float) + 15) & ~(size_t)15);  // nr*w source bytes (+ <= 15 of skew)
+    const int plane = blockIdx.z, rt = blockIdx.y, ct = blockIdx.x;
+    const int TW = p.tw;
+    const int y0 = rt * p.th, y1 = min(y0 + p.th, p.H);
+    const int X0 = ct * TW, X1 = min(X0 + TW, p.W);
+    const int r0 = p.row_r0[rt], nr = p.row_nr[rt];
+    const int c0 = p.col_c0[ct], seg = p.col_len[ct];
+    // shared memory carve-up (no integer round trips on the pointers: the compiler must keep them in the shared window)
+    uint8_t* rows = smem;                                                  // [max_rows][stride] staged source bytes
+    float* tile = reinterpret_cast<float*>(smem + (size_t)p.max_rows * p.stride);  // [max_rows][TW]
+    float* wts_w = tile + (size_t)p.max_rows * TW;                        // [taps_w][TW]
+    float* wts_h = wts_w + (size_t)p.taps_w * TW;                         // [taps_h][th]
+    int* skew = reinterpret_cast<int*>(wts_h + (size_t)p.taps_h * p.th);  // [max_rows]
 
-    // ---- stage the source rows: one contiguous span of the plane; keep the global address's 16-byte phase in shared memory
-    const uint8_t* g = p.src + ((size_t)plane * p.h + r0) * p.w;
-    const size_t nbytes = (size_t)nr * p.w;
-    const int skew = (int)(reinterpret_cast<uintptr_t>(g) & 15);
-    uint8_t* srow = rows + skew;
-    const size_t head = min(nbytes, (size_t)((16 - skew) & 15));
-    for (size_t i = threadIdx.x; i < head; i += blockDim.x) srow[i] = g[i];
-    const size_t nvec = (nbytes - head) >> 4;
-    const uint4* gv = reinterpret_cast<const uint4*>(g + head);
-    uint4* sv = reinterpret_cast<uint4*>(srow + head);
-    for (size_t i = threadIdx.x; i < nvec; i += blockDim.x) sv[i] = __ldg(gv + i);
-    for (size_t i = head + (nvec << 4) + threadIdx.x; i < nbytes; i += blockDim.x) srow[i] = g[i];
-    __syncthreads();
-
-    // ---- width pass: tile[r][X] = sum_j row_r[xmin_w[X] + j] * wt_w[j][X]
-    const int W = p.W;
-    for (int idx = threadIdx.x; idx < nr * W; idx += blockDim.x) {
-        const int r = idx / W, X = idx - r * W;
-        const uint8_t* s = srow + (size_t)r * p.w + p.xmin_w[X];
-        const float* wt = p.wt_w + X;
-        tile[idx] = tap_sum(p.n_w[X], [&](int j) { return (float)s[j]; }, [&](int j) { return __ldg(wt + (size_t)j * W); });
+    // ---- stage: weights of this tile
+    for (int i = threadIdx.x; i < p.taps_w * TW; i += RS_THREADS) {
+        const int j = i / TW, xl = i - j * TW;
+        wts_w[i] = X0 + xl < p.W ? __ldg(p.wt_w + (size_t)j * p.W + X0 + xl) : 0.f;
+    }
+    for (int i = threadIdx.x; i < p.taps_h * p.th; i += RS_THREADS) {
+        const int j = i / p.th, yl = i - j * p.th;
+        wts_h[i] = y0 + yl < p.H ? __ldg(p.wt_h + (size_t)j * p.H + y0 + yl) : 0.f;
+    }
+    // ---- stage: source window, row by row, 16-byte chunks at the global address's own alignment
+    const uint8_t* plane_base = p.src + (size_t)plane * p.h * p.w;
+    const uintptr_t lo = reinterpret_cast<uintptr_t>(p.src), hi = lo + p.src_bytes;
+    const int cpr = p.stride >> 4;  // chunks per staged row
+    for (int i = threadIdx.x; i < nr * cpr; i += RS_THREADS) {
+        const int r = i / cpr, ch = i - r * cpr;
+        const uintptr_t gaddr = reinterpret_cast<uintptr_t>(plane_base + (size_t)(r0 + r) * p.w + c0);
+        const int sk = (int)(gaddr & 15);
+        if (ch == 0) skew[r] = sk;
+        if (ch * 16 >= sk + seg) continue;  // past the window
+        const uintptr_t a = (gaddr & ~uintptr_t(15)) + (uintptr_t)ch * 16;
+        uint4 v;
+        if (a >= lo && a + 16 <= hi) {
+            v = __ldg(reinterpret_cast<const uint4*>(a));
+        } else {  // first / last chunk of the whole clip when its ends are not 16-byte aligned
+            uint32_t wds[4] = {0, 0, 0, 0};
+            for (int b = 0; b < 16; ++b)
+                if (a + b >= lo && a + b < hi) wds[b >> 2] |= (uint32_t)(*reinterpret_cast<const uint8_t*>(a + b)) << ((b & 3) * 8);
+            v = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+        }
+        *reinterpret_cast<uint4*>(rows + (size_t)r * p.stride + ch * 16) = v;
     }
     __syncthreads();
 
-    // ---- height pass + clamp/round/cast
-    uint8_t* out = p.dst + (size_t)plane * p.H * W;
-    if ((W & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 3) == 0) {
-        const int W4 = W >> 2;
-        for (int idx = threadIdx.x; idx < (y1 - y0) * W4; idx += blockDim.x) {
-            const int yy = idx / W4, X = (idx - yy * W4) << 2;
-            const int y = y0 + yy, n = p.n_h[y];
-            const float* t = tile + (size_t)(p.xmin_h[y] - r0) * W + X;
-            const float* wt = p.wt_h + y;
-            float a[4];
+    // ---- width pass: tile[r][xl] = sum_j row_r[xmin_w[X] + j] * wt_w[j][X]; thread = one column, RS_RB rows at a time
+    {
+        const int groups = RS_THREADS / TW;  // row groups working side by side (TW is 64, 128 or 256)
+        const int xl = threadIdx.x % TW, g = threadIdx.x / TW;
+        const int X = min(X0 + xl, p.W - 1);
+        const int n = __ldg(p.n_w + X), x0 = __ldg(p.xmin_w + X) - c0;
+        const int unfused = ((n - 1) >> 2) << 2;
+        const float* wc = wts_w + xl;
+        if (n > 0 && X0 + xl < X1) {
+            for (int rb = g * RS_RB; rb < nr; rb += groups * RS_RB) {
+                const uint8_t* s[RS_RB];
+                float acc[RS_RB];
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
-                a[c] = tap_sum(n, [&](int j) { return t[(size_t)j * W + c]; }, [&](int j) { return __ldg(wt + (size_t)j * p.H); });
-            *reinterpret_cast<uint32_t*>(out + (size_t)y * W + X) =
-                to_u8(a[0]) | (to_u8(a[1]) << 8) | (to_u8(a[2]) << 16) | (to_u8(a[3]) << 24);
+                for (int q = 0; q < RS_RB; ++q) {
+                    const int r = min(rb + q, nr - 1);
+                    s[q] = rows + (size_t)r * p.stride + skew[r] + x0;
+                }
+                const float w0 = wc[0];
+#pragma unroll
+                for (int q = 0; q < RS_RB; ++q) acc[q] = __fmul_rn(u8_to_float(s[q][0]), w0);
+                int j = 1;
+                for (; j <= unfused; j += 4) {  // whole groups of 4 unfused steps
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float wj = wc[(j + k) * TW];
+#pragma unroll
+                        for (int q = 0; q < RS_RB; ++q) acc[q] = __fadd_rn(acc[q], __fmul_rn(u8_to_float(s[q][j + k]), wj));
+                    }
+                }
+                for (; j < n; ++j) {  // <= 3 fused steps
+                    const float wj = wc[j * TW];
+#pragma unroll
+                    for (int q = 0; q < RS_RB; ++q) acc[q] = __fmaf_rn(u8_to_float(s[q][j]), wj, acc[q]);
+                }
+#pragma unroll
+                for (int q = 0; q < RS_RB; ++q)
+                    if (rb + q < nr) tile[(size_t)(rb + q) * TW + xl] = acc[q];
+            }
+        } else if (X0 + xl < X1) {
+            for (int r = g; r < nr; r += groups) tile[(size_t)r * TW + xl] = 0.f;
         }
-    } else {
-        for (int idx = threadIdx.x; idx < (y1 - y0) * W; idx += blockDim.x) {
-            const int yy = idx / W, X = idx - yy * W;
-            const int y = y0 + yy;
-            const float* t = tile + (size_t)(p.xmin_h[y] - r0) * W + X;
-            const float* wt = p.wt_h + y;
-            out[(size_t)y * W + X] = (uint8_t)to_u8(
-                tap_sum(p.n_h[y], [&](int j) { return t[(size_t)j * W]; }, [&](int j) { return __ldg(wt + (size_t)j * p.H); }));
+    }
+    __syncthreads();
+
+    // ---- height pass + clamp/round/cast: thread = 4 adjacent columns of one output row
+    uint8_t* out = p.dst + (size_t)plane * p.H * p.W;
+    const bool vec = (p.W & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 3) == 0;
+    const int TW4 = TW >> 2;
+    for (int idx = threadIdx.x; idx < (y1 - y0) * TW4; idx += RS_THREADS) {
+        const int yl = idx / TW4, xl = (idx - yl * TW4) << 2;
+        if (X0 + xl >= X1) continue;
+        const int y = y0 + yl;
+        const int n = __ldg(p.n_h + y);
+        const float* t = tile + (size_t)(__ldg(p.xmin_h + y) - r0) * TW + xl;
+        const float* wc = wts_h + yl;
+        float a[4] = {0.f, 0.f, 0.f, 0.f};
+        if (n > 0) {
+            const int unfused = ((n - 1) >> 2) << 2;
+            const float4 v0 = *reinterpret_cast<const float4*>(t);
+            const float w0 = wc[0];
+            a[0] = __fmul_rn(v0.x, w0); a[1] = __fmul_rn(v0.y, w0); a[2] = __fmul_rn(v0.z, w0); a[3] = __fmul_rn(v0.w, w0);
+            int j = 1;
+            for (; j <= unfused; ++j) {
+                const float4 v = *reinterpret_cast<const float4*>(t + (size_t)j * TW);
+                const float wj = wc[j * p.th];
+                a[0] = __fadd_rn(a[0], __fmul_rn(v.x, wj)); a[1] = __fadd_rn(a[1], __fmul_rn(v.y, wj));
+                a[2] = __fadd_rn(a[2], __fmul_rn(v.z, wj)); a[3] = __fadd_rn(a[3], __fmul_rn(v.w, wj));
+            }
+            for (; j < n; ++j) {
+                const float4 v = *reinterpret_cast<const float4*>(t + (size_t)j * TW);
+                const float wj = wc[j * p.th];
+                a[0] = __fmaf_rn(v.x, wj, a[0]); a[1] = __fmaf_rn(v.y, wj, a[1]);
+                a[2] = __fmaf_rn(v.z, wj, a[2]); a[3] = __fmaf_rn(v.w, wj, a[3]);
+            }
+        }
+        uint8_t* o = out + (size_t)y * p.W + X0 + xl;
+        if (vec && X0 + xl + 4 <= X1) {
+            *reinterpret_cast<uint32_t*>(o) = to_u8(a[0]) | (to_u8(a[1]) << 8) | (to_u8(a[2]) << 16) | (to_u8(a[3]) << 24);
+        } else {
+            for (int c = 0; c < 4 && X0 + xl + c < X1; ++c) o[c] = (uint8_t)to_u8(a[c]);
         }
     }
 }
@@ -178,10 +249,10 @@ __global__ void __launch_bounds__(256) resize_bicubic_aa_u8_kernel(const ResizeP
 struct ResizePlan {
     int h, w, H, W;
     int taps_w, taps_h;
-    int th, max_rows;
+    int th, tw, max_rows, stride, row_tiles, col_tiles;
     size_t smem;
-    void* dev = nullptr;  // one allocation: xmin_w, n_w, xmin_h, n_h, wt_w, wt_h
-    const int32_t *xmin_w, *n_w, *xmin_h, *n_h;
+    void* dev = nullptr;  // one allocation: all int tables, then both weight tables
+    const int32_t *xmin_w, *n_w, *xmin_h, *n_h, *col_c0, *col_len, *row_r0, *row_nr;
     const float *wt_w, *wt_h;
 };
 
@@ -189,53 +260,74 @@ static SmemAttrOnce g_resize_smem;
 
 ResizePlan* resize_plan_create(int h, int w, int H, int W, int th_override) {
     if (h <= 0 || w <= 0 || H <= 0 || W <= 0 || w > (1 << 15) || h > (1 << 15) || W > (1 << 14) || H > (1 << 14)) return nullptr;
-    const int tw = resize_aa_taps(w, W), thh = resize_aa_taps(h, H);
+    const int tw_taps = resize_aa_taps(w, W), th_taps = resize_aa_taps(h, H);
     std::vector<int32_t> xw(W), nw(W), xh(H), nh(H);
-    std::vector<float> ww((size_t)tw * W), wh((size_t)thh * H);
+    std::vector<float> ww((size_t)tw_taps * W), wh((size_t)th_taps * H);
     if (resize_aa_table(w, W, xw.data(), nw.data(), ww.data()) || resize_aa_table(h, H, xh.data(), nh.data(), wh.data()))
         return nullptr;
-    // rows per CTA: the largest of 16/8/4/2/1 whose tile fits ~100 KB (two CTAs per SM), else whatever fits 227 KB
-    auto rows_needed = [&](int th) {
-        int m = 0;
+    // column tiles: 128 output columns (64 when the output is narrow: more CTAs), multiples of 4 for the float4 height pass
+    const int TW = W <= 64 ? 64 : 128;
+    const int col_tiles = (W + TW - 1) / TW;
+    std::vector<int32_t> cc0(col_tiles), clen(col_tiles);
+    int max_seg = 1;
+    for (int ct = 0; ct < col_tiles; ++ct) {
+        int lo = xw[ct * TW], hi = lo;
+        for (int X = ct * TW; X < std::min((ct + 1) * TW, W); ++X) { lo = std::min(lo, xw[X]); hi = std::max(hi, xw[X] + nw[X]); }
+        cc0[ct] = lo; clen[ct] = std::max(hi - lo, 1);
+        max_seg = std::max(max_seg, clen[ct]);
+    }
+    const int stride = ((max_seg + 30) >> 4) << 4;
+    auto row_windows = [&](int th, std::vector<int32_t>& r0s, std::vector<int32_t>& nrs) {
+        int m = 1;
+        r0s.clear(); nrs.clear();
         for (int y0 = 0; y0 < H; y0 += th) {
-            int r1 = xh[y0];
-            for (int y = y0; y < std::min(y0 + th, H); ++y) r1 = std::max(r1, xh[y] + nh[y]);
-            m = std::max(m, r1 - xh[y0]);
+            int lo = xh[y0], hi = lo;
+            for (int y = y0; y < std::min(y0 + th, H); ++y) { lo = std::min(lo, xh[y]); hi = std::max(hi, xh[y] + nh[y]); }
+            r0s.push_back(lo); nrs.push_back(std::max(hi - lo, 1));
+            m = std::max(m, hi - lo);
         }
         return m;
     };
-    auto smem_bytes = [&](int rows) { return (((size_t)rows * W * 4 + 15) & ~(size_t)15) + (size_t)rows * w + 32; };
+    auto smem_bytes = [&](int th, int rows) {
+        return ((size_t)rows * TW + (size_t)tw_taps * TW + (size_t)th_taps * th + rows) * 4 + 16 + (size_t)rows * stride;
+    };
+    // rows per CTA: the largest of 16/8/4/2/1 whose tile leaves room for 4 CTAs per SM (~56 KB), else 2 (~110 KB), else 1
+    std::vector<int32_t> rr0, rnr;
     int best = 0;
     const int cands[5] = {16, 8, 4, 2, 1};
+    const size_t limits[3] = {56 * 1024, 110 * 1024, 227 * 1024};
     if (th_override > 0) {
-        if (smem_bytes(rows_needed(th_override)) <= 227 * 1024) best = th_override;
+        if (smem_bytes(th_override, row_windows(th_override, rr0, rnr)) <= limits[2]) best = th_override;
     } else {
-        for (int c : cands)
-            if (smem_bytes(rows_needed(c)) <= 100 * 1024) { best = c; break; }
-        if (!best)
+        for (size_t lim : limits) {
             for (int c : cands)
-                if (smem_bytes(rows_needed(c)) <= 227 * 1024) { best = c; break; }
+                if (smem_bytes(c, row_windows(c, rr0, rnr)) <= lim) { best = c; break; }
+            if (best) break;
+        }
     }
     if (!best) return nullptr;  // a single output row's window does not fit in shared memory
     ResizePlan* pl = new ResizePlan();
     pl->h = h; pl->w = w; pl->H = H; pl->W = W;
-    pl->taps_w = tw; pl->taps_h = thh;
-    pl->th = best;
-    pl->max_rows = rows_needed(best);
-    pl->smem = (smem_bytes(pl->max_rows) + 15) & ~(size_t)15;
-    const size_t ints = (size_t)2 * W + 2 * H;
-    const size_t bytes = ints * 4 + ((size_t)tw * W + (size_t)thh * H) * 4;
+    pl->taps_w = tw_taps; pl->taps_h = th_taps;
+    pl->th = best; pl->tw = TW; pl->stride = stride;
+    pl->max_rows = row_windows(best, rr0, rnr);
+    pl->row_tiles = (int)rr0.size(); pl->col_tiles = col_tiles;
+    pl->smem = (smem_bytes(best, pl->max_rows) + 15) & ~(size_t)15;
+    std::vector<int32_t> ints;
+    auto put = [&](const std::vector<int32_t>& v) { size_t o = ints.size(); ints.insert(ints.end(), v.begin(), v.end()); return o; };
+    const size_t o_xw = put(xw), o_nw = put(nw), o_xh = put(xh), o_nh = put(nh), o_c0 = put(cc0), o_cl = put(clen), o_r0 = put(rr0),
+                 o_rn = put(rnr);
+    const size_t bytes = ints.size() * 4 + (ww.size() + wh.size()) * 4;
     if (cudaMalloc(&pl->dev, bytes) != cudaSuccess) { delete pl; return nullptr; }
     std::vector<uint8_t> host(bytes);
-    int32_t* ip = reinterpret_cast<int32_t*>(host.data());
-    memcpy(ip, xw.data(), (size_t)W * 4); memcpy(ip + W, nw.data(), (size_t)W * 4);
-    memcpy(ip + 2 * W, xh.data(), (size_t)H * 4); memcpy(ip + 2 * W + H, nh.data(), (size_t)H * 4);
-    float* fp = reinterpret_cast<float*>(ip + ints);
+    memcpy(host.data(), ints.data(), ints.size() * 4);
+    float* fp = reinterpret_cast<float*>(host.data() + ints.size() * 4);
     memcpy(fp, ww.data(), ww.size() * 4); memcpy(fp + ww.size(), wh.data(), wh.size() * 4);
     if (cudaMemcpy(pl->dev, host.data(), bytes, cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(pl->dev); delete pl; return nullptr; }
     const int32_t* dip = reinterpret_cast<const int32_t*>(pl->dev);
-    pl->xmin_w = dip; pl->n_w = dip + W; pl->xmin_h = dip + 2 * W; pl->n_h = dip + 2 * W + H;
-    const float* dfp = reinterpret_cast<const float*>(dip + ints);
+    pl->xmin_w = dip + o_xw; pl->n_w = dip + o_nw; pl->xmin_h = dip + o_xh; pl->n_h = dip + o_nh;
+    pl->col_c0 = dip + o_c0; pl->col_len = dip + o_cl; pl->row_r0 = dip + o_r0; pl->row_nr = dip + o_rn;
+    const float* dfp = reinterpret_cast<const float*>(dip + ints.size());
     pl->wt_w = dfp; pl->wt_h = dfp + ww.size();
     return pl;
 }
@@ -253,17 +345,20 @@ void resize_plan_info(const ResizePlan* pl, int* th, int* max_rows, int64_t* sme
 }
 
 int resize_bicubic_aa_u8(const ResizePlan* pl, const uint8_t* src, int planes, uint8_t* dst, cudaStream_t s) {
-    if (!pl || planes <= 0 || planes > 65535) return -1;
+    if (!pl || planes <= 0 || planes > 65535 || pl->row_tiles > 65535) return -1;
     if (ensure_dyn_smem(g_resize_smem, resize_bicubic_aa_u8_kernel, 227 * 1024)) return -2;
     ResizeParams p;
     p.src = src; p.dst = dst;
+    p.src_bytes = (size_t)planes * pl->h * pl->w;
     p.h = pl->h; p.w = pl->w; p.H = pl->H; p.W = pl->W;
+    p.taps_w = pl->taps_w; p.taps_h = pl->taps_h;
     p.xmin_w = pl->xmin_w; p.n_w = pl->n_w; p.wt_w = pl->wt_w;
     p.xmin_h = pl->xmin_h; p.n_h = pl->n_h; p.wt_h = pl->wt_h;
-    p.th = pl->th; p.max_rows = pl->max_rows;
-    dim3 grid((pl->H + pl->th - 1) / pl->th, planes);
+    p.col_c0 = pl->col_c0; p.col_len = pl->col_len; p.row_r0 = pl->row_r0; p.row_nr = pl->row_nr;
+    p.th = pl->th; p.tw = pl->tw; p.max_rows = pl->max_rows; p.stride = pl->stride;
+    dim3 grid(pl->col_tiles, pl->row_tiles, planes);
     count_launch();
-    resize_bicubic_aa_u8_kernel<<<grid, 256, pl->smem, s>>>(p);
+    resize_bicubic_aa_u8_kernel<<<grid, RS_THREADS, pl->smem, s>>>(p);
     return 0;
 }
 

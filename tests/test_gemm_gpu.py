@@ -18,7 +18,7 @@ def _ints(shape, lo, hi, seed):
     return torch.randint(lo, hi + 1, shape, device="cuda", generator=g).to(torch.bfloat16)
 
 
-@pytest.mark.parametrize("block_n", [0, 64, 128, 256])
+@pytest.mark.parametrize("block_n", [0, 32, 48, 64, 80, 112, 128, 144, 176, 208, 224, 240, 256])
 @pytest.mark.parametrize("M,N,K", SHAPES)
 def test_gemm_exact_integer_operands(ctx, M, N, K, block_n):
     a = _ints((M, K), -2, 2, 1)
@@ -86,6 +86,33 @@ def test_gemm_swiglu(ctx, M, I, K):
     out = ctx.gemm(a, interleave_gate_up(wg, wu), epilogue=A.EPI_SWIGLU)
     assert out.shape == (M, I)
     assert _close(out, ref) < 1e-3
+
+
+@pytest.mark.parametrize("block_n", [32, 96, 160, 224])
+def test_gemm_swiglu_every_tile_width(ctx, block_n):
+    """The N tile is a run-time value (multiples of 32 for the SwiGLU epilogue): every width gives the same bits as 256."""
+    from livecc_b200.checkpoint import interleave_gate_up
+
+    g = torch.Generator(device="cuda").manual_seed(18)
+    M, I, K = 281, 1184, 512
+    a = torch.randn((M, K), device="cuda", generator=g).to(torch.bfloat16)
+    w = interleave_gate_up((torch.randn((I, K), device="cuda", generator=g) * 0.03).to(torch.bfloat16),
+                           (torch.randn((I, K), device="cuda", generator=g) * 0.03).to(torch.bfloat16))
+    assert torch.equal(ctx.gemm(a, w, epilogue=A.EPI_SWIGLU, block_n=block_n), ctx.gemm(a, w, epilogue=A.EPI_SWIGLU, block_n=256))
+
+
+@pytest.mark.parametrize("block_n", [48, 80, 144, 240])
+def test_gemm_epilogues_every_tile_width(ctx, block_n):
+    """Bias / activation / residual epilogues with a half-used last 32-column chunk (block_n % 32 == 16) and a ragged N."""
+    g = torch.Generator(device="cuda").manual_seed(19)
+    M, N, K = 300, 1096, 320
+    a = torch.randn((M, K), device="cuda", generator=g).to(torch.bfloat16)
+    b = (torch.randn((N, K), device="cuda", generator=g) * 0.05).to(torch.bfloat16)
+    bias = (torch.randn((N,), device="cuda", generator=g) * 0.1).to(torch.bfloat16)
+    res = torch.randn((M, N), device="cuda", generator=g).to(torch.bfloat16)
+    for epi, kw in [(A.EPI_BIAS, dict(bias=bias)), (A.EPI_BIAS_QUICKGELU, dict(bias=bias)), (A.EPI_BIAS_GELU, dict(bias=bias)),
+                    (A.EPI_RESIDUAL, dict(residual=res)), (A.EPI_BIAS_RESIDUAL, dict(bias=bias, residual=res))]:
+        assert torch.equal(ctx.gemm(a, b, epilogue=epi, block_n=block_n, **kw), ctx.gemm(a, b, epilogue=epi, block_n=256, **kw)), epi
 
 
 def test_gemm_strided_views(ctx):

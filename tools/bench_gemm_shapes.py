@@ -47,7 +47,19 @@ def run(name, iters=20, copies=8, block_n=0):
     us = e0.elapsed_time(e1) * 1e3 / iters
     flops = 2.0 * M * N * K
     wbytes = N * K * 2
-    print(f"{name:16s} bn={block_n:3d} M={M:5d} N={N:6d} K={K:6d}: {us:8.1f} us  {flops / us / 1e6:7.1f} TFLOP/s  weights {wbytes / us / 1e3:7.1f} GB/s",
+    ref = ""
+    if os.environ.get("CUBLAS"):  # the library GEMM (torch.matmul -> cuBLASLt, no fused epilogue) on the same operands
+        for w in ws:
+            torch.matmul(a, w.t())
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(iters):
+            torch.matmul(a, ws[i % copies].t())
+        e1.record()
+        torch.cuda.synchronize()
+        cu = e0.elapsed_time(e1) * 1e3 / iters
+        ref = f"  | cuBLAS plain GEMM {cu:7.1f} us {flops / cu / 1e6:7.1f} TFLOP/s"
+    print(f"{name:16s} bn={block_n:3d} M={M:5d} N={N:6d} K={K:6d}: {us:8.1f} us  {flops / us / 1e6:7.1f} TFLOP/s  weights {wbytes / us / 1e3:7.1f} GB/s{ref}",
           flush=True)
 
 
@@ -57,7 +69,7 @@ if __name__ == "__main__":
         run(case, iters=2, copies=2)
     elif os.environ.get("SWEEP_BN"):
         for n in SHAPES:
-            for bn in (0, 64, 128, 256):
+            for bn in (0, 96, 128, 160, 192, 224, 256):
                 run(n, block_n=bn)
     else:
         for n in SHAPES:
