@@ -77,9 +77,10 @@ uint64_t lcc_launch_count(void);
  * Replaces every nn.Linear / Conv3d-as-GEMM call with M >= 16 on the path:
  * mq2vl.py:304-310 (patch embed), :385,:401-403,:456 (ViT qkv/proj), :329-337 (ViT MLP),
  * :317-326 (merger), :539-541,:559-565,:593 (decoder q/k/v/o), :502-504 (MLP).
- * K, N and all leading dimensions must be multiples of 8 elements. block_n (N tile): 0 = cost model, else a multiple of 16 in [32,256] (SwiGLU: of 32).
+ * K, N and all leading dimensions must be multiples of 8 elements. block_n (N tile): 0 = dispatch rule, else a multiple of 16 in [32,256] (SwiGLU: of 32);
+ * a negative value selects the CTA-pair kernel (cta_group::2, 256 x |block_n| tiles, |block_n| a multiple of 32).
  * splitk_ws: optional fp32 scratch (>= 8*M*N*4 bytes) that allows split-K for M <= 384 when the tile count cannot
- * occupy the SMs; only used when the process runs with LIVECC_B200_GEMM_SPLITK=1 (experimental). NULL = never. */
+ * occupy the SMs; used for K >= 8192 by default (LIVECC_B200_GEMM_SPLITK=1 forces it for every eligible shape, =0 disables). NULL = never. */
 int lcc_gemm_bf16(lcc_ctx* ctx, const void* A, int lda, const void* B, int ldb, void* C, int ldc,
                   int M, int N, int K, const void* bias, const void* residual, int ldr, int epilogue,
                   int block_n, void* splitk_ws, int64_t splitk_ws_bytes, lcc_stream_t stream);

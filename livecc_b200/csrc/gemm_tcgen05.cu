@@ -41,16 +41,16 @@ struct GemmTile {
     uint32_t idesc;  // tcgen05 instruction descriptor (M = 128, N = bn)
     int smem_bytes;
 };
-static GemmTile make_tile(int bn) {
+static GemmTile make_tile(int bn, bool pair = false) {
     GemmTile t;
     t.bn = bn;
-    const int stage_bytes = A_BYTES + bn * BLOCK_K * 2;
+    const int stage_bytes = A_BYTES + (pair ? bn / 2 : bn) * BLOCK_K * 2;
     t.stages = (227 * 1024 - 1024 - 256) / stage_bytes;
     if (t.stages > MAX_STAGES) t.stages = MAX_STAGES;
     int cols = 2 * bn + ((bn & 31) ? 16 : 0);
     t.tmem_cols = 32;
     while (t.tmem_cols < cols) t.tmem_cols <<= 1;
-    t.idesc = make_idesc_bf16(BLOCK_M, bn);
+    t.idesc = make_idesc_bf16(pair ? 2 * BLOCK_M : BLOCK_M, bn);
     t.smem_bytes = t.stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
     return t;
 }
@@ -302,6 +302,167 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
 }
 
 // ----------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): one 256 x BLOCK_N output tile per pair of CTAs on a TPC.
+// Each CTA stages ITS 128 rows of A and HALF of the B tile (BLOCK_N/2 rows) per k-block: shared-memory traffic per CTA and
+// k-block drops from 2*(16 KB + 128*bn) to 2*(16 KB + 64*bn) bytes, which lifts the shared-memory bound of the one-CTA
+// kernel (bn = 256: 768 -> 512 clocks per k-block = the tensor floor). The leader CTA (cluster rank 0) issues the MMAs for
+// both; accumulators live in both CTAs' TMEM (rows 0-127 in the leader, 128-255 in the peer), each CTA runs the epilogue of
+// its own rows. Barriers: `full` lives in the leader and is credited by both CTAs' TMA loads; `empty` and `tmem_full` exist
+// in both CTAs and are signalled by the leader's multicast commits; `tmem_empty` lives in the leader and counts the epilogue
+// warps of both CTAs.
+// ----------------------------------------------------------------------------
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
+gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, bf16* C, int M,
+                     int N, int K, int ldc, const bf16* __restrict__ bias, const bf16* residual /* may alias C */, int ldr,
+                     int splits_arg /* >= 1 */, const GemmTile cfg) {
+    const int splits = (EPI == EPI_PARTIAL_F32) ? splits_arg : 1;
+    const int BLOCK_N = cfg.bn;
+    const int HALF_N = BLOCK_N >> 1;
+    const int STAGE_BYTES = A_BYTES + HALF_N * BLOCK_K * 2;
+    const int STAGES = cfg.stages;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + MAX_STAGES;
+    uint64_t* tmem_full = empty_bar + MAX_STAGES;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+    const int m_pairs = (M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+    const int n_tiles = (N + BLOCK_N - 1) / BLOCK_N;
+    const int num_k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
+    const int num_units = m_pairs * n_tiles * splits;  // (m pair, k split, n tile), m fastest
+    const int kbps = (num_k_blocks + splits - 1) / splits;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tensormap(&tmap_a);
+        prefetch_tensormap(&tmap_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(&full_bar[i], 1);   // used in the leader: its producer's arrive.expect_tx (bytes of both CTAs)
+            mbar_init(&empty_bar[i], 1);  // one multicast commit of the leader's MMA warp
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full[i], 1);    // one multicast commit
+            mbar_init(&tmem_empty[i], 16);  // used in the leader: 8 epilogue warps of each CTA
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc_cg2(tmem_holder, cfg.tmem_cols);
+        tmem_relinquish_cg2();
+    }
+    tc_fence_before();
+    __syncwarp();        // barrier.cluster is .aligned: the warp must be converged
+    cluster_sync_all();  // barriers of BOTH CTAs are initialised before any remote arrive / TMA credit
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs) =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int unit = pair; unit < num_units; unit += num_pairs) {
+                const int m_pair = unit % m_pairs, ks = (unit / m_pairs) % splits, n_blk = unit / (m_pairs * splits);
+                const int kb0 = ks * kbps, kb1 = min(kb0 + kbps, num_k_blocks);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * STAGE_BYTES;
+                    uint8_t* sb = sa + A_BYTES;
+                    if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
+                    const uint32_t bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
+                    tma_load_2d_cg2(sa, &tmap_a, bar, kb * BLOCK_K, m_pair * 2 * BLOCK_M + (int)rank * BLOCK_M);
+                    tma_load_2d_cg2(sb, &tmap_b, bar, kb * BLOCK_K, n_blk * BLOCK_N + (int)rank * HALF_N);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (leader) {
+            const uint32_t idesc = cfg.idesc;  // M = 256, N = BLOCK_N
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int unit = pair; unit < num_units; unit += num_pairs) {
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+                const int ks = (unit / m_pairs) % splits;
+                const int kb0 = ks * kbps, kb1 = min(kb0 + kbps, num_k_blocks);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+                        const uint32_t sb = sa + A_BYTES;
+                        const uint64_t da = make_sw128_kmajor_desc(sa);
+                        const uint64_t db = make_sw128_kmajor_desc(sb);
+#pragma unroll
+                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                            umma_bf16_ss_cg2(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
+                                             ((kb - kb0) | k) != 0 ? 1u : 0u);
+                        umma_commit_cg2(&empty_bar[stage], 3);  // frees the slot in both CTAs when the MMAs retire
+                        if (kb == kb1 - 1) umma_commit_cg2(&tmem_full[acc], 3);
+                    }
+                    __syncwarp();
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== Epilogue (both CTAs, own 128 rows) =====================
+        const int q = warp & 3;
+        const int half = (warp - 4) >> 2;
+        const int chunks = (BLOCK_N + 31) >> 5;
+        const int chunks_h0 = (chunks + 1) >> 1;
+        const int c_begin = half ? chunks_h0 : 0, c_end = half ? chunks : chunks_h0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int unit = pair; unit < num_units; unit += num_pairs) {
+            const int m_pair = unit % m_pairs, ks = (unit / m_pairs) % splits, n_blk = unit / (m_pairs * splits);
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const int row = m_pair * 2 * BLOCK_M + (int)rank * BLOCK_M + q * 32 + lane;
+            const bool row_ok = row < M;
+            const int tile_end = min(N, (n_blk + 1) * BLOCK_N);
+#pragma unroll 1
+            for (int c = c_begin; c < c_end; ++c) {
+                uint32_t v[32];
+                const uint32_t taddr = tmem_base + (uint32_t)(acc * BLOCK_N + c * 32) + ((uint32_t)(q * 32) << 16);
+                tmem_ld_32x32b_x32(taddr, v);
+                tmem_ld_wait();
+                const int col0 = n_blk * BLOCK_N + c * 32;
+                epilogue_chunk<EPI>(v, C, ldc, M, row, row_ok, col0, tile_end, ks, bias, residual, ldr);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[acc]), 0));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncwarp();        // lanes that skipped a single-lane role loop wait here for their lane 0
+    cluster_sync_all();  // neither CTA may exit (or free TMEM) while the pair's MMAs / remote arrives can still touch it
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_cg2(tmem_base, cfg.tmem_cols);
+    }
+}
+
+// ----------------------------------------------------------------------------
 // Host side
 // ----------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -376,6 +537,38 @@ static int launch_cfg(const GemmArgs& a, int bn, int num_sms, cudaStream_t strea
                                                 (const bf16*)a.bias, (const bf16*)a.residual,
                                                 a.ldr, splits, cfg);
     return cudaGetLastError() == cudaSuccess ? 0 : -13;
+}
+
+template <int EPI>
+static int launch_cfg2(const GemmArgs& a, int bn, int num_sms, cudaStream_t stream) {
+    const GemmTile cfg = make_tile(bn, true);
+    CUtensorMap ta, tb;
+    if (make_tmap_bf16_2d(&ta, a.A, a.M, a.K, a.lda, BLOCK_M)) return -10;
+    if (make_tmap_bf16_2d(&tb, a.B, a.N, a.K, a.ldb, bn / 2)) return -11;
+    auto kern = gemm2_bf16_tn_kernel<EPI>;
+    static SmemAttrOnce once;
+    if (ensure_dyn_smem(once, kern, 227 * 1024)) return -12;
+    const int m_pairs = (a.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M), n_tiles = (a.N + bn - 1) / bn;
+    const int splits = (EPI == EPI_PARTIAL_F32 && a.splits > 1) ? a.splits : 1;
+    const int units = m_pairs * n_tiles * splits;
+    const int pairs = units < num_sms / 2 ? units : num_sms / 2;
+    lcc::count_launch();
+    kern<<<2 * pairs, 384, cfg.smem_bytes, stream>>>(ta, tb, (bf16*)a.C, a.M, a.N, a.K, a.ldc, (const bf16*)a.bias,
+                                                     (const bf16*)a.residual, a.ldr, splits, cfg);
+    return cudaGetLastError() == cudaSuccess ? 0 : -13;
+}
+
+static int launch_epi2(const GemmArgs& a, int bn, int num_sms, cudaStream_t stream) {
+    switch (a.epi) {
+        case EPI_NONE: return launch_cfg2<EPI_NONE>(a, bn, num_sms, stream);
+        case EPI_BIAS: return launch_cfg2<EPI_BIAS>(a, bn, num_sms, stream);
+        case EPI_BIAS_QUICKGELU: return launch_cfg2<EPI_BIAS_QUICKGELU>(a, bn, num_sms, stream);
+        case EPI_BIAS_GELU: return launch_cfg2<EPI_BIAS_GELU>(a, bn, num_sms, stream);
+        case EPI_RESIDUAL: return launch_cfg2<EPI_RESIDUAL>(a, bn, num_sms, stream);
+        case EPI_BIAS_RESIDUAL: return launch_cfg2<EPI_BIAS_RESIDUAL>(a, bn, num_sms, stream);
+        case EPI_SWIGLU: return launch_cfg2<EPI_SWIGLU>(a, bn, num_sms, stream);
+    }
+    return -14;
 }
 
 static int launch_epi(const GemmArgs& a, int bn, int num_sms, cudaStream_t stream) {
@@ -516,7 +709,11 @@ int gemm_bf16_tn(const GemmArgs& a, int num_sms, cudaStream_t stream) {
         }
         block_n = forced > 0 ? forced : choose_bn(a.M, a.N, num_sms);
     }
+    // block_n < 0 selects the CTA-pair kernel with tile width -block_n (explicit: tests and tuning)
+    const bool pair = block_n < 0;
+    if (pair) block_n = -block_n;
     if (block_n < 32 || block_n > 256 || (block_n % 16) || (a.epi == EPI_SWIGLU && (block_n % 32))) return -6;
+    if (pair) return (block_n % 32) ? -6 : launch_epi2(a, block_n, num_sms, stream);
     return launch_epi(a, block_n, num_sms, stream);
 }
 

@@ -18,7 +18,7 @@ def _ints(shape, lo, hi, seed):
     return torch.randint(lo, hi + 1, shape, device="cuda", generator=g).to(torch.bfloat16)
 
 
-@pytest.mark.parametrize("block_n", [0, 32, 48, 64, 80, 112, 128, 144, 176, 208, 224, 240, 256])
+@pytest.mark.parametrize("block_n", [0, 32, 48, 64, 80, 112, 128, 144, 176, 208, 224, 240, 256, -64, -96, -128, -160, -224, -256])
 @pytest.mark.parametrize("M,N,K", SHAPES)
 def test_gemm_exact_integer_operands(ctx, M, N, K, block_n):
     a = _ints((M, K), -2, 2, 1)
@@ -88,9 +88,10 @@ def test_gemm_swiglu(ctx, M, I, K):
     assert _close(out, ref) < 1e-3
 
 
-@pytest.mark.parametrize("block_n", [32, 96, 160, 224])
+@pytest.mark.parametrize("block_n", [32, 96, 160, 224, -64, -160, -256])
 def test_gemm_swiglu_every_tile_width(ctx, block_n):
-    """The N tile is a run-time value (multiples of 32 for the SwiGLU epilogue): every width gives the same bits as 256."""
+    """The N tile is a run-time value (multiples of 32 for the SwiGLU epilogue): every width gives the same bits as 256.
+    Negative widths select the CTA-pair kernel (cta_group::2, 256 x |block_n| tiles)."""
     from livecc_b200.checkpoint import interleave_gate_up
 
     g = torch.Generator(device="cuda").manual_seed(18)
@@ -101,7 +102,7 @@ def test_gemm_swiglu_every_tile_width(ctx, block_n):
     assert torch.equal(ctx.gemm(a, w, epilogue=A.EPI_SWIGLU, block_n=block_n), ctx.gemm(a, w, epilogue=A.EPI_SWIGLU, block_n=256))
 
 
-@pytest.mark.parametrize("block_n", [48, 80, 144, 240])
+@pytest.mark.parametrize("block_n", [48, 80, 144, 240, -96, -192, -256])
 def test_gemm_epilogues_every_tile_width(ctx, block_n):
     """Bias / activation / residual epilogues with a half-used last 32-column chunk (block_n % 32 == 16) and a ragged N."""
     g = torch.Generator(device="cuda").manual_seed(19)

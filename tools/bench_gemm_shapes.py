@@ -20,6 +20,8 @@ SHAPES = {
     "vit_fc1": (1024, 5120, 1280, A.EPI_BIAS_QUICKGELU),
     "vit_fc2": (1024, 1280, 5120, A.EPI_BIAS_RESIDUAL),
     "vit_fc1_3072": (3072, 5120, 1280, A.EPI_BIAS_QUICKGELU),
+    "vit_fc1_8192": (8192, 5120, 1280, A.EPI_BIAS_QUICKGELU),
+    "mcq_gateup_2090": (2090, 37888, 3584, A.EPI_SWIGLU),
 }
 
 
@@ -69,8 +71,11 @@ if __name__ == "__main__":
         run(case, iters=2, copies=2)
     elif os.environ.get("SWEEP_BN"):
         for n in SHAPES:
-            for bn in (0, 96, 128, 160, 192, 224, 256):
-                run(n, block_n=bn)
+            for bn in [int(x) for x in os.environ.get('BNS', '0,128,256,-128,-160,-192,-224,-256').split(',')]:
+                try:
+                    run(n, block_n=bn)
+                except A.LiveCCNativeError as ex:
+                    print(f"{n:16s} bn={bn:3d}: rejected ({str(ex)[:60]})", flush=True)
     else:
         for n in SHAPES:
             run(n)
