@@ -98,6 +98,8 @@ class LiveCCB200ForConditionalGeneration:
         self._captured_launches = 0   # launches recorded into graphs (counted by the library at capture, never executed then)
         self._replayed_launches = 0   # kernel nodes executed through graph replays
         self.use_cuda_graph = os.environ.get("LIVECC_B200_NO_GRAPH", "0") != "1"
+        self.use_vit_graph = self.use_cuda_graph and os.environ.get("LIVECC_B200_VIT_GRAPH", "1") != "0"
+        self._vit_graphs = {}
         # split-KV factor of the decode attention: at most one CTA per SM, at least ~8 KV tiles (512 tokens) per split
         self.max_nsplit = max(1, min(64, (self.ctx.num_sms + t.num_key_value_heads - 1) // t.num_key_value_heads))
         self.nsplit = self.max_nsplit
@@ -168,6 +170,34 @@ class LiveCCB200ForConditionalGeneration:
         torch.cuda.synchronize(self.device)
         self._native.bind_workspace(self._cap_patches, self._cap_tokens, self.device)
         self._graphs = {}
+        self._vit_graphs = {}  # captured against the old workspace pointers
+
+    # fixed-shape ViT passes (the 2-frame streaming chunk, the 6-frame opening chunk) are replayed from a CUDA graph: ~260
+    # launches per 1024 patches, many of them a few microseconds long
+    VIT_GRAPH_MAX_PATCHES = 3072
+
+    def _vit_replay(self, key, src: torch.Tensor, n_out_rows: int, launch):
+        """`launch(static_src, static_out)` is captured once per (kind, shape); later calls copy `src` into the static input
+        and replay. Returns the STATIC output buffer (valid until the next pass of the same shape)."""
+        ent = self._vit_graphs.get(key)
+        if ent is None:
+            static_src = torch.empty_like(src)
+            static_out = torch.empty((n_out_rows, self.config.vision_config.hidden_size), dtype=torch.bfloat16, device=self.device)
+            static_src.copy_(src)
+            launch(static_src, static_out)  # eager once: kernel attributes, lazy module loading
+            torch.cuda.synchronize(self.device)
+            graph = torch.cuda.CUDAGraph()
+            n0 = _cabi.launch_count()
+            with torch.cuda.graph(graph):
+                launch(static_src, static_out)
+            graph.lcc_nodes = _cabi.launch_count() - n0
+            self._captured_launches += graph.lcc_nodes
+            ent = self._vit_graphs[key] = (graph, static_src, static_out)
+        graph, static_src, static_out = ent
+        static_src.copy_(src, non_blocking=True)
+        graph.replay()
+        self._replayed_launches += graph.lcc_nodes
+        return static_out
 
     # ------------------------------------------------------------------------------------------
     # HF-surface helpers
@@ -202,7 +232,7 @@ class LiveCCB200ForConditionalGeneration:
     # the hot path
     # ------------------------------------------------------------------------------------------
     @torch.inference_mode()
-    def get_video_features(self, pixel_values_videos: torch.Tensor, video_grid_thw: torch.Tensor) -> torch.Tensor:
+    def get_video_features(self, pixel_values_videos: torch.Tensor, video_grid_thw: torch.Tensor, _static_ok: bool = False) -> torch.Tensor:
         """ViT + merger for the videos of one call (mq2vl.py:1094-1112): [sum t*h*w, 1176] f32 -> [n_tok, H] bf16."""
         grids = video_grid_thw.tolist() if isinstance(video_grid_thw, torch.Tensor) else list(video_grid_thw)
         v = self.config.vision_config
@@ -212,6 +242,10 @@ class LiveCCB200ForConditionalGeneration:
             raise ValueError(f"pixel_values_videos has shape {tuple(pixel_values_videos.shape)}, expected {(n_rows, v.patch_dim)}")
         px = pixel_values_videos.to(device=self.device, dtype=torch.float32, non_blocking=True).contiguous()
         self._ensure_workspace(max(t * h * w for t, h, w in grids), 0)
+        if self.use_vit_graph and len(grids) == 1 and n_rows <= self.VIT_GRAPH_MAX_PATCHES:
+            t, h, w = grids[0]
+            out = self._vit_replay(("rows", t, h, w), px, n_rows // m2, lambda a, b: self._native.vit_forward(a, t, h, w, b))
+            return out if _static_ok else out.clone()
         out = torch.empty((n_rows // m2, v.hidden_size), dtype=torch.bfloat16, device=self.device)
         r0 = 0
         for t, h, w in grids:
@@ -221,7 +255,7 @@ class LiveCCB200ForConditionalGeneration:
         return out
 
     @torch.inference_mode()
-    def get_video_features_from_frames(self, frames: torch.Tensor) -> torch.Tensor:
+    def get_video_features_from_frames(self, frames: torch.Tensor, _static_ok: bool = False) -> torch.Tensor:
         """GPU frame ingest: uint8 [T,3,H,W] (H, W multiples of 28) -> [n_tok, H] bf16; the processor's
         rescale/normalize/patchify and the bf16 cast run fused in front of the patch-embed GEMM. Bit-identical to
         get_video_features(patchify_video(frames))."""
@@ -239,7 +273,11 @@ class LiveCCB200ForConditionalGeneration:
         # the processor's fused constants (image_processing_backends.py:301-304): fp32(mean) * (1 / (1/255))
         mean255 = (torch.tensor(OPENAI_CLIP_MEAN) * (1.0 / (1 / 255))).tolist()
         std255 = (torch.tensor(OPENAI_CLIP_STD) * (1.0 / (1 / 255))).tolist()
-        out = torch.empty((t * h * w // v.spatial_merge_size ** 2, v.hidden_size), dtype=torch.bfloat16, device=self.device)
+        n_out = t * h * w // v.spatial_merge_size ** 2
+        if self.use_vit_graph and t * h * w <= self.VIT_GRAPH_MAX_PATCHES:
+            out = self._vit_replay(("frames", T, H, W), fr, n_out, lambda a, b: self._native.vit_forward_frames(a, mean255, std255, b))
+            return out if _static_ok else out.clone()
+        out = torch.empty((n_out, v.hidden_size), dtype=torch.bfloat16, device=self.device)
         self._native.vit_forward_frames(fr, mean255, std255, out)
         return out
 
@@ -464,10 +502,10 @@ class LiveCCB200ForConditionalGeneration:
         if pixel_values_videos is not None:
             if video_grid_thw is None:
                 raise ValueError("video_grid_thw is required with pixel_values_videos")
-            video_embeds = self.get_video_features(pixel_values_videos, video_grid_thw)
+            video_embeds = self.get_video_features(pixel_values_videos, video_grid_thw, _static_ok=True)  # consumed by this prefill
             n_video_expected = video_embeds.shape[0]
         elif video_frames is not None:
-            video_embeds = self.get_video_features_from_frames(video_frames)
+            video_embeds = self.get_video_features_from_frames(video_frames, _static_ok=True)
             n_video_expected = video_embeds.shape[0]
         if timed:
             self._ev[1].record()

@@ -231,6 +231,31 @@ def test_gpu_frame_ingest_is_bit_identical(small):
     assert all(torch.equal(x, y) for x, y in zip(o1.logits, o2.logits))
 
 
+def test_vit_graph_replay_is_bit_identical_to_eager_launches(small):
+    """Fixed-shape ViT passes are replayed from a CUDA graph (one capture per shape): same bits as eager launches, for both
+    input kinds, across different inputs of the same shape and after a workspace re-bind."""
+    cfg, sd, eng, rs = small
+    from livecc_b200.processing import patchify_video
+
+    assert eng.use_vit_graph
+    clips = [torch.randint(0, 256, (2, 3, 112, 112), generator=torch.Generator().manual_seed(40 + i), dtype=torch.uint8) for i in range(3)]
+    try:
+        eng.use_vit_graph = False
+        want_f = [eng.get_video_features_from_frames(c.to(DEV)).clone() for c in clips]
+        want_r = [eng.get_video_features(*[x.to(DEV) if i == 0 else x for i, x in enumerate(patchify_video(c))]).clone() for c in clips]
+    finally:
+        eng.use_vit_graph = True
+    for rep in range(2):
+        got_f = [eng.get_video_features_from_frames(c.to(DEV)) for c in clips]   # public call: a copy, not the static buffer
+        got_r = [eng.get_video_features(patchify_video(c)[0].to(DEV), patchify_video(c)[1]) for c in clips]
+        torch.cuda.synchronize()
+        assert all(torch.equal(a, b) for a, b in zip(got_f, want_f)) and all(torch.equal(a, b) for a, b in zip(got_r, want_r))
+        assert ("frames", 2, 112, 112) in eng._vit_graphs and any(k[0] == "rows" for k in eng._vit_graphs)
+        if rep == 0:
+            eng._ensure_workspace(eng._cap_patches + 64, 0)   # re-bind: graphs captured on the old pointers are dropped
+            assert not eng._vit_graphs
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # the production decode path (CUDA-graph replay) is asserted, not printed
 # ---------------------------------------------------------------------------------------------------------------
