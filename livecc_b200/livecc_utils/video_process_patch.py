@@ -324,8 +324,9 @@ def get_smart_resized_clip(video_reader, resized_height: int, resized_width: int
     if odd:  # the reference trims the timestamps only by the frames dropped for evenness (not to the clip length)
         timestamps = timestamps[:-odd]
     clip = torch.from_numpy(video_reader.get_batch(clip_idxs).asnumpy())
-    if device is not None and torch.device(device).type == "cuda" and clip.numel() and \
-            tuple(clip.shape[1:3]) != (resized_height, resized_width):
+    if device is not None and torch.device(device).type == "cuda" and clip.numel():
+        # decoded THWC bytes go up as they are (pinned staging, async copy); the layout change to TCHW and the resize run
+        # on the device (on the host the strided TCHW copy alone costs as much as the upload)
         clip = clip.pin_memory().to(device, non_blocking=True)
     clip = clip.permute(0, 3, 1, 2)  # THWC -> TCHW
     if clip.shape[0] == 3 and clip.shape[1] == len(clip_idxs):  # a reader that returns channel-first batches

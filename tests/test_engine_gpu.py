@@ -231,6 +231,51 @@ def test_gpu_frame_ingest_is_bit_identical(small):
     assert all(torch.equal(x, y) for x, y in zip(o1.logits, o2.logits))
 
 
+def test_streaming_with_gpu_frame_ingest_equals_host_ingest(small):
+    """LiveCCDemoInfer.live_cc over a source that NEEDS resizing (112x140 -> 252x336, video_process_patch.py:150-155), driven
+    like REF/demo/cli.py: decoded frames uploaded as uint8 + GPU resize + fused normalize/patchify (gpu_ingest) must give the same
+    spans, token ids and cache lengths as the host torchvision resize feeding the same engine, and must actually launch the
+    resize kernel."""
+    cfg, sd, eng, rs = small
+    from livecc_b200 import _cabi
+    from livecc_b200.livecc_utils import video_process_patch as vpp
+    from livecc_b200.streaming import LiveCCDemoInfer
+
+    def run(gpu_ingest):
+        infer = LiveCCDemoInfer(model=eng, processor=StubProcessor(cfg, emit_frames=True), gpu_ingest=gpu_ingest)
+        state = {"video_path": "synthetic://180x112x140@30?seed=9"}
+        outs = []
+        for t in range(8):
+            state["video_timestamp"] = t
+            for (s0, e0), resp, state in infer.live_cc(message="Please describe the video.", state=state, repetition_penalty=1.05,
+                                                       do_sample=False, max_new_tokens=6):
+                outs.append((s0, e0, resp, state["past_key_values"].get_seq_length()))
+            if state.get("video_end", False):
+                break
+        ids = state["past_ids"][0].tolist()
+        state["past_key_values"].release()
+        return outs, ids
+
+    calls = []
+    orig = _cabi.Context.resize_bicubic_aa_u8
+
+    def spy(self, clip, size, **kw):
+        calls.append((tuple(clip.shape), tuple(size)))
+        return orig(self, clip, size, **kw)
+
+    _cabi.Context.resize_bicubic_aa_u8 = spy
+    try:
+        host_outs, host_ids = run(False)
+        assert not calls
+        gpu_outs, gpu_ids = run(True)
+    finally:
+        _cabi.Context.resize_bicubic_aa_u8 = orig
+    assert calls and calls[0] == ((6, 3, 112, 140), (252, 336)) and all(c[0][0] == 2 for c in calls[1:])
+    assert len(host_outs) >= 4 and [o[:2] for o in host_outs] == [o[:2] for o in gpu_outs]
+    if torch.backends.cpu.get_cpu_capability() == "AVX512":  # the ATen build the resize's rounding order is pinned on
+        assert host_outs == gpu_outs and host_ids == gpu_ids
+
+
 def test_vit_graph_replay_is_bit_identical_to_eager_launches(small):
     """Fixed-shape ViT passes are replayed from a CUDA graph (one capture per shape): same bits as eager launches, for both
     input kinds, across different inputs of the same shape and after a workspace re-bind."""
