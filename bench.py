@@ -476,9 +476,9 @@ def run_hf_gpu(args, cfg, config, dev):
 # ------------------------------------------------------------------------------------------------
 def main():
     args = parse_args()
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    from livecc_b200 import runner  # the repo's own multi-GPU plumbing (rank env, NCCL init, barrier + device sync)
+
+    rank, world, local_rank = runner.dist_env()
     cfg = get_config(args.model)
     workload = (f"LiveCC-{'7B' if args.model == '7b' else 'small'} streaming 2fps {args.seconds}s clip "
                 f"({args.seconds * 2} frames) {args.size}x{args.size} greedy decode bf16, one stream per GPU")
@@ -506,10 +506,9 @@ def main():
     dev = torch.device("cuda", local_rank)
     if args.impl == "hf_gpu":
         return run_hf_gpu(args, cfg, config, dev) if rank == 0 else 0
-    if world > 1:
-        import torch.distributed as dist
+    import torch.distributed as dist
 
-        dist.init_process_group("nccl", device_id=dev)
+    runner.init_distributed("nccl", device=dev)  # no-op for one rank
 
     from livecc_b200.engine import LiveCCB200ForConditionalGeneration
     from livecc_b200.streaming import LiveCCDemoInfer
@@ -523,10 +522,7 @@ def main():
     infer = LiveCCDemoInfer(model=eng, processor=StubProcessor(cfg, emit_frames=True))  # uint8 frames, GPU ingest
     infer._last_hw = (args.size, args.size)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    barrier = runner.barrier  # dist.barrier() when initialised, then torch.cuda.synchronize()
 
     # ---- device-resident arm ----
     for _ in range(args.warmup):

@@ -55,10 +55,17 @@ def test_vit_forward_matches_restatement(small):
         out = eng.get_video_features(px, inp.video_grid_thw)
         ref = rs.vit_forward(px, inp.video_grid_thw)
         torch.cuda.synchronize()
-        err = (out.float() - ref.float()).abs()
-        scale = ref.float().abs().mean().item()
-        assert err.max().item() < 0.15 * max(scale, 1.0), (err.max().item(), scale)
-        assert err.mean().item() < 0.01 * max(scale, 1.0), (err.mean().item(), scale)
+        # per-element error in bf16 ulps of max(|ref|, row rms): a wrong head, a mis-rotated block or a swapped patch order
+        # moves whole rows by O(1) of their norm, far outside this histogram
+        o, r = out.float(), ref.float()
+        rms = r.pow(2).mean(dim=1, keepdim=True).sqrt()
+        ulps = (o - r).abs() / (2.0 ** -8 * torch.maximum(r.abs(), rms))
+        cos = torch.nn.functional.cosine_similarity(o, r, dim=1)
+        stats = dict(p50=ulps.median().item(), p99=ulps.flatten().kthvalue(int(0.99 * ulps.numel())).values.item(),
+                     max=ulps.max().item(), min_cos=cos.min().item())
+        # measured on B200 (gpurun call 29): p50 0.51, p99 2.2-2.4, max 4.1-5.1 ulps, min cosine 0.99999
+        assert stats["min_cos"] > 0.9999, stats
+        assert stats["p50"] < 0.8 and stats["p99"] < 4.0 and stats["max"] < 12.0, stats
 
 
 def _run_stream(cfg, eng, oracle_generate, turns, max_new, hw=(112, 112)):
