@@ -119,11 +119,14 @@ class SyntheticVideoReader:
             self._BASE_CACHE[key] = base
         return base
 
-    def _frame(self, i: int) -> np.ndarray:
+    def _crop(self, i: int):
         base = self._base()
         dy = (int(i) * 7) % 64
         dx = (int(i) * 13) % 64
-        return base[dy:dy + self.h, dx:dx + self.w].numpy().copy()
+        return base[dy:dy + self.h, dx:dx + self.w]
+
+    def _frame(self, i: int) -> np.ndarray:
+        return self._crop(i).numpy().copy()
 
     def next(self):
         f = self._frame(self._cursor)
@@ -131,8 +134,10 @@ class SyntheticVideoReader:
         return f
 
     def get_batch(self, idxs):
-        return _Batch(np.stack([self._frame(i) for i in idxs], axis=0) if len(idxs) else
-                      np.zeros((0, self.h, self.w, 3), np.uint8))
+        out = np.empty((len(idxs), self.h, self.w, 3), np.uint8)  # one copy per frame, straight into the batch
+        for k, i in enumerate(idxs):
+            out[k] = self._crop(i).numpy()
+        return _Batch(out)
 
 
 class Cv2VideoReader:

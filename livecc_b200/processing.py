@@ -216,15 +216,21 @@ class StubProcessor:
                     grids.append(g)
                 data["pixel_values_videos"] = torch.cat(flats, dim=0)
                 data["video_grid_thw"] = torch.cat(grids, dim=0)
-            # processing_qwen2_vl.py:111-119: one <|video_pad|> per merged token
-            idx = 0
+            # processing_qwen2_vl.py:111-119: one <|video_pad|> per merged token. The reference expands the placeholder in the
+            # TEXT and tokenizes the result; splicing n pad ids between the tokenized pieces gives the same ids (the pad is a
+            # special token: the tokenizer splits on it before anything else) without a regex pass over ~3 KB of pads per chunk.
             merge_len = self.merge_size ** 2
-            while self.video_token in text:
+            pieces = text.split(self.video_token)
+            if len(pieces) - 1 > len(data["video_grid_thw"]):
+                raise ValueError("more <|video_pad|> placeholders in the text than videos")
+            id_list = self.tokenizer.encode(pieces[0])
+            for idx, piece in enumerate(pieces[1:]):
                 n = int(data["video_grid_thw"][idx].prod().item()) // merge_len
-                text = text.replace(self.video_token, "<|placeholder|>" * n, 1)
-                idx += 1
-            text = text.replace("<|placeholder|>", self.video_token)
-        ids = torch.tensor([self.tokenizer.encode(text)], dtype=torch.int64)
+                id_list.extend([self.video_token_id] * n)
+                id_list.extend(self.tokenizer.encode(piece))
+            ids = torch.tensor([id_list], dtype=torch.int64)
+        else:
+            ids = torch.tensor([self.tokenizer.encode(text)], dtype=torch.int64)
         data["input_ids"] = ids
         if return_attention_mask:
             data["attention_mask"] = torch.ones_like(ids)
