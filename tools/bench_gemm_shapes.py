@@ -68,7 +68,7 @@ def run(name, iters=20, copies=8, block_n=0):
 if __name__ == "__main__":
     case = os.environ.get("CASE")
     if case:
-        run(case, iters=2, copies=2)
+        run(case, iters=2, copies=2, block_n=int(os.environ.get('BN', '0')))
     elif os.environ.get("SWEEP_BN"):
         for n in SHAPES:
             for bn in [int(x) for x in os.environ.get('BNS', '0,128,256,-128,-160,-192,-224,-256').split(',')]:
