@@ -260,6 +260,10 @@ static SmemAttrOnce g_resize_smem;
 
 ResizePlan* resize_plan_create(int h, int w, int H, int W, int th_override) {
     if (h <= 0 || w <= 0 || H <= 0 || W <= 0 || w > (1 << 15) || h > (1 << 15) || W > (1 << 14) || H > (1 << 14)) return nullptr;
+    // Output width 1 together with a height change: the reference's dependency (ATen) gives a result that is NOT the separable
+    // filter (its [h, 1] intermediate is stride-ambiguous; found by the randomized oracle check). Unreachable from the path
+    // (sizes are multiples of 28): refuse rather than differ silently.
+    if (W == 1 && h != H) return nullptr;
     const int tw_taps = resize_aa_taps(w, W), th_taps = resize_aa_taps(h, H);
     std::vector<int32_t> xw(W), nw(W), xh(H), nh(H);
     std::vector<float> ww((size_t)tw_taps * W), wh((size_t)th_taps * H);

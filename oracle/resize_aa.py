@@ -20,6 +20,9 @@ live torchvision and tests/golden/resize_aa_golden.json holds the wheel's output
   * the tap accumulation `t = s0*w0; for j in 1..n-1: t += s_j*w_j` runs its first 4*floor((n-1)/4) iterations as
     separate multiply and add (a 4-wide unrolled body whose products come from a vector multiply) and the remaining
     (n-1) mod 4 iterations as fused multiply-adds (the scalar epilogue).
+Domain: every size except "output width 1 with a height change" (there torchvision's result is not the separable filter: ATen's
+[h, 1] intermediate is stride-ambiguous; the native plan refuses that case, tests/test_resize_cpu.py documents it). The hot path only
+produces multiples of 28.
 Parity status: pinned against torchvision 0.26.0 + torch 2.11.0 (CPU capability AVX512) on every size in the tests; a
 differently compiled ATen may order these roundings differently (the uint8 results then differ on ~1e-4 of the pixels
 by one level — the same spread as between two builds of the reference's own dependency).

@@ -76,6 +76,27 @@ def test_cabi_host_table_matches_oracle(in_size, out_size):
         assert not w[len(ws):, k].any()
 
 
+def test_oracle_matches_torchvision_on_random_sizes():
+    """60 seeded random (h, w) -> (H, W) pairs, 1..260 -> 1..200 plus a few large sources: bit-exact, except the one degenerate
+    family the oracle header names (output width 1 with a height change), where torchvision's own result is not the separable
+    filter; that family is asserted to differ so that a change in the dependency is noticed."""
+    if torch.backends.cpu.get_cpu_capability() != GOLDEN["cpu_capability"] or torch.__version__ != GOLDEN["torch"]:
+        pytest.skip("rounding order pinned on a different ATen build")
+    rng = np.random.default_rng(7)
+    for it in range(60):
+        h, w = int(rng.integers(1, 260)), int(rng.integers(1, 260))
+        H, W = int(rng.integers(1, 200)), int(rng.integers(1, 200))
+        if it % 10 == 0:
+            h, w = int(rng.integers(300, 900)), int(rng.integers(300, 900))
+        if W == 1 and H != h:
+            W = 2
+        clip = torch.randint(0, 256, (1, 2, h, w), generator=torch.Generator().manual_seed(it), dtype=torch.uint8)
+        assert np.array_equal(resize_aa.resize_bicubic_aa_u8(clip.numpy(), (H, W)), torchvision_resize(clip, (H, W)).numpy()), (h, w, H, W)
+    clip = torch.randint(0, 256, (1, 1, 60, 20), generator=torch.Generator().manual_seed(1), dtype=torch.uint8)
+    assert not np.array_equal(resize_aa.resize_bicubic_aa_u8(clip.numpy(), (30, 1)), torchvision_resize(clip, (30, 1)).numpy())
+    assert np.array_equal(resize_aa.resize_bicubic_aa_u8(clip.numpy(), (60, 1)), torchvision_resize(clip, (60, 1)).numpy())  # width only
+
+
 REF_SOURCES = "/root/reference/demo/sources"
 
 

@@ -117,3 +117,6 @@ def test_plan_rejects_windows_larger_than_shared_memory(ctx):
 
     with pytest.raises(_cabi.LiveCCNativeError):
         ctx.resize_plan(30000, 30000, 28, 28)
+    with pytest.raises(_cabi.LiveCCNativeError):  # output width 1 with a height change: outside the oracle's domain
+        ctx.resize_plan(60, 20, 30, 1)
+    ctx.resize_plan(60, 20, 60, 1)  # width only: fine
