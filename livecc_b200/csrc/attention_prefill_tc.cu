@@ -23,6 +23,8 @@
 namespace lcc {
 namespace ptc {
 constexpr int D = 128, BM = 128, BN = 64, STAGES = 4;
+// P operand through TMEM instead of shared memory (see attention_tc.cu). LIVECC_B200_ATTN_PTMEM=0/1 overrides.
+constexpr int kPtmemDefault = 1;
 constexpr int Q_ATOM_BYTES = BM * 128;       // [128 rows][64 bf16]
 constexpr int Q_BYTES = 2 * Q_ATOM_BYTES;
 constexpr int KV_ATOM_BYTES = BN * 128;      // [64 tokens][64 bf16]
@@ -372,8 +374,8 @@ int attn_prefill_tc(const bf16* q, int q_ld, const bf16* kc, const bf16* vc, con
     if (make_tmap_bf16_2d_box(&tv, vc, pool_rows, D, D, 64, BN, false)) return -11;
     static int ptmem = -1;
     if (ptmem < 0) {
-        const char* pe = getenv("LIVECC_B200_ATTN_PTMEM");
-        ptmem = (pe && pe[0] == '1') ? 1 : 0;
+        const char* pe = getenv("LIVECC_B200_ATTN_PTMEM");  // "1" / "0" force the variant; unset = kPtmemDefault
+        ptmem = pe ? (pe[0] == '1' ? 1 : 0) : kPtmemDefault;
     }
     static SmemAttrOnce once_a, once_b;
     if (ensure_dyn_smem(once_a, attn_prefill_tc_kernel<false>, SMEM_BYTES) ||

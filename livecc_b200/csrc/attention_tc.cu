@@ -29,6 +29,9 @@ constexpr int DSLABS = D / SLAB_COLS;  // 5
 constexpr int Q_SLAB_BYTES = BM * 32;
 constexpr int Q_BYTES = DSLABS * Q_SLAB_BYTES;
 constexpr float RESCALE_THRESHOLD = 8.f;  // log2 units: P stays <= 2^8 between rescales
+// P operand of the P.V MMA read from TMEM (tcgen05.st) instead of shared memory. Bit-identical results, 7-11 % faster on B200
+// (profiles/r02_vit_attn_ptmem.md). LIVECC_B200_ATTN_PTMEM=0/1 overrides.
+constexpr int kPtmemDefault = 1;
 // BN = keys per tile. BN=128: one CTA per SM (512 TMEM columns); BN=64: two CTAs per SM (256 columns, <= 113 KB smem)
 // PTMEM: P goes to TMEM (tcgen05.st) and P.V reads its A operand from TMEM instead of staging P in shared memory
 // (experimental, LIVECC_B200_ATTN_PTMEM=1: written without GPU time at the end of round 1, not validated yet).
@@ -376,8 +379,8 @@ int vit_attention_tc(const bf16* qkv, int ld, int64_t n_rows, bf16* out, int o_l
     const int variant = e ? atoi(e) : ((int)(grid.x * grid.y * grid.z) <= dev_sms ? 128 : 64);
     static int ptmem = -1;
     if (ptmem < 0) {
-        const char* pe = getenv("LIVECC_B200_ATTN_PTMEM");
-        ptmem = (pe && pe[0] == '1') ? 1 : 0;
+        const char* pe = getenv("LIVECC_B200_ATTN_PTMEM");  // "1" / "0" force the variant; unset = kPtmemDefault
+        ptmem = pe ? (pe[0] == '1' ? 1 : 0) : kPtmemDefault;
     }
     if (ptmem) {
         if (variant == 128) return launch_tc<Cfg<128, 3, true>>(qkv, ld, n_rows, p, grid, s);

@@ -45,6 +45,8 @@ def run(S, past, iters=10):
 
 
 if __name__ == "__main__":
-    for past in (0, 1000, 3000, 9000, 17000, 70000):
+    pasts = os.environ.get("PASTS")  # e.g. PASTS=9000,17000 for a short run (LIVECC_B200_ATTN_PTMEM=0/1 picks the tc variant)
+    for past in ([int(x) for x in pasts.split(",")] if pasts else (0, 1000, 3000, 9000, 17000, 70000)):
         run(281, past)
-    run(2084, 0, iters=5)
+    if not pasts:
+        run(2084, 0, iters=5)
