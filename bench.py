@@ -224,6 +224,18 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def recorded_pool_peak():
+    """The driver-measured HBM figure BASELINE.md §2 quotes from MEASURED_PEAKS.json (GB/s), or None. Only used to annotate
+    the roofline blocks when MEASURED_PEAKS.json itself is absent from the snapshot (the fractions then use the fallback)."""
+    import re
+
+    try:
+        m = re.search(r"HBM copy bandwidth\s*\|\s*([0-9.]+)\s*GB/s", open(os.path.join(ROOT, "BASELINE.md")).read())
+        return float(m.group(1)) if m else None
+    except OSError:
+        return None
+
+
 def time_gateup_kernel(eng, iters=5):
     """decode gate/up GEMV (gemv_rows_kernel<2,true,SWIGLU>): fused RMSNorm + [2I,H] weight stream + SwiGLU.
     Algorithmic bytes/launch = 2I*H*2 (weights) + H*2 (x) + H*2 (norm w) + I*2 (out). Cycles through all layers
@@ -648,6 +660,13 @@ def main():
                              "bound": "hbm", "bytes_per_step_mean": int(bytes_avg), "ms_per_step": ms_per_dstep,
                              "achieved": bytes_avg / (ms_per_dstep / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
                              "frac": bytes_avg / (ms_per_dstep / 1e3) / 1e9 / peak, "decode_steps": dsteps}
+    if peak_src.startswith("fallback"):
+        rec = recorded_pool_peak()
+        if rec:
+            note = (f"MEASURED_PEAKS.json absent: fractions use the {peak:.0f} GB/s fallback; against the driver-measured "
+                    f"{rec} GB/s recorded in BASELINE.md they are ")
+            line["roofline"]["peak_note"] = note + f"{line['roofline']['achieved'] / rec:.4f}"
+            line["roofline_step"]["peak_note"] = note + f"{line['roofline_step']['achieved'] / rec:.4f}"
     if not args.no_batch and world == 1:
         # multi-stream batching on one GPU: aggregate tokens/s of B concurrent streams over the same clip
         ms = {}
