@@ -27,6 +27,7 @@ class PagePool:
         self.k = self.v = None
         self.free: List[int] = []
         self.generation = 0  # bumped whenever the pool storage moves (invalidates captured graphs)
+        self._free_buffers: List["StreamBuffers"] = []
         self._grow(initial_pages)
 
     def _grow(self, new_total: int):
@@ -57,11 +58,10 @@ class PagePool:
     # Per-stream device buffers (page table, scalars, id buffer) are recycled through the pool so that their
     # addresses — which are baked into captured decode graphs — stay stable from one stream to the next.
     def acquire_buffers(self) -> "StreamBuffers":
-        free = self.__dict__.setdefault("_free_buffers", [])
-        return free.pop() if free else StreamBuffers(self.device)
+        return self._free_buffers.pop() if self._free_buffers else StreamBuffers(self.device)
 
     def release_buffers(self, b: "StreamBuffers"):
-        self.__dict__.setdefault("_free_buffers", []).append(b)
+        self._free_buffers.append(b)
 
     def bytes_per_token(self) -> int:
         return 2 * self.layers * self.kv_heads * 128 * 2
